@@ -1,0 +1,455 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// (accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue with fused element-wise tails.
+//
+// Replaces, on the MicroDiT training path, every nn.Linear / einsum contraction the reference sends
+// to cuBLAS: qkv/proj (reference micro_diffusion/models/utils.py:172-173), cross-attention q/kv/proj
+// (utils.py:109-111), SwiGLU w1/w2/w3 (dit.py:84-89), the expert einsums (dit.py:135-137), the
+// adaLN / stem / mixer-map / final linears, and all their dgrad / wgrad counterparts.
+//
+// Two operand layouts (template kMN):
+//   kMN=false  "NT":  C[M,N] = sum_k A[M,k] * B[N,k]     A,B row-major with k contiguous (K-major)
+//   kMN=true   "TN":  C[P,Q] = sum_r A[r,P] * B[r,Q]     A,B row-major with the reduction index r
+//                     strided (MN-major UMMA operands) -- the weight-gradient contraction.
+// Roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps4-7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31).
+#include "gemm_tcgen05.cuh"
+
+#include <stdio.h>
+
+#include "ptx.cuh"
+
+namespace md {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
+  static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int kAccStages = 2;
+  static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 256 or 512 (power of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BLOCK_N, bool kMN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmDev p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + Cfg::kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + Cfg::kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < Cfg::kAccStages; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Tile enumeration: n fastest so that CTAs resident together share the same A rows through L2.
+  const int m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = (p.K + kBlockK - 1) / kBlockK;
+  const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
+  const long long tiles = 1LL * p.batch * p.splits * m_blocks * n_blocks;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        long long t = tile;
+        const int nb = t % n_blocks; t /= n_blocks;
+        const int mb = t % m_blocks; t /= m_blocks;
+        const int sp = t % p.splits; t /= p.splits;
+        const int bz = static_cast<int>(t);
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kStageBytesA;
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          if constexpr (!kMN) {
+            tma_load_3d(&tmA, &full_bar[s], sa, kb * kBlockK, mb * kBlockM, bz);
+            tma_load_3d(&tmB, &full_bar[s], sb, kb * kBlockK, nb * BLOCK_N, bz);
+          } else {
+            // boxes of 64 (MN, contiguous) x 64 (reduction rows); one box per 64 MN elements
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j)
+              tma_load_3d(&tmA, &full_bar[s], sa + j * (kBlockK * 128), mb * kBlockM + j * 64,
+                          kb * kBlockK, bz);
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(&tmB, &full_bar[s], sb + j * (kBlockK * 128), nb * BLOCK_N + j * 64,
+                          kb * kBlockK, bz);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, kMN, kMN);
+      // K-major: 8-row groups 1024 B apart (SBO), LBO unused (1).  MN-major: 64-element MN groups one
+      // whole box apart (LBO = 64 rows * 128 B), 8-row reduction groups 1024 B apart (SBO).
+      constexpr uint32_t lbo = kMN ? (kBlockK * 128) : 16;
+      constexpr uint32_t sbo = 1024;
+      constexpr uint32_t kstep = kMN ? (kUmmaK * 128) : (kUmmaK * 2);  // bytes per UMMA_K advance
+      uint32_t it = 0;
+      uint32_t acc_it = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++acc_it) {
+        long long t = tile / (1LL * n_blocks * m_blocks);
+        const int sp = t % p.splits;
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        const int as = acc_it % Cfg::kAccStages;
+        const uint32_t aph = (acc_it / Cfg::kAccStages) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kStageBytesA;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * kstep, lbo, sbo);
+            const uint64_t db = umma_smem_desc(sb + k * kstep, lbo, sbo);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int q = warp & 3;  // TMEM lane quarter
+    uint32_t acc_it = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++acc_it) {
+      long long t = tile;
+      const int nb = t % n_blocks; t /= n_blocks;
+      const int mb = t % m_blocks; t /= m_blocks;
+      const int sp = t % p.splits; t /= p.splits;
+      const int bz = static_cast<int>(t);
+      const int kb0 = sp * kb_per_split;
+      const bool has_k = kb0 < kb_total;  // empty split (possible when splits does not divide)
+      const int as = acc_it % Cfg::kAccStages;
+      const uint32_t aph = (acc_it / Cfg::kAccStages) & 1;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+
+      const int row = mb * kBlockM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const long long crow = 1LL * bz * p.strideC + 1LL * row * p.ldc;
+      const float* gate_row = nullptr;
+      if (p.gate != nullptr && row_ok)
+        gate_row = p.gate + 1LL * (row / p.rows_per_gate) * p.ldgate;
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = nb * BLOCK_N + c * 32;
+        // No divergent `continue`: every lane must reach the next (warp-aligned) tcgen05.ld together.
+        if (row_ok && col0 < p.N && has_k) do {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        const int ncols = min(32, p.N - col0);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
+        }
+        if (p.epi == EPI_ATOMIC_F32) {
+          float* dst = reinterpret_cast<float*>(p.C) + crow + col0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                           "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
+          } else {
+            for (int j = 0; j < ncols; ++j) atomicAdd(dst + j, v[j]);
+          }
+          break;
+        }
+        if (p.epi == EPI_GELU_DUAL) {
+          // C = pre-activation (bf16), C2 = gelu_erf(pre) (bf16); activation taken on the bf16-rounded
+          // pre-activation so that backward (which re-reads C) differentiates the same function.
+          __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
+          __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(d1) & 15) == 0) &&
+              ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 a, g;
+              uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+              uint32_t* gp = reinterpret_cast<uint32_t*>(&g);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = __bfloat162float(__float2bfloat16_rn(v[j + 2 * e]));
+                const float x1 = __bfloat162float(__float2bfloat16_rn(v[j + 2 * e + 1]));
+                ap[e] = pack_bf16(x0, x1);
+                gp[e] = pack_bf16(gelu_erf(x0), gelu_erf(x1));
+              }
+              *reinterpret_cast<uint4*>(d1 + j) = a;
+              *reinterpret_cast<uint4*>(d2 + j) = g;
+            }
+          } else {
+            for (int j = 0; j < ncols; ++j) {
+              const float x0 = __bfloat162float(__float2bfloat16_rn(v[j]));
+              d1[j] = __float2bfloat16_rn(x0);
+              d2[j] = __float2bfloat16_rn(gelu_erf(x0));
+            }
+          }
+          break;
+        }
+        if (p.epi == EPI_RESID_F32) {
+          // optional bf16 copy of the raw GEMM result (needed by backward for d(gate))
+          if (p.C2 != nullptr) {
+            __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 a;
+                uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ap[e] = pack_bf16(v[j + 2 * e], v[j + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(d2 + j) = a;
+              }
+            } else {
+              for (int j = 0; j < ncols; ++j) d2[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+          if (gate_row != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] *= gate_row[col0 + j];
+          }
+          const float* res = p.res + crow + col0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rr = *reinterpret_cast<const float4*>(res + j);
+              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+            }
+          } else {
+            for (int j = 0; j < ncols; ++j) v[j] += res[j];
+          }
+        }
+        if (p.epi == EPI_STORE_BF16) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 a;
+              uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ap[e] = pack_bf16(v[j + 2 * e], v[j + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(dst + j) = a;
+            }
+          } else {
+            for (int j = 0; j < ncols; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+          }
+        } else {  // EPI_STORE_F32 / EPI_RESID_F32
+          float* dst = reinterpret_cast<float*>(p.C) + crow + col0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < ncols; ++j) dst[j] = v[j];
+          }
+        }
+        } while (0);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor viewed as [batch][rows][cols] (cols contiguous), box = [1][box_rows][64], 128B swizzle.
+static int make_map(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long batch,
+                    long long ld, long long batch_stride, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0 || (batch > 1 && (batch_stride % 8) != 0))
+    return md_set_error(MD_ERR_INVALID, "gemm operand must be 16-byte aligned with ld %% 8 == 0");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2,
+                           static_cast<cuuint64_t>(batch > 1 ? batch_stride : rows * ld) * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) cols=%lld rows=%lld ld=%lld", (int)r, cols,
+             rows, ld);
+    return md_set_error(MD_ERR_CUDA, msg);
+  }
+  return 0;
+}
+
+template <int BLOCK_N, bool kMN>
+static int launch(const md_gemm_args* a, const GemmDev& dev, int sm_count, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!kMN) {
+    rc = make_map(&tmA, a->A, a->K, a->M, a->batch, a->lda, a->strideA, kBlockM);
+    if (rc) return rc;
+    rc = make_map(&tmB, a->B, a->K, a->N, a->batch, a->ldb, a->strideB, BLOCK_N);
+    if (rc) return rc;
+  } else {
+    rc = make_map(&tmA, a->A, a->M, a->K, a->batch, a->lda, a->strideA, kBlockK);
+    if (rc) return rc;
+    rc = make_map(&tmB, a->B, a->N, a->K, a->batch, a->ldb, a->strideB, kBlockK);
+    if (rc) return rc;
+  }
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, kMN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long m_blocks = (a->M + kBlockM - 1) / kBlockM;
+  const long long n_blocks = (a->N + BLOCK_N - 1) / BLOCK_N;
+  const long long tiles = a->batch * dev.splits * m_blocks * n_blocks;
+  const int grid = static_cast<int>(tiles < sm_count ? tiles : sm_count);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace md
+
+extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
+  using namespace md;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (a == nullptr || a->A == nullptr || a->B == nullptr || a->C == nullptr)
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: null operand");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || a->batch <= 0) return 0;  // empty problem: nothing to do
+  if (a->epilogue < 0 || a->epilogue >= EPI_COUNT) return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: bad epilogue");
+  if (a->epilogue == EPI_RESID_F32 && a->res == nullptr)
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: residual epilogue needs res");
+  if (a->epilogue == EPI_GELU_DUAL && a->C2 == nullptr)
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: gelu epilogue needs C2");
+  if (a->gate != nullptr && a->rows_per_gate <= 0)
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: gate needs rows_per_gate > 0");
+  int splits = a->splits > 0 ? a->splits : 1;
+  if (splits > 1 && a->epilogue != EPI_ATOMIC_F32)
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: split-K needs the atomic epilogue");
+
+  int dev_id = 0, sm_count = 0;
+  cudaError_t e = cudaGetDevice(&dev_id);
+  if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
+  static int cached_sm[64] = {0};
+  if (dev_id < 64 && cached_sm[dev_id] > 0) sm_count = cached_sm[dev_id];
+  else {
+    int major = 0;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev_id);
+    if (major != 10) return md_set_error(MD_ERR_UNSUPPORTED, "md_gemm_bf16: requires an sm_100a device (B200)");
+    if (dev_id < 64) cached_sm[dev_id] = sm_count;
+  }
+
+  GemmDev dev;
+  dev.C = a->C; dev.C2 = a->C2;
+  dev.bias = reinterpret_cast<const float*>(a->bias);
+  dev.res = reinterpret_cast<const float*>(a->res);
+  dev.gate = reinterpret_cast<const float*>(a->gate);
+  dev.M = static_cast<int>(a->M); dev.N = static_cast<int>(a->N); dev.K = static_cast<int>(a->K);
+  dev.batch = static_cast<int>(a->batch); dev.splits = splits;
+  dev.ldc = a->ldc; dev.strideC = a->strideC; dev.strideBias = a->strideBias;
+  dev.ldgate = a->ldgate; dev.rows_per_gate = static_cast<int>(a->rows_per_gate > 0 ? a->rows_per_gate : 1);
+  dev.epi = a->epilogue;
+  dev.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
+
+  const bool mn = a->layout == MD_GEMM_TN;
+  // Tile-N choice: 256 when it divides well and there are enough tiles to fill the machine.
+  const long long m_blocks = (a->M + kBlockM - 1) / kBlockM;
+  const long long tiles256 = a->batch * splits * m_blocks * ((a->N + 255) / 256);
+  const bool use256 = (a->N % 256 == 0 || a->N > 1024) && tiles256 >= 2LL * sm_count;
+  if (mn) return use256 ? launch<256, true>(a, dev, sm_count, stream) : launch<128, true>(a, dev, sm_count, stream);
+  return use256 ? launch<256, false>(a, dev, sm_count, stream) : launch<128, false>(a, dev, sm_count, stream);
+}

@@ -1,0 +1,24 @@
+#pragma once
+#include "common.cuh"
+
+namespace md {
+enum {
+  EPI_STORE_BF16 = MD_EPI_STORE_BF16,
+  EPI_STORE_F32 = MD_EPI_STORE_F32,
+  EPI_RESID_F32 = MD_EPI_RESID_F32,
+  EPI_ATOMIC_F32 = MD_EPI_ATOMIC_F32,
+  EPI_GELU_DUAL = MD_EPI_GELU_DUAL,
+  EPI_COUNT
+};
+// Kernel-side argument block (everything the device needs besides the two tensor maps).
+struct GemmDev {
+  void* C;
+  void* C2;
+  const float* bias;
+  const float* res;
+  const float* gate;
+  long long ldc, strideC, strideBias, ldgate;
+  int M, N, K, batch, splits, rows_per_gate, epi;
+  float alpha;
+};
+}  // namespace md
