@@ -9,6 +9,11 @@
  * The reference (SonyResearch/micro_diffusion) has no FFI: its hot path is Python calling torch ops.
  * Each function below names the reference code it replaces (file:line under the reference root).
  * The Python binding a maintainer would add is the ctypes stub in INTEGRATION.md.
+ *
+ * Conventions: "rows" are tokens (sample-major: row = sample * T + token); bf16 = __nv_bfloat16;
+ * per-sample modulation vectors (shift / scale / gate) are passed as a pointer to sample 0 plus a row
+ * pitch `ldmod` in elements (they are column slices of one [samples, sum(6*D)] adaLN buffer);
+ * `T` = rows per sample.
  */
 #ifndef MICRODIT_B200_H_
 #define MICRODIT_B200_H_
@@ -34,16 +39,14 @@ MD_API const char* md_last_error(void);
 MD_API int md_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------ GEMM */
-/* layouts */
 #define MD_GEMM_NT 0 /* C[M,N] = A[M,K] . B[N,K]^T   (A, B row-major, K contiguous)                 */
 #define MD_GEMM_TN 1 /* C[M,N] = A[K,M]^T . B[K,N]   (A, B row-major, reduction index K strided)    */
-/* epilogues */
 #define MD_EPI_STORE_BF16 0 /* C(bf16) = alpha*acc (+bias)                                           */
 #define MD_EPI_STORE_F32 1  /* C(f32)  = alpha*acc (+bias)                                           */
-#define MD_EPI_RESID_F32 2  /* C(f32)  = res + gate[row/rows_per_gate] * (alpha*acc+bias);           */
+#define MD_EPI_RESID_F32 2  /* C(f32)  = res[row % res_mod] + gate[row/rows_per_gate]*(alpha*acc+bias) */
                             /*           C2(bf16, optional) = alpha*acc+bias                         */
 #define MD_EPI_ATOMIC_F32 3 /* C(f32) += alpha*acc   (red.global.add; the only mode allowing splits) */
-#define MD_EPI_GELU_DUAL 4  /* C(bf16) = pre = alpha*acc+bias ; C2(bf16) = gelu_erf(pre)             */
+#define MD_EPI_ACT_DUAL 4   /* C(bf16) = pre = alpha*acc+bias ; C2(bf16) = act(pre); act: 0 gelu-erf, 1 gelu-tanh */
 
 typedef struct md_gemm_args {
   const void* A; /* bf16 */
@@ -51,24 +54,170 @@ typedef struct md_gemm_args {
   void* C;
   void* C2;
   const void* bias; /* f32 [batch][N] or NULL */
-  const void* res;  /* f32, same indexing as C (may alias C) */
+  const void* res;  /* f32, indexed like C (may alias C); row taken modulo res_mod when res_mod > 0 */
   const void* gate; /* f32 [M / rows_per_gate][ldgate] or NULL (=1) */
   int64_t M, N, K;
   int64_t lda, ldb, ldc; /* row pitches in elements */
   int64_t batch;         /* >= 1; batch strides in elements */
   int64_t strideA, strideB, strideC, strideBias;
   int64_t ldgate, rows_per_gate;
+  int64_t res_mod;  /* 0: res row == C row */
   int32_t layout;   /* MD_GEMM_* */
   int32_t epilogue; /* MD_EPI_*  */
   int32_t splits;   /* split of the reduction dimension (>=1) */
+  int32_t act;      /* activation of MD_EPI_ACT_DUAL */
   float alpha;      /* 0 is treated as 1 */
 } md_gemm_args;
 
-/* Dense / batched bf16 GEMM with fp32 accumulation on tcgen05 tensor cores.
- * Replaces: nn.Linear under autocast -- qkv/proj utils.py:172-173, cross-attn q/kv/proj utils.py:109-111,
- * SwiGLU dit.py:84-89, adaLN dit.py:227-230, stem/mixer maps dit.py:377-388, final linear utils.py:226-230 --
- * the expert einsums dit.py:135-137 (batch = experts), and the autograd dgrad/wgrad of all of them. */
+/* Dense / batched bf16 GEMM, fp32 accumulation, tcgen05 tensor cores fed by TMA.
+ * Replaces nn.Linear under autocast -- qkv/proj utils.py:172-173, cross-attn q/kv/proj utils.py:109-111,
+ * SwiGLU dit.py:84-89, adaLN dit.py:227-230, stem/mixer maps dit.py:377-388, final linear utils.py:226-230,
+ * patch-embed conv dit.py:312-314 (as a K=C*p*p GEMM) -- the expert einsums dit.py:135-137 (batch =
+ * experts) and the autograd dgrad/wgrad of all of them. */
 MD_API int md_gemm_bf16(const md_gemm_args* args, void* stream);
+
+/* --------------------------------------------------------------------------- LayerNorm (+modulate) */
+/* y = LN(x; gamma, eps) * (1 + scale[sample]) + shift[sample]   (create_norm utils.py:71-78 +
+ * modulate utils.py:28-30; call sites dit.py:236-238, utils.py:238).  x: f32 (x_bf16=0) or bf16 (1),
+ * [rows, D]; src_rows (optional, int32 [rows]) gathers input rows (mask_out_token utils.py:406-414 fused
+ * into the patch_mixer_map_xout norm, dit.py:504-508).  gamma / shift / scale may be NULL.  y bf16 [rows,D];
+ * mean, rstd f32 [rows].  D % 8 == 0, D <= 2048. */
+MD_API int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const float* gamma,
+                     const float* shift, const float* scale, int64_t ldmod, int64_t T, void* y, float* mean,
+                     float* rstd, int64_t rows, int64_t D, float eps, void* stream);
+/* Backward of the above.  dy bf16 [rows, D].  dx_mode: 0 = dx(f32)[r] += , 1 = dx(bf16)[r] = ,
+ * 2 = dx(f32)[src_rows[r]] += (scatter).  dgamma f32 [D] += (atomic); dshift / dscale f32 [samples, D]
+ * pitched by ldmod, += (atomic; caller zeroes them once per step).  NULL outputs are skipped. */
+MD_API int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_t* src_rows, const float* gamma,
+                     const float* scale, int64_t ldmod, int64_t T, const float* mean, const float* rstd,
+                     void* dx, int dx_mode, float* dgamma, float* dshift, float* dscale, int64_t rows,
+                     int64_t D, void* stream);
+/* Non-affine LayerNorm over a W-wide column slice, in place on bf16 (QK-norm: ln_q / ln_k utils.py:183-186,
+ * 122-125).  fwd: x <- (x-mean)*rstd, rstd out.  bwd: dy <- rstd*(dy - mean(dy) - xhat*mean(dy*xhat)). */
+MD_API int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, float eps, void* stream);
+MD_API int md_rownorm_bwd(void* dy, int64_t ld_dy, const void* xhat, int64_t ld_x, const float* rstd, int64_t rows,
+                          int64_t W, void* stream);
+/* Backward of x_new = x + gate[sample] * y (dit.py:236,238): dy(bf16) = gate * dres;
+ * dgate[sample] += sum_t dres * y (atomic).  y / gate / dgate may be NULL (plain f32->bf16 cast). */
+MD_API int md_gate_bwd(const float* dres, const void* y, const float* gate, int64_t ldmod, int64_t T, void* dy,
+                       float* dgate, int64_t rows, int64_t D, void* stream);
+
+/* ------------------------------------------------------------------------------------- attention */
+/* softmax(Q K^T / sqrt(hd)) V, non-causal (F.scaled_dot_product_attention at utils.py:188-193 self,
+ * 127-132 cross).  q [B*Tq, *] pitch ldq, k / v [B*Tk, *] pitch ldk / ldv, head h at column h*hd;
+ * o bf16 [B*Tq, H*hd] pitch ldo; lse f32 [B,H,Tq] (log2 domain).  hd in {32, 64}. */
+MD_API int md_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                       int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
+                       void* stream);
+/* delta scratch f32 [B,H,Tq]; dq/dk/dv bf16 with the pitches of q/k/v. */
+MD_API int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                       const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
+                       void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
+                       int64_t Tq, int64_t Tk, int64_t hd, void* stream);
+
+/* ------------------------------------------------------------------------------ feed-forward tails */
+/* SwiGLU (dit.py:88-89): u bf16 [rows, 2f] = [w1 x | w2 x];  h = silu(u[:, :f]) * u[:, f:]. */
+MD_API int md_swiglu_fwd(const void* u, void* h, int64_t rows, int64_t f, void* stream);
+MD_API int md_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int64_t f, void* stream);
+/* dpre = dact * act'(pre), bf16 (act: 0 gelu-erf dit.py:136, 1 gelu-tanh utils.py:65). */
+MD_API int md_act_bwd(const void* dact, const void* pre, void* dpre, int64_t n, int act, void* stream);
+/* c_act(bf16) = gelu_tanh(c f32)  (the nn.GELU in every adaLN_modulation, dit.py:227-230);
+ * bwd: dc(f32) (+)= dc_act(f32) * gelu_tanh'(c). */
+MD_API int md_gelu_tanh_f32_fwd(const float* c, void* out_bf16, int64_t n, void* stream);
+MD_API int md_gelu_tanh_f32_bwd(const float* dact, const float* c, float* dc, int accumulate, int64_t n, void* stream);
+
+/* -------------------------------------------------------------------------- expert-choice MoE */
+/* FeedForwardECMoe (dit.py:126-143).  E <= 16, D % 8 == 0. */
+/* probs(f32 [rows,E]) = softmax(x(bf16 [rows,D]) . Wg(f32 [E,D])^T)   (dit.py:130-131) */
+MD_API int md_moe_gate_fwd(const void* x, const float* wg, float* probs, int64_t rows, int64_t D, int64_t E,
+                           void* stream);
+/* per (sample, expert) top-k over the T tokens (dit.py:132): idx int32 [B,E,k], gval f32 [B,E,k],
+ * inv int32 [B,T,E] = slot of token t in expert e's list or -1.  T <= 4096. */
+MD_API int md_moe_topk(const float* probs, int32_t* idx, float* gval, int32_t* inv, int64_t B, int64_t T, int64_t E,
+                       int64_t k, void* stream);
+/* dispatch (the one-hot einsum dit.py:134 as a gather): xin bf16 [E, B*k, D] */
+MD_API int md_moe_gather(const void* x, const int32_t* idx, void* xin, int64_t B, int64_t T, int64_t E, int64_t k,
+                         int64_t D, void* stream);
+/* combine (dit.py:139-140) fused with the gated residual (dit.py:238):
+ * ymoe(bf16 [rows,D]) = sum_e g*h2 ; xout(f32) = xres + gate[sample]*ymoe */
+MD_API int md_moe_combine_fwd(const void* h2, const float* gval, const int32_t* inv, const float* xres,
+                              const float* gate, int64_t ldmod, float* xout, void* ymoe, int64_t B, int64_t T,
+                              int64_t E, int64_t k, int64_t D, void* stream);
+/* dh2(bf16 [E,B*k,D]) = g * dy[token] ; dgval(f32 [B,E,k]) = <h2, dy[token]> */
+MD_API int md_moe_combine_bwd(const void* dy, const void* h2, const float* gval, const int32_t* idx, void* dh2,
+                              float* dgval, int64_t B, int64_t T, int64_t E, int64_t k, int64_t D, void* stream);
+/* softmax/top-k backward + un-dispatch: dscores f32 [rows,E]; dx(bf16 [rows,D]) = sum_e dxin[slot] + dscores.Wg */
+MD_API int md_moe_dx_bwd(const void* dxin, const int32_t* inv, const float* dgval, const float* probs,
+                         const float* wg, float* dscores, void* dx, int64_t B, int64_t T, int64_t E, int64_t k,
+                         int64_t D, void* stream);
+/* dWg(f32 [E,D]) += dscores^T . x  (atomic) */
+MD_API int md_moe_gate_wgrad(const float* dscores, const void* x, float* dwg, int64_t rows, int64_t D, int64_t E,
+                             void* stream);
+
+/* ------------------------------------------------------------------------- masking (utils.py:382-426) */
+/* get_mask with the uniform noise given: ascending argsort per sample (ties by index).
+ * ids_shuffle, ids_restore int32 [B,T]; mask f32 [B,T] (0 keep, 1 drop); keep_rows int32 [B*keep] = global
+ * row (b*T + token) of every kept token in shuffle order.  T <= 4096. */
+MD_API int md_mask_sort(const float* noise, int32_t* ids_shuffle, int32_t* ids_restore, float* mask,
+                        int32_t* keep_rows, int64_t B, int64_t T, int64_t keep, void* stream);
+/* f32 row gather / scatter-add (mask_out_token when the mixer maps are Identity, dit.py:386-388,504) */
+MD_API int md_gather_rows_f32(const float* x, const int32_t* src_rows, float* y, int64_t rows, int64_t D, void* stream);
+MD_API int md_scatter_rows_f32(const float* dy, const int32_t* src_rows, float* dx, int64_t rows, int64_t D,
+                               void* stream);
+
+/* ---------------------------------------------------------- EDM noise / preconditioning / loss */
+/* conditioning *= drop_caption_mask; .float() (model.py:132-139): cap fp16 [B, L*Dc] -> bf16.  keep f64 or NULL;
+ * cap_out_f16 (optional, may alias cap_f16) receives the masked fp16 captions (the reference's in-place `*=`). */
+MD_API int md_cond_prepare(const void* cap_f16, const double* keep, void* out_bf16, void* cap_out_f16, int64_t B,
+                           int64_t per_sample, void* stream);
+/* model.py:182-188,153-166 + the im2col of the patch-embed conv (dit.py:479):
+ * sigma = exp(rnd*P_std+P_mean); xn = x + sigma*eps; patches(bf16 [B*T, Kp]) = c_in * xn, column
+ * (c*p+i)*p+j, Kp = C*p*p; coef f32 [6,B] = sigma, c_skip, c_out, c_in, c_noise, weight.
+ * lat: fp16 (lat_f16=1) or f32.  sigma_in (optional) overrides the draw (sampler path). */
+MD_API int md_edm_prepare(const void* lat, int lat_f16, const float* eps, const float* rnd, const float* sigma_in,
+                          float p_mean, float p_std, float sigma_data, float* xn, void* patches, float* coef,
+                          int64_t B, int64_t C, int64_t H, int64_t W, int64_t p, void* stream);
+/* im2col of the patch-embed conv for the plain DiT.forward entry (dit.py:479,552): patches(bf16 [B*T, C*p*p]) =
+ * scale[b] * x, scale f32 [B] or NULL. */
+MD_API int md_patchify(const float* x, const float* scale, void* patches, int64_t B, int64_t C, int64_t H, int64_t W,
+                       int64_t p, void* stream);
+/* TimestepEmbedder.timestep_embedding (utils.py:265-281): out bf16 [B, dim] = [cos | sin](t * freqs) */
+MD_API int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, void* stream);
+/* weighted masked MSE (model.py:199-210) straight from the final-layer tokens ftok f32 [B*Tk, p*p*C]
+ * (column (i*p+j)*C+c, unpatchify dit.py:566-575); keep_tok int32 [B,Tk] = global rows (b*T + token) of the kept
+ * tokens (md_mask_sort's keep_rows) or NULL (all tokens).
+ * per_sample f32 [B]; loss f32 [1] += mean (caller zeroes). */
+MD_API int md_edm_loss_fwd(const float* ftok, const int32_t* keep_tok, const void* lat, int lat_f16, const float* xn,
+                           const float* coef, float* per_sample, float* loss, int64_t B, int64_t C, int64_t H,
+                           int64_t W, int64_t p, int64_t Tk, void* stream);
+/* d loss / d ftok * gscale[0] (f32 device scalar: the incoming grad_output) -> bf16 [B*Tk, p*p*C] */
+MD_API int md_edm_loss_bwd(const float* ftok, const int32_t* keep_tok, const void* lat, int lat_f16, const float* xn,
+                           const float* coef, const float* gscale, void* dftok, int64_t B, int64_t C, int64_t H,
+                           int64_t W, int64_t p, int64_t Tk, void* stream);
+/* unmask_tokens + unpatchify (utils.py:417-426, dit.py:566-575) + D = c_skip*xn + c_out*F (model.py:173-178).
+ * ids_restore int32 [B,T] or NULL; mask_token f32 [p*p*C]; fx (raw network output) and dx (denoised), f32
+ * [B,C,H,W]; either may be NULL. */
+MD_API int md_edm_output(const float* ftok, const int32_t* ids_restore, const float* mask_token, const float* xn,
+                         const float* coef, float* fx, float* dx, int64_t B, int64_t C, int64_t H, int64_t W,
+                         int64_t p, int64_t Tk, void* stream);
+
+/* ------------------------------------------------------------------------------------ utilities */
+/* mean over the L tokens of each sample (dit.py:484): x f32 [B,L,D] -> bf16 [B,D]; bwd: dx[b,l,:] += d[b,:]/L */
+MD_API int md_mean_tokens_fwd(const float* x, void* out, int64_t B, int64_t L, int64_t D, void* stream);
+MD_API int md_mean_tokens_bwd(const float* d, float* dx, int64_t B, int64_t L, int64_t D, void* stream);
+MD_API int md_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+/* out(f32 [N]) += column sums of x [rows, N] (bf16 if x_bf16 else f32), pitch ld (bias gradients) */
+MD_API int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int64_t rows, int64_t N, void* stream);
+/* W f32 [batch, rows, cols] -> wb bf16 same layout (optional) and wbt bf16 [batch, cols, rows] (optional):
+ * the per-step bf16 operand copies of the fp32 master weights (what autocast does per call in the reference). */
+MD_API int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch, int64_t rows, int64_t cols,
+                             void* stream);
+/* sumsq(f32 [1]) += sum x^2  (gradient-norm clipping, train.py:85-86) */
+MD_API int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream);
+/* fused (clip-scaled) AdamW on flat fp32 buffers (train.py:39, configs/res_256_pretrain.yaml:50-57):
+ * g *= min(1, clip / (sqrt(sumsq[0]) + 1e-6)) if sumsq != NULL; decoupled weight decay; bias correction by step. */
+MD_API int md_adamw(float* p, const float* g, float* m, float* v, const float* sumsq, float clip, float lr,
+                    float beta1, float beta2, float eps, float wd, int64_t step, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

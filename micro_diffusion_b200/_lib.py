@@ -24,8 +24,9 @@ class GemmArgs(C.Structure):
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
         ("batch", C.c_int64),
         ("strideA", C.c_int64), ("strideB", C.c_int64), ("strideC", C.c_int64), ("strideBias", C.c_int64),
-        ("ldgate", C.c_int64), ("rows_per_gate", C.c_int64),
-        ("layout", C.c_int32), ("epilogue", C.c_int32), ("splits", C.c_int32), ("alpha", C.c_float),
+        ("ldgate", C.c_int64), ("rows_per_gate", C.c_int64), ("res_mod", C.c_int64),
+        ("layout", C.c_int32), ("epilogue", C.c_int32), ("splits", C.c_int32), ("act", C.c_int32),
+        ("alpha", C.c_float),
     ]
 
 

@@ -1,0 +1,449 @@
+// Non-causal multi-head attention forward / backward for short sequences (T in {64, 77, 256, 1024}),
+// head_dim 32 or 64: F.scaled_dot_product_attention at utils.py:188-193 (self) and utils.py:127-132
+// (cross, 77 caption tokens) and its autograd backward.
+//
+// Round-1 implementation: flash-style tiles of 64 queries x 64 keys per CTA (4 warps x 16 rows),
+// bf16 mma.sync m16n8k16 with fp32 accumulation and online softmax in the log2 domain; backward is
+// the deterministic two-kernel split (dK/dV per key tile, dQ per query tile; no atomics).
+// SDPA is 2.7 % of the step's FLOPs at the benchmark configuration, so the
+// tcgen05 rewrite of this kernel ranks after the GEMM work; DESIGN.md tracks it.
+#include "common.cuh"
+
+namespace md {
+
+constexpr int kTile = 64;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int HD>
+struct Smem {
+  static constexpr int kPitch = HD + 8;  // bf16 elements; 16-byte row skew -> conflict-free ldmatrix
+};
+
+// Load rows [row0, row0+64) x HD columns (starting at column col0) of a [*, ld] bf16 matrix; rows >= nrows -> 0.
+template <int HD>
+__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, long long ld, long long row0,
+                                          long long nrows, int col0) {
+  constexpr int kChunks = HD / 8;
+  for (int i = threadIdx.x; i < kTile * kChunks; i += blockDim.x) {
+    const int r = i / kChunks, c = (i % kChunks) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row0 + r < nrows) v = *reinterpret_cast<const uint4*>(g + (row0 + r) * ld + col0 + c);
+    *reinterpret_cast<uint4*>(s + r * Smem<HD>::kPitch + c) = v;
+  }
+}
+
+// A fragments of a 16 x HD row block starting at smem row r0.
+template <int HD>
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[HD / 16][4], const __nv_bfloat16* s, int r0, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks)
+    ldsm_x4(a[ks], s + (r0 + (lane & 15)) * Smem<HD>::kPitch + ks * 16 + (lane >> 4) * 8);
+}
+
+// acc[nt] (16 x 64, nt = 8 tiles of 8 columns) = A(16 x HD) . M^T where M is a 64 x HD smem tile ([n][k]).
+template <int HD>
+__device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&a)[HD / 16][4], const __nv_bfloat16* m,
+                                         int lane) {
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      uint32_t b[4];
+      const int mi = lane >> 3;
+      ldsm_x4(b, m + (np * 16 + (lane & 7) + (mi >> 1) * 8) * Smem<HD>::kPitch + ks * 16 + (mi & 1) * 8);
+      mma16816(acc[2 * np], a[ks], b[0], b[1]);
+      mma16816(acc[2 * np + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+
+// out[dt] (16 x HD) += P(16 x 64, given as 4 k-steps of A fragments) . M where M is a 64 x HD smem tile ([k][n]).
+template <int HD>
+__device__ __forceinline__ void mma_p_m(float (&out)[HD / 8][4], const uint32_t (&pa)[4][4], const __nv_bfloat16* m,
+                                        int lane) {
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+    for (int dp = 0; dp < HD / 16; ++dp) {
+      uint32_t b[4];
+      const int mi = lane >> 3;
+      ldsm_x4_t(b, m + (kt * 16 + (lane & 7) + (mi & 1) * 8) * Smem<HD>::kPitch + dp * 16 + (mi >> 1) * 8);
+      mma16816(out[2 * dp], pa[kt], b[0], b[1]);
+      mma16816(out[2 * dp + 1], pa[kt], b[2], b[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void acc_to_afrag(uint32_t (&pa)[4][4], const float (&s)[8][4]) {
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    pa[kt][0] = pack2(s[2 * kt][0], s[2 * kt][1]);
+    pa[kt][1] = pack2(s[2 * kt][2], s[2 * kt][3]);
+    pa[kt][2] = pack2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+    pa[kt][3] = pack2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ k, long long ldk,
+                const __nv_bfloat16* __restrict__ v, long long ldv, __nv_bfloat16* __restrict__ o, long long ldo,
+                float* __restrict__ lse, int H, int Tq, int Tk, float scale_log2) {
+  constexpr int P = Smem<HD>::kPitch;
+  __shared__ __align__(16) __nv_bfloat16 sq[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sk[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sv[kTile * P];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int q0 = blockIdx.x * kTile;
+
+  load_tile<HD>(sq, q + b * Tq * ldq, ldq, q0, Tq, h * HD);
+  __syncthreads();
+  uint32_t qa[HD / 16][4];
+  load_a_frags<HD>(qa, sq, warp * 16, lane);
+
+  float oacc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+
+  for (int k0 = 0; k0 < Tk; k0 += kTile) {
+    __syncthreads();
+    load_tile<HD>(sk, k + b * Tk * ldk, ldk, k0, Tk, h * HD);
+    load_tile<HD>(sv, v + b * Tk * ldv, ldv, k0, Tk, h * HD);
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    mma_a_bt<HD>(s, qa, sk, lane);
+    float mx[2] = {mrow[0], mrow[1]};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = k0 + nt * 8 + 2 * t + (j & 1);
+        s[nt][j] = key < Tk ? s[nt][j] * scale_log2 : -INFINITY;
+        mx[j >> 1] = fmaxf(mx[j >> 1], s[nt][j]);
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float corr[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) corr[r] = exp2f(mrow[r] - mx[r]);  // first tile: exp2(-inf) = 0
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[nt][j] = exp2f(s[nt][j] - mx[j >> 1]);
+        rs[j >> 1] += s[nt][j];
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      lrow[r] = lrow[r] * corr[r] + rs[r];
+      mrow[r] = mx[r];
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      oacc[i][0] *= corr[0]; oacc[i][1] *= corr[0];
+      oacc[i][2] *= corr[1]; oacc[i][3] *= corr[1];
+    }
+    uint32_t pa[4][4];
+    acc_to_afrag(pa, s);
+    mma_p_m<HD>(oacc, pa, sv, lane);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + g + r * 8;
+    if (row < Tq) {
+      const float inv = 1.f / lrow[r];
+      __nv_bfloat16* dst = o + (b * Tq + row) * ldo + h * HD;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i)
+        *reinterpret_cast<uint32_t*>(dst + i * 8 + 2 * t) = pack2(oacc[i][2 * r] * inv, oacc[i][2 * r + 1] * inv);
+      if (t == 0) lse[(b * H + h) * Tq + row] = mrow[r] + log2f(lrow[r]);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------- delta
+// delta[b,h,q] = sum_d dO * O; one warp per (row, head).
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ o,
+                  long long ldo, float* __restrict__ delta, long long B, int H, int Tq, int HD) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = B * Tq * H;
+  for (long long w = 1LL * blockIdx.x * 8 + warp; w < total; w += 1LL * gridDim.x * 8) {
+    const int h = static_cast<int>(w % H);
+    const long long row = w / H;  // b*Tq + q
+    float s = 0.f;
+    for (int d = lane * 2; d < HD; d += 64) {
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(dout + row * lddo + h * HD + d);
+      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(o + row * ldo + h * HD + d);
+      s += __low2float(a) * __low2float(c) + __high2float(a) * __high2float(c);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      const long long b = row / Tq;
+      const int qq = static_cast<int>(row % Tq);
+      delta[(b * H + h) * Tq + qq] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- dK / dV kernel
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ q,
+                     long long ldq, const __nv_bfloat16* __restrict__ k, long long ldk,
+                     const __nv_bfloat16* __restrict__ v, long long ldv, const float* __restrict__ lse,
+                     const float* __restrict__ delta, __nv_bfloat16* __restrict__ dk, long long lddk,
+                     __nv_bfloat16* __restrict__ dv, long long lddv, int H, int Tq, int Tk, float scale,
+                     float scale_log2) {
+  constexpr int P = Smem<HD>::kPitch;
+  __shared__ __align__(16) __nv_bfloat16 sk[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sv[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sq[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sdo[kTile * P];
+  __shared__ float slse[kTile], sdelta[kTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int k0 = blockIdx.x * kTile;
+
+  load_tile<HD>(sk, k + b * Tk * ldk, ldk, k0, Tk, h * HD);
+  load_tile<HD>(sv, v + b * Tk * ldv, ldv, k0, Tk, h * HD);
+  __syncthreads();
+  uint32_t ka[HD / 16][4], va[HD / 16][4];
+  load_a_frags<HD>(ka, sk, warp * 16, lane);
+  load_a_frags<HD>(va, sv, warp * 16, lane);
+
+  float dkacc[HD / 8][4], dvacc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dkacc[i][j] = dvacc[i][j] = 0.f;
+
+  for (int q0 = 0; q0 < Tq; q0 += kTile) {
+    __syncthreads();
+    load_tile<HD>(sq, q + b * Tq * ldq, ldq, q0, Tq, h * HD);
+    load_tile<HD>(sdo, dout + b * Tq * lddo, lddo, q0, Tq, h * HD);
+    if (threadIdx.x < kTile) {
+      const int qq = q0 + threadIdx.x;
+      slse[threadIdx.x] = qq < Tq ? lse[(b * H + h) * Tq + qq] : INFINITY;  // +inf -> P = 0
+      sdelta[threadIdx.x] = qq < Tq ? delta[(b * H + h) * Tq + qq] : 0.f;
+    }
+    __syncthreads();
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st[i][j] = dpt[i][j] = 0.f;
+    mma_a_bt<HD>(st, ka, sq, lane);    // S^T  = K . Q^T     (16 keys x 64 queries)
+    mma_a_bt<HD>(dpt, va, sdo, lane);  // dP^T = V . dO^T
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int qc = nt * 8 + 2 * t + (j & 1);
+        const float p = exp2f(st[nt][j] * scale_log2 - slse[qc]);
+        st[nt][j] = p;
+        dpt[nt][j] = p * (dpt[nt][j] - sdelta[qc]);
+      }
+    uint32_t pa[4][4];
+    acc_to_afrag(pa, st);
+    mma_p_m<HD>(dvacc, pa, sdo, lane);  // dV += P^T . dO
+    acc_to_afrag(pa, dpt);
+    mma_p_m<HD>(dkacc, pa, sq, lane);   // dK += dS^T . Q
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = k0 + warp * 16 + g + r * 8;
+    if (key < Tk) {
+      __nv_bfloat16* pk = dk + (b * Tk + key) * lddk + h * HD;
+      __nv_bfloat16* pv = dv + (b * Tk + key) * lddv + h * HD;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        *reinterpret_cast<uint32_t*>(pk + i * 8 + 2 * t) = pack2(dkacc[i][2 * r] * scale, dkacc[i][2 * r + 1] * scale);
+        *reinterpret_cast<uint32_t*>(pv + i * 8 + 2 * t) = pack2(dvacc[i][2 * r], dvacc[i][2 * r + 1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ dQ kernel
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ q,
+                   long long ldq, const __nv_bfloat16* __restrict__ k, long long ldk,
+                   const __nv_bfloat16* __restrict__ v, long long ldv, const float* __restrict__ lse,
+                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dq, long long lddq, int H, int Tq,
+                   int Tk, float scale, float scale_log2) {
+  constexpr int P = Smem<HD>::kPitch;
+  __shared__ __align__(16) __nv_bfloat16 sq[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sdo[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sk[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sv[kTile * P];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int q0 = blockIdx.x * kTile;
+
+  load_tile<HD>(sq, q + b * Tq * ldq, ldq, q0, Tq, h * HD);
+  load_tile<HD>(sdo, dout + b * Tq * lddo, lddo, q0, Tq, h * HD);
+  __syncthreads();
+  uint32_t qa[HD / 16][4], doa[HD / 16][4];
+  load_a_frags<HD>(qa, sq, warp * 16, lane);
+  load_a_frags<HD>(doa, sdo, warp * 16, lane);
+  float lrow[2], drow[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + g + r * 8;
+    lrow[r] = row < Tq ? lse[(b * H + h) * Tq + row] : INFINITY;
+    drow[r] = row < Tq ? delta[(b * H + h) * Tq + row] : 0.f;
+  }
+  float dqacc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dqacc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Tk; k0 += kTile) {
+    __syncthreads();
+    load_tile<HD>(sk, k + b * Tk * ldk, ldk, k0, Tk, h * HD);
+    load_tile<HD>(sv, v + b * Tk * ldv, ldv, k0, Tk, h * HD);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.f;
+    mma_a_bt<HD>(s, qa, sk, lane);    // S  = Q . K^T
+    mma_a_bt<HD>(dp, doa, sv, lane);  // dP = dO . V^T
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = k0 + nt * 8 + 2 * t + (j & 1);
+        const float p = key < Tk ? exp2f(s[nt][j] * scale_log2 - lrow[j >> 1]) : 0.f;
+        s[nt][j] = p * (dp[nt][j] - drow[j >> 1]);
+      }
+    uint32_t pa[4][4];
+    acc_to_afrag(pa, s);
+    mma_p_m<HD>(dqacc, pa, sk, lane);  // dQ += dS . K
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + g + r * 8;
+    if (row < Tq) {
+      __nv_bfloat16* dst = dq + (b * Tq + row) * lddq + h * HD;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i)
+        *reinterpret_cast<uint32_t*>(dst + i * 8 + 2 * t) = pack2(dqacc[i][2 * r] * scale, dqacc[i][2 * r + 1] * scale);
+    }
+  }
+}
+
+static int check_attn(const char* what, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd, int64_t ld_min) {
+  if (hd != 32 && hd != 64) return md_set_error(MD_ERR_UNSUPPORTED, "attention: head_dim must be 32 or 64");
+  if (B < 0 || H <= 0 || Tq <= 0 || Tk <= 0 || H > 65535 || B > 65535)
+    return md_set_error(MD_ERR_INVALID, what);
+  if (ld_min % 8 != 0) return md_set_error(MD_ERR_INVALID, "attention: row pitches must be multiples of 8 elements");
+  return 0;
+}
+
+}  // namespace md
+
+using namespace md;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int md_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                           int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
+                           void* stream) {
+  if (int rc = check_attn("md_attn_fwd: bad sizes", B, H, Tq, Tk, hd, (ldq | ldk | ldv | ldo))) return rc;
+  if (B == 0) return 0;
+  if (!q || !k || !v || !o || !lse) return md_set_error(MD_ERR_INVALID, "md_attn_fwd: null pointer");
+  const float sl2 = 1.4426950408889634f / sqrtf((float)hd);
+  dim3 grid((unsigned)((Tq + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
+  if (hd == 64)
+    attn_fwd_kernel<64><<<grid, 128, 0, ST(stream)>>>(CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, BF(o), ldo, lse, (int)H,
+                                                      (int)Tq, (int)Tk, sl2);
+  else
+    attn_fwd_kernel<32><<<grid, 128, 0, ST(stream)>>>(CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, BF(o), ldo, lse, (int)H,
+                                                      (int)Tq, (int)Tk, sl2);
+  return check_launch("md_attn_fwd");
+}
+
+extern "C" int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                           const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
+                           void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
+                           int64_t Tq, int64_t Tk, int64_t hd, void* stream) {
+  if (int rc = check_attn("md_attn_bwd: bad sizes", B, H, Tq, Tk, hd, (lddo | ldq | ldk | ldv | ldo | lddq | lddk | lddv)))
+    return rc;
+  if (B == 0) return 0;
+  if (!dout || !q || !k || !v || !o || !lse || !delta || !dq || !dk || !dv)
+    return md_set_error(MD_ERR_INVALID, "md_attn_bwd: null pointer");
+  const float scale = 1.f / sqrtf((float)hd);
+  const float sl2 = 1.4426950408889634f * scale;
+  long long warps = B * Tq * H;
+  long long blocks = (warps + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  attn_delta_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(o), ldo, delta, B, (int)H, (int)Tq,
+                                                              (int)hd);
+  dim3 gkv((unsigned)((Tk + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
+  dim3 gq((unsigned)((Tq + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
+  if (hd == 64) {
+    attn_bwd_dkdv_kernel<64><<<gkv, 128, 0, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, lse,
+                                                          delta, BF(dk), lddk, BF(dv), lddv, (int)H, (int)Tq, (int)Tk,
+                                                          scale, sl2);
+    attn_bwd_dq_kernel<64><<<gq, 128, 0, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, lse,
+                                                       delta, BF(dq), lddq, (int)H, (int)Tq, (int)Tk, scale, sl2);
+  } else {
+    attn_bwd_dkdv_kernel<32><<<gkv, 128, 0, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, lse,
+                                                          delta, BF(dk), lddk, BF(dv), lddv, (int)H, (int)Tq, (int)Tk,
+                                                          scale, sl2);
+    attn_bwd_dq_kernel<32><<<gq, 128, 0, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, lse,
+                                                       delta, BF(dq), lddq, (int)H, (int)Tq, (int)Tk, scale, sl2);
+  }
+  return check_launch("md_attn_bwd");
+}

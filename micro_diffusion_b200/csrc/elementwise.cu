@@ -1,0 +1,383 @@
+// HBM-bound element-wise / reduction tails of the MicroDiT hot path: SwiGLU, activation backward,
+// conditioning GELU, token mean, casts, bias gradients (column sums), per-step bf16 weight copies,
+// timestep sinusoid, caption-drop cast, gradient sum-of-squares and fused AdamW.
+// 16-byte vector accesses, grids sized as multiples of the SM count with grid-stride loops.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace md {
+
+static int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = 148LL * 16;  // 16 resident 256-thread CTAs worth of waves per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __low2float(h[e]);
+    f[2 * e + 1] = __high2float(h[e]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return r;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------ SwiGLU
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, long long rows,
+                                  int f) {
+  const int fv = f >> 3;
+  const long long total = rows * fv;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const long long r = i / fv;
+    const int c = static_cast<int>(i % fv) * 8;
+    float a[8], b[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(u + r * 2 * f + c), a);
+    unpack8(*reinterpret_cast<const uint4*>(u + r * 2 * f + f + c), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = silu_f(a[e]) * b[e];
+    *reinterpret_cast<uint4*>(h + r * f + c) = pack8(o);
+  }
+}
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ u,
+                                  __nv_bfloat16* __restrict__ du, long long rows, int f) {
+  const int fv = f >> 3;
+  const long long total = rows * fv;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const long long r = i / fv;
+    const int c = static_cast<int>(i % fv) * 8;
+    float a[8], b[8], d[8], da[8], db[8];
+    unpack8(*reinterpret_cast<const uint4*>(u + r * 2 * f + c), a);
+    unpack8(*reinterpret_cast<const uint4*>(u + r * 2 * f + f + c), b);
+    unpack8(*reinterpret_cast<const uint4*>(dh + r * f + c), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sg = 1.f / (1.f + __expf(-a[e]));
+      const float sl = a[e] * sg;
+      da[e] = d[e] * b[e] * (sg * (1.f + a[e] * (1.f - sg)));
+      db[e] = d[e] * sl;
+    }
+    *reinterpret_cast<uint4*>(du + r * 2 * f + c) = pack8(da);
+    *reinterpret_cast<uint4*>(du + r * 2 * f + f + c) = pack8(db);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- act bwd
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const __nv_bfloat16* __restrict__ pre,
+                               __nv_bfloat16* __restrict__ dpre, long long nvec, int act) {
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 1LL * gridDim.x * blockDim.x) {
+    float d[8], x[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dact + 8 * i), d);
+    unpack8(*reinterpret_cast<const uint4*>(pre + 8 * i), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = d[e] * (act ? gelu_tanh_grad_f(x[e]) : gelu_erf_grad_f(x[e]));
+    *reinterpret_cast<uint4*>(dpre + 8 * i) = pack8(o);
+  }
+}
+__global__ void gelu_tanh_f32_fwd_kernel(const float* __restrict__ c, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(gelu_tanh_f(c[i]));
+}
+__global__ void gelu_tanh_f32_bwd_kernel(const float* __restrict__ dact, const float* __restrict__ c,
+                                         float* __restrict__ dc, int accumulate, long long n) {
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) {
+    const float v = dact[i] * gelu_tanh_grad_f(c[i]);
+    dc[i] = accumulate ? dc[i] + v : v;
+  }
+}
+
+// -------------------------------------------------------------------------------------- token mean
+__global__ void mean_tokens_fwd_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int L, int D) {
+  const long long b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float s = 0.f;
+  for (int l = 0; l < L; ++l) s += x[(b * L + l) * D + c];
+  out[b * D + c] = __float2bfloat16_rn(s / L);
+}
+__global__ void mean_tokens_bwd_kernel(const float* __restrict__ d, float* __restrict__ dx, int L, int D) {
+  const long long b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const float v = d[b * D + c] / L;
+  for (int l = 0; l < L; ++l) dx[(b * L + l) * D + c] += v;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long nv = n >> 2;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += 1LL * gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(x + 4 * i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t*>(&a);
+    raw.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(y + 4 * i) = raw;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (nv << 2) + threadIdx.x;
+    y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ colsum
+// grid (ceil(N/256), ceil(rows/256)): each thread owns one column of a 256-row slab.
+__global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, float* __restrict__ out,
+                              long long rows, long long N) {
+  const long long c = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const long long r0 = 1LL * blockIdx.y * 256, r1 = min(rows, r0 + 256);
+  float s = 0.f;
+  if (x_bf16) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(x);
+    for (long long r = r0; r < r1; ++r) s += __bfloat162float(p[r * ld + c]);
+  } else {
+    const float* p = reinterpret_cast<const float*>(x);
+    for (long long r = r0; r < r1; ++r) s += p[r * ld + c];
+  }
+  atomicAdd(out + c, s);
+}
+
+// ---------------------------------------------------------------------------------- cast_transpose
+// 32x32 tiles through padded smem: coalesced fp32 reads, coalesced bf16 writes in both orientations.
+__global__ void cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
+                                      __nv_bfloat16* __restrict__ wbt, long long rows, long long cols) {
+  __shared__ float tile[32][33];
+  const long long bz = blockIdx.z;
+  const float* wsrc = w + bz * rows * cols;
+  const long long c0 = 1LL * blockIdx.x * 32, r0 = 1LL * blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = wsrc[r * cols + c];
+      if (wb) wb[bz * rows * cols + r * cols + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (wbt) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const long long c = c0 + i, r = r0 + threadIdx.x;  // output row = original column
+      if (c < cols && r < rows) wbt[bz * rows * cols + c * rows + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- timestep / cond
+__global__ void timestep_embed_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int dim) {
+  const long long b = blockIdx.x;
+  const int half = dim / 2;
+  const float tv = t[b];
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float freq = expf(-9.210340371976184f * static_cast<float>(i) / static_cast<float>(half));
+    const float a = tv * freq;
+    out[b * dim + i] = __float2bfloat16_rn(cosf(a));
+    out[b * dim + half + i] = __float2bfloat16_rn(sinf(a));
+  }
+  if ((dim & 1) && threadIdx.x == 0) out[b * dim + dim - 1] = __float2bfloat16_rn(0.f);
+}
+
+__global__ void cond_prepare_kernel(const __half* cap, const double* __restrict__ keep,
+                                    __nv_bfloat16* __restrict__ out, __half* cap_out, long long per_sample) {
+  const long long b = blockIdx.y;
+  const float k = keep ? static_cast<float>(keep[b]) : 1.f;
+  const long long nv = per_sample >> 3;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += 1LL * gridDim.x * blockDim.x) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(cap + b * per_sample + 8 * i);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    float o[8];
+    uint4 masked;
+    __half2* mh = reinterpret_cast<__half2*>(&masked);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // the reference multiplies in fp16 (in-place `conditioning *= mask`, model.py:132-135), then .float()
+      const __half2 m = __hmul2(h[e], __float2half2_rn(k));
+      mh[e] = m;
+      const float2 f = __half22float2(m);
+      o[2 * e] = f.x;
+      o[2 * e + 1] = f.y;
+    }
+    *reinterpret_cast<uint4*>(out + b * per_sample + 8 * i) = pack8(o);
+    if (cap_out) *reinterpret_cast<uint4*>(cap_out + b * per_sample + 8 * i) = masked;
+  }
+}
+
+// ----------------------------------------------------------------------------------- sumsq / AdamW
+__global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+  float s = 0.f;
+  const long long nv = n >> 2;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += 1LL * gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(x + 4 * i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = x[(nv << 2) + threadIdx.x];
+    s += v * v;
+  }
+  s = warp_sum(s);
+  __shared__ float part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, const float* __restrict__ sumsq, float clip, float lr, float b1,
+                             float b2, float eps, float wd, float bc1, float bc2, long long n) {
+  float gs = 1.f;
+  if (sumsq != nullptr && clip > 0.f) {
+    const float norm = sqrtf(sumsq[0]);
+    gs = fminf(1.f, clip / (norm + 1e-6f));
+  }
+  const long long nv = n >> 2;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += 1LL * gridDim.x * blockDim.x) {
+    float4 pv = *reinterpret_cast<float4*>(p + 4 * i);
+    const float4 gv = *reinterpret_cast<const float4*>(g + 4 * i);
+    float4 mv = *reinterpret_cast<float4*>(m + 4 * i);
+    float4 vv = *reinterpret_cast<float4*>(v + 4 * i);
+    float* pp = reinterpret_cast<float*>(&pv);
+    const float* gp = reinterpret_cast<const float*>(&gv);
+    float* mp = reinterpret_cast<float*>(&mv);
+    float* vp = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gg = gp[e] * gs;
+      pp[e] *= 1.f - lr * wd;
+      mp[e] = b1 * mp[e] + (1.f - b1) * gg;
+      vp[e] = b2 * vp[e] + (1.f - b2) * gg * gg;
+      const float denom = sqrtf(vp[e]) / sqrtf(bc2) + eps;
+      pp[e] -= (lr / bc1) * mp[e] / denom;
+    }
+    *reinterpret_cast<float4*>(p + 4 * i) = pv;
+    *reinterpret_cast<float4*>(m + 4 * i) = mv;
+    *reinterpret_cast<float4*>(v + 4 * i) = vv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (nv << 2) + threadIdx.x;
+    const float gg = g[i] * gs;
+    float pp = p[i] * (1.f - lr * wd);
+    const float mm = b1 * m[i] + (1.f - b1) * gg;
+    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+    pp -= (lr / bc1) * mm / (sqrtf(vv) / sqrtf(bc2) + eps);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
+}  // namespace md
+
+using namespace md;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int md_swiglu_fwd(const void* u, void* h, int64_t rows, int64_t f, void* stream) {
+  if (rows == 0) return 0;
+  if (!u || !h || f % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_swiglu_fwd: null pointer or f % 8 != 0");
+  swiglu_fwd_kernel<<<grid_for(rows * (f / 8), 256), 256, 0, ST(stream)>>>(CBF(u), BF(h), rows, (int)f);
+  return check_launch("md_swiglu_fwd");
+}
+extern "C" int md_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int64_t f, void* stream) {
+  if (rows == 0) return 0;
+  if (!dh || !u || !du || f % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_swiglu_bwd: null pointer or f % 8 != 0");
+  swiglu_bwd_kernel<<<grid_for(rows * (f / 8), 256), 256, 0, ST(stream)>>>(CBF(dh), CBF(u), BF(du), rows, (int)f);
+  return check_launch("md_swiglu_bwd");
+}
+extern "C" int md_act_bwd(const void* dact, const void* pre, void* dpre, int64_t n, int act, void* stream) {
+  if (n == 0) return 0;
+  if (!dact || !pre || !dpre || n % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_act_bwd: null pointer or n % 8 != 0");
+  act_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>(CBF(dact), CBF(pre), BF(dpre), n / 8, act);
+  return check_launch("md_act_bwd");
+}
+extern "C" int md_gelu_tanh_f32_fwd(const float* c, void* out, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  if (!c || !out) return md_set_error(MD_ERR_INVALID, "md_gelu_tanh_f32_fwd: null pointer");
+  gelu_tanh_f32_fwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(c, BF(out), n);
+  return check_launch("md_gelu_tanh_f32_fwd");
+}
+extern "C" int md_gelu_tanh_f32_bwd(const float* dact, const float* c, float* dc, int accumulate, int64_t n,
+                                    void* stream) {
+  if (n == 0) return 0;
+  if (!dact || !c || !dc) return md_set_error(MD_ERR_INVALID, "md_gelu_tanh_f32_bwd: null pointer");
+  gelu_tanh_f32_bwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(dact, c, dc, accumulate, n);
+  return check_launch("md_gelu_tanh_f32_bwd");
+}
+extern "C" int md_mean_tokens_fwd(const float* x, void* out, int64_t B, int64_t L, int64_t D, void* stream) {
+  if (B == 0) return 0;
+  if (!x || !out) return md_set_error(MD_ERR_INVALID, "md_mean_tokens_fwd: null pointer");
+  dim3 grid((unsigned)((D + 127) / 128), (unsigned)B);
+  mean_tokens_fwd_kernel<<<grid, 128, 0, ST(stream)>>>(x, BF(out), (int)L, (int)D);
+  return check_launch("md_mean_tokens_fwd");
+}
+extern "C" int md_mean_tokens_bwd(const float* d, float* dx, int64_t B, int64_t L, int64_t D, void* stream) {
+  if (B == 0) return 0;
+  if (!d || !dx) return md_set_error(MD_ERR_INVALID, "md_mean_tokens_bwd: null pointer");
+  dim3 grid((unsigned)((D + 127) / 128), (unsigned)B);
+  mean_tokens_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(d, dx, (int)L, (int)D);
+  return check_launch("md_mean_tokens_bwd");
+}
+extern "C" int md_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  if (!x || !y) return md_set_error(MD_ERR_INVALID, "md_cast_f32_bf16: null pointer");
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(x, BF(y), n);
+  return check_launch("md_cast_f32_bf16");
+}
+extern "C" int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int64_t rows, int64_t N, void* stream) {
+  if (rows == 0 || N == 0) return 0;
+  if (!x || !out) return md_set_error(MD_ERR_INVALID, "md_colsum: null pointer");
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)((rows + 255) / 256));
+  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(x, x_bf16, ld, out, rows, N);
+  return check_launch("md_colsum");
+}
+extern "C" int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch, int64_t rows, int64_t cols,
+                                 void* stream) {
+  if (batch * rows * cols == 0) return 0;
+  if (!w) return md_set_error(MD_ERR_INVALID, "md_cast_transpose: null pointer");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch);
+  cast_transpose_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(w, BF(wb), BF(wbt), rows, cols);
+  return check_launch("md_cast_transpose");
+}
+extern "C" int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, void* stream) {
+  if (B == 0) return 0;
+  if (!t || !out) return md_set_error(MD_ERR_INVALID, "md_timestep_embed: null pointer");
+  timestep_embed_kernel<<<(unsigned)B, 128, 0, ST(stream)>>>(t, BF(out), (int)dim);
+  return check_launch("md_timestep_embed");
+}
+extern "C" int md_cond_prepare(const void* cap_f16, const double* keep, void* out_bf16, void* cap_out_f16, int64_t B,
+                               int64_t per_sample, void* stream) {
+  if (B == 0) return 0;
+  if (!cap_f16 || !out_bf16 || per_sample % 8 != 0)
+    return md_set_error(MD_ERR_INVALID, "md_cond_prepare: null pointer or per_sample % 8 != 0");
+  dim3 grid((unsigned)min((long long)((per_sample / 8 + 255) / 256), 64LL), (unsigned)B);
+  cond_prepare_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(cap_f16), keep, BF(out_bf16),
+                                                    reinterpret_cast<__half*>(cap_out_f16), per_sample);
+  return check_launch("md_cond_prepare");
+}
+extern "C" int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  if (!x || !sumsq) return md_set_error(MD_ERR_INVALID, "md_sumsq: null pointer");
+  sumsq_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(x, sumsq, n);
+  return check_launch("md_sumsq");
+}
+extern "C" int md_adamw(float* p, const float* g, float* m, float* v, const float* sumsq, float clip, float lr,
+                        float beta1, float beta2, float eps, float wd, int64_t step, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  if (!p || !g || !m || !v || step < 1) return md_set_error(MD_ERR_INVALID, "md_adamw: null pointer or step < 1");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adamw_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(p, g, m, v, sumsq, clip, lr, beta1, beta2, eps, wd,
+                                                                 bc1, bc2, n);
+  return check_launch("md_adamw");
+}

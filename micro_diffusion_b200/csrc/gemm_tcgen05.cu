@@ -36,10 +36,6 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -185,6 +181,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = mb * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const long long crow = 1LL * bz * p.strideC + 1LL * row * p.ldc;
+      const long long rrow = 1LL * bz * p.strideC + 1LL * (p.res_mod > 0 ? row % p.res_mod : row) * p.ldc;
       const float* gate_row = nullptr;
       if (p.gate != nullptr && row_ok)
         gate_row = p.gate + 1LL * (row / p.rows_per_gate) * p.ldgate;
@@ -219,7 +216,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           break;
         }
-        if (p.epi == EPI_GELU_DUAL) {
+        if (p.epi == EPI_ACT_DUAL) {
           // C = pre-activation (bf16), C2 = gelu_erf(pre) (bf16); activation taken on the bf16-rounded
           // pre-activation so that backward (which re-reads C) differentiates the same function.
           __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
@@ -236,7 +233,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const float x0 = __bfloat162float(__float2bfloat16_rn(v[j + 2 * e]));
                 const float x1 = __bfloat162float(__float2bfloat16_rn(v[j + 2 * e + 1]));
                 ap[e] = pack_bf16(x0, x1);
-                gp[e] = pack_bf16(gelu_erf(x0), gelu_erf(x1));
+                gp[e] = p.act ? pack_bf16(gelu_tanh_f(x0), gelu_tanh_f(x1)) : pack_bf16(gelu_erf_f(x0), gelu_erf_f(x1));
               }
               *reinterpret_cast<uint4*>(d1 + j) = a;
               *reinterpret_cast<uint4*>(d2 + j) = g;
@@ -245,7 +242,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < ncols; ++j) {
               const float x0 = __bfloat162float(__float2bfloat16_rn(v[j]));
               d1[j] = __float2bfloat16_rn(x0);
-              d2[j] = __float2bfloat16_rn(gelu_erf(x0));
+              d2[j] = __float2bfloat16_rn(p.act ? gelu_tanh_f(x0) : gelu_erf_f(x0));
             }
           }
           break;
@@ -272,7 +269,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; ++j)
               if (j < ncols) v[j] *= gate_row[col0 + j];
           }
-          const float* res = p.res + crow + col0;
+          const float* res = p.res + rrow + col0;
           if (ncols == 32 && ((reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -412,8 +409,8 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   if (a->epilogue < 0 || a->epilogue >= EPI_COUNT) return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: bad epilogue");
   if (a->epilogue == EPI_RESID_F32 && a->res == nullptr)
     return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: residual epilogue needs res");
-  if (a->epilogue == EPI_GELU_DUAL && a->C2 == nullptr)
-    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: gelu epilogue needs C2");
+  if (a->epilogue == EPI_ACT_DUAL && a->C2 == nullptr)
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: activation epilogue needs C2");
   if (a->gate != nullptr && a->rows_per_gate <= 0)
     return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: gate needs rows_per_gate > 0");
   int splits = a->splits > 0 ? a->splits : 1;
@@ -443,6 +440,8 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   dev.ldc = a->ldc; dev.strideC = a->strideC; dev.strideBias = a->strideBias;
   dev.ldgate = a->ldgate; dev.rows_per_gate = static_cast<int>(a->rows_per_gate > 0 ? a->rows_per_gate : 1);
   dev.epi = a->epilogue;
+  dev.res_mod = static_cast<int>(a->res_mod);
+  dev.act = a->act;
   dev.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
 
   const bool mn = a->layout == MD_GEMM_TN;

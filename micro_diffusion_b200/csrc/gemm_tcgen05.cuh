@@ -7,7 +7,7 @@ enum {
   EPI_STORE_F32 = MD_EPI_STORE_F32,
   EPI_RESID_F32 = MD_EPI_RESID_F32,
   EPI_ATOMIC_F32 = MD_EPI_ATOMIC_F32,
-  EPI_GELU_DUAL = MD_EPI_GELU_DUAL,
+  EPI_ACT_DUAL = MD_EPI_ACT_DUAL,
   EPI_COUNT
 };
 // Kernel-side argument block (everything the device needs besides the two tensor maps).
@@ -18,7 +18,7 @@ struct GemmDev {
   const float* res;
   const float* gate;
   long long ldc, strideC, strideBias, ldgate;
-  int M, N, K, batch, splits, rows_per_gate, epi;
+  int M, N, K, batch, splits, rows_per_gate, epi, res_mod, act;
   float alpha;
 };
 }  // namespace md

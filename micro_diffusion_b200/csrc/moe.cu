@@ -1,0 +1,425 @@
+// Expert-choice MoE routing (FeedForwardECMoe.forward, dit.py:126-143) around the grouped expert
+// GEMMs: gate + softmax, per-(sample, expert) top-k over tokens, dispatch gather, weighted combine
+// fused with the gated residual, and the matching backward pieces.  The reference materialises a
+// one-hot (n,e,k,t) tensor and contracts with it (dit.py:133-134,140); here dispatch and combine are
+// index gathers (deterministic: an inverse slot table replaces scatter-add atomics).
+#include "common.cuh"
+
+namespace md {
+
+constexpr int kMaxE = 16;
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __low2float(h[e]);
+    f[2 * e + 1] = __high2float(h[e]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------- gate fwd
+// warp per row; gate weights staged in shared memory (E*D fp32 <= 64 KB).
+__global__ void __launch_bounds__(256)
+moe_gate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wg, float* __restrict__ probs,
+                    long long rows, int D, int E) {
+  extern __shared__ float swg[];  // [E][D]
+  for (int i = threadIdx.x; i < E * D; i += blockDim.x) swg[i] = wg[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  for (long long row = 1LL * blockIdx.x * 8 + warp; row < rows; row += 1LL * gridDim.x * 8) {
+    float acc[kMaxE];
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) acc[e] = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+      float xv[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + row * D + 8 * i), xv);
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e) {
+        if (e < E) {
+          const float* w = swg + e * D + 8 * i;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[e] += xv[q] * w[q];
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) {
+      if (e < E) {
+        acc[e] = warp_sum(acc[e]);
+        mx = fmaxf(mx, acc[e]);
+      }
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) {
+      if (e < E) {
+        acc[e] = expf(acc[e] - mx);
+        den += acc[e];
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e)
+        if (e < E) probs[row * E + e] = acc[e] / den;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------- top-k
+// block per (sample, expert): bitonic sort of (prob, token) descending; ties broken by lower token id.
+__global__ void __launch_bounds__(1024)
+moe_topk_kernel(const float* __restrict__ probs, int32_t* __restrict__ idx, float* __restrict__ gval,
+                int32_t* __restrict__ inv, int T, int E, int k, int n) {
+  extern __shared__ unsigned long long keys[];
+  const int e = blockIdx.x % E;
+  const long long b = blockIdx.x / E;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned long long key = ~0ULL;  // padding sorts last
+    if (i < T) {
+      // probs are in [0,1]: the raw bit pattern is monotone.  Descending by prob == ascending by ~bits.
+      const unsigned int u = ~__float_as_uint(probs[(b * T + i) * E + e]);
+      key = (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned int>(i);
+    }
+    keys[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = keys[lo], c = keys[hi];
+        if ((a > c) == up) {
+          keys[lo] = c;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    const int tok = static_cast<int>(keys[j] & 0xffffffffu);
+    if (j < k) {
+      idx[(b * E + e) * k + j] = tok;
+      gval[(b * E + e) * k + j] = __uint_as_float(~static_cast<unsigned int>(keys[j] >> 32));
+    }
+    inv[(b * T + tok) * E + e] = j < k ? j : -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ gather
+// warp per slot: xin[e][b*k + j][:] = x[b*T + idx[b,e,j]][:]
+__global__ void __launch_bounds__(256)
+moe_gather_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ xin,
+                  int B, int T, int E, int k, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long slots = 1LL * B * E * k;
+  const int nvec = D >> 3;
+  for (long long s = 1LL * blockIdx.x * 8 + warp; s < slots; s += 1LL * gridDim.x * 8) {
+    const int j = static_cast<int>(s % k);
+    const int e = static_cast<int>((s / k) % E);
+    const long long b = s / (1LL * k * E);
+    const int tok = idx[s];  // idx is [B,E,k] == s ordering
+    const __nv_bfloat16* src = x + (b * T + tok) * D;
+    __nv_bfloat16* dst = xin + ((1LL * e * B + b) * k + j) * D;
+    for (int i = lane; i < nvec; i += 32)
+      *reinterpret_cast<uint4*>(dst + 8 * i) = *reinterpret_cast<const uint4*>(src + 8 * i);
+  }
+}
+
+// ------------------------------------------------------------------------------------- combine fwd
+// warp per token: ymoe = sum_e g*h2[slot]; xout = xres + gate*ymoe
+__global__ void __launch_bounds__(256)
+moe_combine_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ gval,
+                       const int32_t* __restrict__ inv, const float* __restrict__ xres, const float* __restrict__ gate,
+                       long long ldmod, float* __restrict__ xout, __nv_bfloat16* __restrict__ ymoe, int B, int T, int E,
+                       int k, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rows = 1LL * B * T;
+  const int nvec = D >> 3;
+  for (long long row = 1LL * blockIdx.x * 8 + warp; row < rows; row += 1LL * gridDim.x * 8) {
+    const long long b = row / T;
+    int slot[kMaxE];
+    float g[kMaxE];
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) {
+      slot[e] = -1;
+      g[e] = 0.f;
+      if (e < E) {
+        slot[e] = inv[row * E + e];
+        if (slot[e] >= 0) g[e] = gval[(b * E + e) * k + slot[e]];
+      }
+    }
+    const float* gt = gate ? gate + b * ldmod : nullptr;
+    for (int i = lane; i < nvec; i += 32) {
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e) {
+        if (e < E && slot[e] >= 0) {
+          float hv[8];
+          unpack8(*reinterpret_cast<const uint4*>(h2 + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i), hv);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] += g[e] * hv[q];
+        }
+      }
+      if (ymoe) *reinterpret_cast<uint4*>(ymoe + row * D + 8 * i) = pack8(acc);
+      if (xout) {
+#pragma unroll
+        for (int q = 0; q < 8; q += 4) {
+          float4 r = *reinterpret_cast<const float4*>(xres + row * D + 8 * i + q);
+          float4 gg = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (gt) gg = *reinterpret_cast<const float4*>(gt + 8 * i + q);
+          r.x += gg.x * acc[q]; r.y += gg.y * acc[q + 1]; r.z += gg.z * acc[q + 2]; r.w += gg.w * acc[q + 3];
+          *reinterpret_cast<float4*>(xout + row * D + 8 * i + q) = r;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- combine bwd
+// warp per slot: dh2 = g * dy[token]; dgval = <h2, dy[token]>
+__global__ void __launch_bounds__(256)
+moe_combine_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h2,
+                       const float* __restrict__ gval, const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ dh2,
+                       float* __restrict__ dgval, int B, int T, int E, int k, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long slots = 1LL * B * E * k;
+  const int nvec = D >> 3;
+  for (long long s = 1LL * blockIdx.x * 8 + warp; s < slots; s += 1LL * gridDim.x * 8) {
+    const int j = static_cast<int>(s % k);
+    const int e = static_cast<int>((s / k) % E);
+    const long long b = s / (1LL * k * E);
+    const int tok = idx[s];
+    const float g = gval[s];
+    const __nv_bfloat16* dyr = dy + (b * T + tok) * D;
+    const long long hrow = ((1LL * e * B + b) * k + j) * D;
+    float dot = 0.f;
+    for (int i = lane; i < nvec; i += 32) {
+      float dv[8], hv[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(dyr + 8 * i), dv);
+      unpack8(*reinterpret_cast<const uint4*>(h2 + hrow + 8 * i), hv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        dot += dv[q] * hv[q];
+        o[q] = g * dv[q];
+      }
+      *reinterpret_cast<uint4*>(dh2 + hrow + 8 * i) = pack8(o);
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) dgval[s] = dot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ dx bwd
+// warp per token: dscores (softmax backward of the selected gate values) and
+// dx = sum_e dxin[slot] + dscores . Wg
+__global__ void __launch_bounds__(256)
+moe_dx_bwd_kernel(const __nv_bfloat16* __restrict__ dxin, const int32_t* __restrict__ inv,
+                  const float* __restrict__ dgval, const float* __restrict__ probs, const float* __restrict__ wg,
+                  float* __restrict__ dscores, __nv_bfloat16* __restrict__ dx, int B, int T, int E, int k, int D) {
+  extern __shared__ float swg[];  // [E][D]
+  for (int i = threadIdx.x; i < E * D; i += blockDim.x) swg[i] = wg[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rows = 1LL * B * T;
+  const int nvec = D >> 3;
+  for (long long row = 1LL * blockIdx.x * 8 + warp; row < rows; row += 1LL * gridDim.x * 8) {
+    const long long b = row / T;
+    int slot[kMaxE];
+    float ds[kMaxE];
+    float dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) {
+      slot[e] = -1;
+      ds[e] = 0.f;
+      if (e < E) {
+        slot[e] = inv[row * E + e];
+        const float pe = probs[row * E + e];
+        const float dp = slot[e] >= 0 ? dgval[(b * E + e) * k + slot[e]] : 0.f;
+        ds[e] = dp;
+        dot += pe * dp;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e)
+      if (e < E) ds[e] = probs[row * E + e] * (ds[e] - dot);
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e)
+        if (e < E) dscores[row * E + e] = ds[e];
+    }
+    for (int i = lane; i < nvec; i += 32) {
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e) {
+        if (e < E) {
+          const float* w = swg + e * D + 8 * i;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] += ds[e] * w[q];
+          if (slot[e] >= 0) {
+            float dv[8];
+            unpack8(*reinterpret_cast<const uint4*>(dxin + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i), dv);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += dv[q];
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(dx + row * D + 8 * i) = pack8(acc);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------- gate wgrad
+// block = 256 threads, slab of 128 rows; thread owns columns c, c+256, ... ; dwg[e][c] += sum_r ds[r][e]*x[r][c]
+__global__ void __launch_bounds__(256)
+moe_gate_wgrad_kernel(const float* __restrict__ dscores, const __nv_bfloat16* __restrict__ x, float* __restrict__ dwg,
+                      long long rows, int D, int E) {
+  __shared__ float sds[128 * kMaxE];
+  const long long r0 = 1LL * blockIdx.x * 128;
+  const int nr = static_cast<int>(min(128LL, rows - r0));
+  for (int i = threadIdx.x; i < nr * E; i += blockDim.x) sds[i] = dscores[r0 * E + i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc[kMaxE];
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e) acc[e] = 0.f;
+    for (int r = 0; r < nr; ++r) {
+      const float xv = __bfloat162float(x[(r0 + r) * D + c]);
+#pragma unroll
+      for (int e = 0; e < kMaxE; ++e)
+        if (e < E) acc[e] += sds[r * E + e] * xv;
+    }
+#pragma unroll
+    for (int e = 0; e < kMaxE; ++e)
+      if (e < E) atomicAdd(dwg + e * D + c, acc[e]);
+  }
+}
+
+static int warp_grid(long long warps_needed) {
+  long long blocks = (warps_needed + 7) / 8;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+static int check_moe(const char* what, long long D, long long E) {
+  if (E < 1 || E > kMaxE || D % 8 != 0 || D <= 0) {
+    char buf[128];
+    snprintf(buf, sizeof(buf), "%s: need 1 <= E <= %d and D %% 8 == 0 (E=%lld D=%lld)", what, kMaxE, E, D);
+    return md_set_error(MD_ERR_UNSUPPORTED, buf);
+  }
+  return 0;
+}
+
+}  // namespace md
+
+using namespace md;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int md_moe_gate_fwd(const void* x, const float* wg, float* probs, int64_t rows, int64_t D, int64_t E,
+                               void* stream) {
+  if (int rc = check_moe("md_moe_gate_fwd", D, E)) return rc;
+  if (rows == 0) return 0;
+  if (!x || !wg || !probs) return md_set_error(MD_ERR_INVALID, "md_moe_gate_fwd: null pointer");
+  const size_t smem = E * D * sizeof(float);
+  if (smem > 200 * 1024) return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_gate_fwd: E*D too large for shared memory");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(moe_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  moe_gate_fwd_kernel<<<warp_grid(rows), 256, smem, ST(stream)>>>(CBF(x), wg, probs, rows, (int)D, (int)E);
+  return check_launch("md_moe_gate_fwd");
+}
+
+extern "C" int md_moe_topk(const float* probs, int32_t* idx, float* gval, int32_t* inv, int64_t B, int64_t T, int64_t E,
+                           int64_t k, void* stream) {
+  if (B == 0) return 0;
+  if (!probs || !idx || !gval || !inv) return md_set_error(MD_ERR_INVALID, "md_moe_topk: null pointer");
+  if (T > 4096 || T < 1 || k > T || k < 0 || E < 1 || E > kMaxE)
+    return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_topk: need 1 <= T <= 4096, k <= T, E <= 16");
+  int n = 2;
+  while (n < T) n <<= 1;
+  const int threads = n / 2 < 32 ? 32 : (n / 2 > 1024 ? 1024 : n / 2);
+  moe_topk_kernel<<<(unsigned)(B * E), threads, n * sizeof(unsigned long long), ST(stream)>>>(probs, idx, gval, inv,
+                                                                                             (int)T, (int)E, (int)k, n);
+  return check_launch("md_moe_topk");
+}
+
+extern "C" int md_moe_gather(const void* x, const int32_t* idx, void* xin, int64_t B, int64_t T, int64_t E, int64_t k,
+                             int64_t D, void* stream) {
+  if (int rc = check_moe("md_moe_gather", D, E)) return rc;
+  if (B * k == 0) return 0;
+  if (!x || !idx || !xin) return md_set_error(MD_ERR_INVALID, "md_moe_gather: null pointer");
+  moe_gather_kernel<<<warp_grid(B * E * k), 256, 0, ST(stream)>>>(CBF(x), idx, BF(xin), (int)B, (int)T, (int)E, (int)k,
+                                                                  (int)D);
+  return check_launch("md_moe_gather");
+}
+
+extern "C" int md_moe_combine_fwd(const void* h2, const float* gval, const int32_t* inv, const float* xres,
+                                  const float* gate, int64_t ldmod, float* xout, void* ymoe, int64_t B, int64_t T,
+                                  int64_t E, int64_t k, int64_t D, void* stream) {
+  if (int rc = check_moe("md_moe_combine_fwd", D, E)) return rc;
+  if (B * T == 0) return 0;
+  if (!h2 || !gval || !inv || (xout && !xres)) return md_set_error(MD_ERR_INVALID, "md_moe_combine_fwd: null pointer");
+  moe_combine_fwd_kernel<<<warp_grid(B * T), 256, 0, ST(stream)>>>(CBF(h2), gval, inv, xres, gate, ldmod, xout, BF(ymoe),
+                                                                   (int)B, (int)T, (int)E, (int)k, (int)D);
+  return check_launch("md_moe_combine_fwd");
+}
+
+extern "C" int md_moe_combine_bwd(const void* dy, const void* h2, const float* gval, const int32_t* idx, void* dh2,
+                                  float* dgval, int64_t B, int64_t T, int64_t E, int64_t k, int64_t D, void* stream) {
+  if (int rc = check_moe("md_moe_combine_bwd", D, E)) return rc;
+  if (B * k == 0) return 0;
+  if (!dy || !h2 || !gval || !idx || !dh2 || !dgval)
+    return md_set_error(MD_ERR_INVALID, "md_moe_combine_bwd: null pointer");
+  moe_combine_bwd_kernel<<<warp_grid(B * E * k), 256, 0, ST(stream)>>>(CBF(dy), CBF(h2), gval, idx, BF(dh2), dgval,
+                                                                       (int)B, (int)T, (int)E, (int)k, (int)D);
+  return check_launch("md_moe_combine_bwd");
+}
+
+extern "C" int md_moe_dx_bwd(const void* dxin, const int32_t* inv, const float* dgval, const float* probs,
+                             const float* wg, float* dscores, void* dx, int64_t B, int64_t T, int64_t E, int64_t k,
+                             int64_t D, void* stream) {
+  if (int rc = check_moe("md_moe_dx_bwd", D, E)) return rc;
+  if (B * T == 0) return 0;
+  if (!dxin || !inv || !dgval || !probs || !wg || !dscores || !dx)
+    return md_set_error(MD_ERR_INVALID, "md_moe_dx_bwd: null pointer");
+  const size_t smem = E * D * sizeof(float);
+  if (smem > 200 * 1024) return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_dx_bwd: E*D too large for shared memory");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(moe_dx_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  moe_dx_bwd_kernel<<<warp_grid(B * T), 256, smem, ST(stream)>>>(CBF(dxin), inv, dgval, probs, wg, dscores, BF(dx),
+                                                                 (int)B, (int)T, (int)E, (int)k, (int)D);
+  return check_launch("md_moe_dx_bwd");
+}
+
+extern "C" int md_moe_gate_wgrad(const float* dscores, const void* x, float* dwg, int64_t rows, int64_t D, int64_t E,
+                                 void* stream) {
+  if (int rc = check_moe("md_moe_gate_wgrad", D, E)) return rc;
+  if (rows == 0) return 0;
+  if (!dscores || !x || !dwg) return md_set_error(MD_ERR_INVALID, "md_moe_gate_wgrad: null pointer");
+  moe_gate_wgrad_kernel<<<(unsigned)((rows + 127) / 128), 256, 0, ST(stream)>>>(dscores, CBF(x), dwg, rows, (int)D,
+                                                                               (int)E);
+  return check_launch("md_moe_gate_wgrad");
+}

@@ -1,0 +1,321 @@
+"""Python face of the C ABI: every method takes torch CUDA tensors (device memory + strides are the only
+thing torch provides here), checks dtypes/contiguity, and forwards raw pointers and sizes to
+libmicrodit_b200.so on the current CUDA stream.  No method computes anything in PyTorch and there is no
+fallback: a missing library or a failing call raises `MicroditLibraryError`.
+
+The engine (`engine.py`) is written against this interface; `oracle/emu_ops.py` (test infrastructure)
+implements the same interface on CPU tensors so the host-side orchestration can be tested without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, MicroditLibraryError
+
+NT, TN = 0, 1
+EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL = 0, 1, 2, 3, 4
+ACT_GELU_ERF, ACT_GELU_TANH = 0, 1
+
+_I64 = C.c_int64
+_F = C.c_float
+_P = C.c_void_p
+_I = C.c_int
+
+_PROTOS = {
+    "md_ln_fwd": [_P, _I, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I64, _F, _P],
+    "md_ln_bwd": [_P, _P, _I, _P, _P, _P, _I64, _I64, _P, _P, _P, _I, _P, _P, _P, _I64, _I64, _P],
+    "md_rownorm_fwd": [_P, _I64, _P, _I64, _I64, _F, _P],
+    "md_rownorm_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _P],
+    "md_gate_bwd": [_P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _P],
+    "md_attn_fwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_attn_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I64,
+                    _I64, _I64, _I64, _I64, _I64, _P],
+    "md_swiglu_fwd": [_P, _P, _I64, _I64, _P],
+    "md_swiglu_bwd": [_P, _P, _P, _I64, _I64, _P],
+    "md_act_bwd": [_P, _P, _P, _I64, _I, _P],
+    "md_gelu_tanh_f32_fwd": [_P, _P, _I64, _P],
+    "md_gelu_tanh_f32_bwd": [_P, _P, _P, _I, _I64, _P],
+    "md_moe_gate_fwd": [_P, _P, _P, _I64, _I64, _I64, _P],
+    "md_moe_topk": [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _P],
+    "md_moe_gather": [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_moe_combine_fwd": [_P, _P, _P, _P, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_moe_combine_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_moe_dx_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_moe_gate_wgrad": [_P, _P, _P, _I64, _I64, _I64, _P],
+    "md_mask_sort": [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P],
+    "md_gather_rows_f32": [_P, _P, _P, _I64, _I64, _P],
+    "md_scatter_rows_f32": [_P, _P, _P, _I64, _I64, _P],
+    "md_cond_prepare": [_P, _P, _P, _P, _I64, _I64, _P],
+    "md_patchify": [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_edm_prepare": [_P, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_timestep_embed": [_P, _P, _I64, _I64, _P],
+    "md_edm_loss_fwd": [_P, _P, _P, _I, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_edm_loss_bwd": [_P, _P, _P, _I, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_edm_output": [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_mean_tokens_fwd": [_P, _P, _I64, _I64, _I64, _P],
+    "md_mean_tokens_bwd": [_P, _P, _I64, _I64, _I64, _P],
+    "md_cast_f32_bf16": [_P, _P, _I64, _P],
+    "md_colsum": [_P, _I, _I64, _P, _I64, _I64, _P],
+    "md_cast_transpose": [_P, _P, _P, _I64, _I64, _I64, _P],
+    "md_sumsq": [_P, _P, _I64, _P],
+    "md_adamw": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I64, _I64, _P],
+}
+
+EXPORTED_SYMBOLS = ["md_last_error", "md_abi_version", "md_gemm_bf16", *_PROTOS.keys()]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _mod(t):
+    """(pointer, row pitch) of a per-sample modulation view [samples, D] (a column slice of the adaLN buffer)."""
+    if t is None:
+        return None, 0
+    assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+    return t.data_ptr(), t.stride(0)
+
+
+class CudaOps:
+    """Launches the sm_100a kernels.  One instance per device."""
+
+    is_emulation = False
+    lowp_dtype = torch.bfloat16
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise MicroditLibraryError("the MicroDiT hot path runs on a B200 (CUDA) device only; there is no CPU path")
+        self.lib = _lib.load()
+        for name, argtypes in _PROTOS.items():
+            fn = getattr(self.lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = argtypes
+        self.launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, name)(*args, self._stream())
+        self.launches += 1
+        if rc != 0:
+            raise MicroditLibraryError(f"{name} failed ({rc}): {self.lib.md_last_error().decode()}")
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ GEMM
+    def gemm(self, A, B, Cm, *, layout=NT, epi=EPI_BF16, C2=None, bias=None, res=None, gate=None, rows_per_gate=0,
+             res_mod=0, splits=1, act=0, alpha=1.0):
+        a = GemmArgs()
+        batched = A.dim() == 3
+        A3, B3, C3 = (A, B, Cm) if batched else (A.unsqueeze(0), B.unsqueeze(0), Cm.unsqueeze(0))
+        assert A3.dtype == torch.bfloat16 and B3.dtype == torch.bfloat16
+        assert A3.stride(2) == 1 and B3.stride(2) == 1 and C3.stride(2) == 1
+        if layout == NT:
+            M, K = A3.shape[1], A3.shape[2]
+            N = B3.shape[1]
+            assert B3.shape[2] == K
+        else:
+            K, M = A3.shape[1], A3.shape[2]
+            N = B3.shape[2]
+            assert B3.shape[1] == K
+        assert C3.shape[1] == M and C3.shape[2] == N, (C3.shape, M, N)
+        a.A, a.B, a.C, a.C2 = A3.data_ptr(), B3.data_ptr(), C3.data_ptr(), _ptr(C2)
+        a.bias, a.res = _ptr(bias), _ptr(res)
+        a.M, a.N, a.K = M, N, K
+        a.lda, a.ldb, a.ldc = A3.stride(1), B3.stride(1), C3.stride(1)
+        a.batch = A3.shape[0]
+        a.strideA, a.strideB, a.strideC = A3.stride(0), B3.stride(0), C3.stride(0)
+        a.strideBias = bias.stride(0) if (bias is not None and bias.dim() == 2) else N
+        a.gate, a.ldgate = _mod(gate)
+        a.rows_per_gate = rows_per_gate
+        a.res_mod = res_mod
+        a.layout, a.epilogue, a.splits, a.act, a.alpha = layout, epi, splits, act, alpha
+        if C2 is not None:
+            assert C2.is_contiguous() or C2.stride(-2) == C3.stride(1)
+        if res is not None:
+            assert res.dtype == torch.float32 and res.stride(-1) == 1 and res.stride(-2) == C3.stride(1)
+        want = torch.bfloat16 if epi in (EPI_BF16, EPI_ACT_DUAL) else torch.float32
+        assert Cm.dtype == want, (Cm.dtype, epi)
+        rc = self.lib.md_gemm_bf16(C.byref(a), self._stream())
+        self.launches += 1
+        if rc != 0:
+            raise MicroditLibraryError(f"md_gemm_bf16 failed ({rc}): {self.lib.md_last_error().decode()} "
+                                       f"[M={M} N={N} K={K} layout={layout} epi={epi}]")
+
+    # ------------------------------------------------------------------ norms
+    def ln_fwd(self, x, y, mean, rstd, *, gamma=None, shift=None, scale=None, T, src_rows=None, eps=1e-6):
+        rows, D = y.shape
+        sh, ld1 = _mod(shift)
+        sc, ld2 = _mod(scale)
+        self._call("md_ln_fwd", x.data_ptr(), int(x.dtype == torch.bfloat16), _ptr(src_rows), _ptr(gamma), sh, sc,
+                   ld1 or ld2, T, y.data_ptr(), _ptr(mean), _ptr(rstd), rows, D, eps)
+
+    def ln_bwd(self, dy, x, mean, rstd, *, gamma=None, scale=None, T, src_rows=None, dx=None, dx_mode=0,
+               dgamma=None, dshift=None, dscale=None):
+        rows, D = dy.shape
+        sc, ld = _mod(scale)
+        dsh, ld2 = _mod(dshift)
+        dsc, ld3 = _mod(dscale)
+        self._call("md_ln_bwd", dy.data_ptr(), x.data_ptr(), int(x.dtype == torch.bfloat16), _ptr(src_rows),
+                   _ptr(gamma), sc, ld or ld2 or ld3, T, mean.data_ptr(), rstd.data_ptr(), _ptr(dx), dx_mode,
+                   _ptr(dgamma), dsh, dsc, rows, D)
+
+    def rownorm_fwd(self, x, rstd, eps=1e-6):
+        rows, W = x.shape
+        self._call("md_rownorm_fwd", x.data_ptr(), x.stride(0), rstd.data_ptr(), rows, W, eps)
+
+    def rownorm_bwd(self, dy, xhat, rstd):
+        rows, W = dy.shape
+        self._call("md_rownorm_bwd", dy.data_ptr(), dy.stride(0), xhat.data_ptr(), xhat.stride(0), rstd.data_ptr(),
+                   rows, W)
+
+    def gate_bwd(self, dres, dy, *, y=None, gate=None, dgate=None, T):
+        rows, D = dres.shape
+        g, ld = _mod(gate)
+        dg, ld2 = _mod(dgate)
+        self._call("md_gate_bwd", dres.data_ptr(), _ptr(y), g, ld or ld2, T, dy.data_ptr(), dg, rows, D)
+
+    # ------------------------------------------------------------------ attention
+    def attn_fwd(self, q, k, v, o, lse, B, H, Tq, Tk, hd):
+        self._call("md_attn_fwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                   o.data_ptr(), o.stride(0), lse.data_ptr(), B, H, Tq, Tk, hd)
+
+    def attn_bwd(self, dout, q, k, v, o, lse, delta, dq, dk, dv, B, H, Tq, Tk, hd):
+        self._call("md_attn_bwd", dout.data_ptr(), dout.stride(0), q.data_ptr(), q.stride(0), k.data_ptr(),
+                   k.stride(0), v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(),
+                   delta.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
+                   dv.stride(0), B, H, Tq, Tk, hd)
+
+    # ------------------------------------------------------------------ feed-forward tails
+    def swiglu_fwd(self, u, h):
+        self._call("md_swiglu_fwd", u.data_ptr(), h.data_ptr(), h.shape[0], h.shape[1])
+
+    def swiglu_bwd(self, dh, u, du):
+        self._call("md_swiglu_bwd", dh.data_ptr(), u.data_ptr(), du.data_ptr(), dh.shape[0], dh.shape[1])
+
+    def act_bwd(self, dact, pre, dpre, act):
+        self._call("md_act_bwd", dact.data_ptr(), pre.data_ptr(), dpre.data_ptr(), dact.numel(), act)
+
+    def gelu_tanh_f32_fwd(self, c, out):
+        self._call("md_gelu_tanh_f32_fwd", c.data_ptr(), out.data_ptr(), c.numel())
+
+    def gelu_tanh_f32_bwd(self, dact, c, dc, accumulate):
+        self._call("md_gelu_tanh_f32_bwd", dact.data_ptr(), c.data_ptr(), dc.data_ptr(), int(accumulate), c.numel())
+
+    # ------------------------------------------------------------------ MoE
+    def moe_gate_fwd(self, x, wg, probs):
+        self._call("md_moe_gate_fwd", x.data_ptr(), wg.data_ptr(), probs.data_ptr(), x.shape[0], x.shape[1],
+                   wg.shape[0])
+
+    def moe_topk(self, probs, idx, gval, inv, B, T, E, k):
+        self._call("md_moe_topk", probs.data_ptr(), idx.data_ptr(), gval.data_ptr(), inv.data_ptr(), B, T, E, k)
+
+    def moe_gather(self, x, idx, xin, B, T, E, k):
+        self._call("md_moe_gather", x.data_ptr(), idx.data_ptr(), xin.data_ptr(), B, T, E, k, x.shape[1])
+
+    def moe_combine_fwd(self, h2, gval, inv, xres, gate, xout, ymoe, B, T, E, k):
+        g, ld = _mod(gate)
+        self._call("md_moe_combine_fwd", h2.data_ptr(), gval.data_ptr(), inv.data_ptr(), _ptr(xres), g, ld,
+                   _ptr(xout), _ptr(ymoe), B, T, E, k, h2.shape[-1])
+
+    def moe_combine_bwd(self, dy, h2, gval, idx, dh2, dgval, B, T, E, k):
+        self._call("md_moe_combine_bwd", dy.data_ptr(), h2.data_ptr(), gval.data_ptr(), idx.data_ptr(),
+                   dh2.data_ptr(), dgval.data_ptr(), B, T, E, k, h2.shape[-1])
+
+    def moe_dx_bwd(self, dxin, inv, dgval, probs, wg, dscores, dx, B, T, E, k):
+        self._call("md_moe_dx_bwd", dxin.data_ptr(), inv.data_ptr(), dgval.data_ptr(), probs.data_ptr(),
+                   wg.data_ptr(), dscores.data_ptr(), dx.data_ptr(), B, T, E, k, dx.shape[-1])
+
+    def moe_gate_wgrad(self, dscores, x, dwg):
+        self._call("md_moe_gate_wgrad", dscores.data_ptr(), x.data_ptr(), dwg.data_ptr(), x.shape[0], x.shape[1],
+                   dwg.shape[0])
+
+    # ------------------------------------------------------------------ masking
+    def mask_sort(self, noise, ids_shuffle, ids_restore, mask, keep_rows, keep):
+        B, T = noise.shape
+        self._call("md_mask_sort", noise.data_ptr(), _ptr(ids_shuffle), _ptr(ids_restore), _ptr(mask),
+                   _ptr(keep_rows), B, T, keep)
+
+    def gather_rows(self, x, src_rows, y):
+        self._call("md_gather_rows_f32", x.data_ptr(), src_rows.data_ptr(), y.data_ptr(), y.shape[0], y.shape[1])
+
+    def scatter_rows(self, dy, src_rows, dx):
+        self._call("md_scatter_rows_f32", dy.data_ptr(), src_rows.data_ptr(), dx.data_ptr(), dy.shape[0], dy.shape[1])
+
+    # ------------------------------------------------------------------ EDM
+    def cond_prepare(self, cap, keep, out, cap_out=None):
+        assert cap.dtype == torch.float16 and cap.is_contiguous()
+        B = cap.shape[0]
+        self._call("md_cond_prepare", cap.data_ptr(), _ptr(keep), out.data_ptr(), _ptr(cap_out), B, cap.numel() // B)
+
+    def patchify(self, x, scale, patches, p):
+        B, Cc, H, W = x.shape
+        assert x.is_contiguous() and x.dtype == torch.float32
+        self._call("md_patchify", x.data_ptr(), _ptr(scale), patches.data_ptr(), B, Cc, H, W, p)
+
+    def edm_prepare(self, lat, eps, rnd, sigma_in, p_mean, p_std, sigma_data, xn, patches, coef, p):
+        B, Cc, H, W = lat.shape
+        assert lat.is_contiguous() and eps.is_contiguous() and lat.dtype in (torch.float16, torch.float32)
+        self._call("md_edm_prepare", lat.data_ptr(), int(lat.dtype == torch.float16), eps.data_ptr(), _ptr(rnd),
+                   _ptr(sigma_in), p_mean, p_std, sigma_data, xn.data_ptr(), patches.data_ptr(), coef.data_ptr(),
+                   B, Cc, H, W, p)
+
+    def timestep_embed(self, t, out):
+        self._call("md_timestep_embed", t.data_ptr(), out.data_ptr(), out.shape[0], out.shape[1])
+
+    def edm_loss_fwd(self, ftok, keep_tok, lat, xn, coef, per_sample, loss, p, Tk):
+        B, Cc, H, W = lat.shape
+        self._call("md_edm_loss_fwd", ftok.data_ptr(), _ptr(keep_tok), lat.data_ptr(),
+                   int(lat.dtype == torch.float16), xn.data_ptr(), coef.data_ptr(), per_sample.data_ptr(),
+                   loss.data_ptr(), B, Cc, H, W, p, Tk)
+
+    def edm_loss_bwd(self, ftok, keep_tok, lat, xn, coef, gscale, dftok, p, Tk):
+        B, Cc, H, W = lat.shape
+        self._call("md_edm_loss_bwd", ftok.data_ptr(), _ptr(keep_tok), lat.data_ptr(),
+                   int(lat.dtype == torch.float16), xn.data_ptr(), coef.data_ptr(), gscale.data_ptr(),
+                   dftok.data_ptr(), B, Cc, H, W, p, Tk)
+
+    def edm_output(self, ftok, ids_restore, mask_token, xn, coef, fx, dx, p, Tk):
+        ref = fx if fx is not None else dx
+        B, Cc, H, W = ref.shape
+        self._call("md_edm_output", ftok.data_ptr(), _ptr(ids_restore), _ptr(mask_token), _ptr(xn), _ptr(coef),
+                   _ptr(fx), _ptr(dx), B, Cc, H, W, p, Tk)
+
+    # ------------------------------------------------------------------ utilities
+    def mean_tokens_fwd(self, x, out, B, L):
+        self._call("md_mean_tokens_fwd", x.data_ptr(), out.data_ptr(), B, L, out.shape[1])
+
+    def mean_tokens_bwd(self, d, dx, B, L):
+        self._call("md_mean_tokens_bwd", d.data_ptr(), dx.data_ptr(), B, L, d.shape[1])
+
+    def cast_bf16(self, x, y):
+        assert x.is_contiguous() and y.is_contiguous()
+        self._call("md_cast_f32_bf16", x.data_ptr(), y.data_ptr(), x.numel())
+
+    def colsum(self, x, out):
+        rows, N = x.shape
+        self._call("md_colsum", x.data_ptr(), int(x.dtype == torch.bfloat16), x.stride(0), out.data_ptr(), rows, N)
+
+    def cast_transpose(self, w, wb, wbt):
+        if w.dim() == 2:
+            batch, (rows, cols) = 1, w.shape
+        else:
+            batch, rows, cols = w.shape
+        self._call("md_cast_transpose", w.data_ptr(), _ptr(wb), _ptr(wbt), batch, rows, cols)
+
+    def sumsq(self, x, out):
+        self._call("md_sumsq", x.data_ptr(), out.data_ptr(), x.numel())
+
+    def adamw(self, p, g, m, v, sumsq, clip, lr, beta1, beta2, eps, wd, step):
+        self._call("md_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(sumsq), clip, lr, beta1,
+                   beta2, eps, wd, step, p.numel())

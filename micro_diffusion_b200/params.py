@@ -1,0 +1,158 @@
+"""Flat parameter / gradient storage for the MicroDiT denoiser.
+
+All trainable tensors live in ONE fp32 buffer (and their gradients in a second one); the named
+`nn.Parameter`s the reference exposes (`model.dit.named_parameters()`, the 476-entry state_dict) are
+views into it.  That gives
+  * one NCCL all-reduce (or a few buckets) over `grad` for the data-parallel gradient mean,
+  * one fused AdamW launch over `flat`,
+  * contiguous "GEMM groups": every adaLN weight stacked as one [sum(6D)+2D, dim] matrix so the 35
+    per-block modulation linears (dit.py:233-235, utils.py:237) are a single GEMM, and w1|w2 of each
+    SwiGLU stacked as one [2f, D] matrix (dit.py:84-89),
+  * per-step bf16 operand copies (`wb`, same layout) and transposed copies (`wbt`) produced by
+    md_cast_transpose -- what torch.autocast re-does on every call in the reference.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import torch
+
+from .arch import DiTConfig
+
+
+def _numel(shape) -> int:
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+@dataclass
+class MatGroup:
+    """A [batch, rows, cols] matrix living at `offset` in the flat buffers (one weight or a stacked group)."""
+    name: str
+    offset: int
+    batch: int
+    rows: int
+    cols: int
+    need_t: bool = True  # transposed bf16 copy needed (dgrad, or expert forward)
+
+    @property
+    def numel(self) -> int:
+        return self.batch * self.rows * self.cols
+
+
+class ParamLayout:
+    """Name -> (offset, shape) in the flat buffers, plus the GEMM groups."""
+
+    ALIGN = 8  # elements: 16 B for bf16 TMA bases, 32 B for fp32 vector loads
+
+    def __init__(self, cfg: DiTConfig):
+        self.cfg = cfg
+        specs = cfg.param_specs()
+        ada_w = [s for s in specs if s[0].endswith("adaLN_modulation.1.weight")]
+        ada_b = [s for s in specs if s[0].endswith("adaLN_modulation.1.bias")]
+        rest = [s for s in specs if "adaLN_modulation.1." not in s[0]]
+        self.order: List[Tuple[str, Tuple[int, ...]]] = ada_w + ada_b + rest
+        self.reference_order = [s[0] for s in specs]
+        self.slots: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in self.order:
+            n = _numel(shape)
+            assert off % self.ALIGN == 0
+            self.slots[name] = (off, tuple(shape))
+            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.total = off
+
+        # adaLN stack
+        self.ada_rows = sum(s[1][0] for s in ada_w)
+        self.ada_offset: Dict[str, int] = {}  # block name (or "final_layer") -> first row in the stack
+        r = 0
+        for name, shape in ada_w:
+            self.ada_offset[name[: -len(".adaLN_modulation.1.weight")]] = r
+            r += shape[0]
+        self.ada_w_offset = self.slots[ada_w[0][0]][0]
+        self.ada_b_offset = self.slots[ada_b[0][0]][0]
+        # contiguity of the stacks (no padding holes)
+        assert self.slots[ada_w[-1][0]][0] + _numel(ada_w[-1][1]) - self.ada_w_offset == self.ada_rows * cfg.dim
+        assert self.slots[ada_b[-1][0]][0] + _numel(ada_b[-1][1]) - self.ada_b_offset == self.ada_rows
+
+        self.groups: Dict[str, MatGroup] = {}
+        self.groups["ada"] = MatGroup("ada", self.ada_w_offset, 1, self.ada_rows, cfg.dim)
+        for name, shape in rest:
+            if len(shape) < 2:
+                continue
+            o = self.slots[name][0]
+            if name.endswith("mlp.gate.weight"):
+                continue  # expert gate stays fp32 (read by md_moe_gate_fwd directly)
+            if len(shape) == 3:  # expert banks [E, in, out]
+                self.groups[name] = MatGroup(name, o, shape[0], shape[1], shape[2])
+            elif len(shape) == 4:  # patch-embed conv as [D, C*p*p]; its input is data: no dgrad
+                self.groups[name] = MatGroup(name, o, 1, shape[0], _numel(shape[1:]), need_t=False)
+            elif name.endswith("mlp.w2.weight") and name[: -len("w2.weight")] + "w1.weight" in self.slots:
+                continue  # covered by the w12 stack below
+            elif name.endswith("mlp.w1.weight"):
+                o2 = self.slots[name[: -len("w1.weight")] + "w2.weight"][0]
+                assert o2 == o + _numel(shape), "w1/w2 must be adjacent"
+                self.groups[name[: -len("w1.weight")] + "w12"] = MatGroup(name[: -len("w1.weight")] + "w12", o, 1,
+                                                                         2 * shape[0], shape[1])
+            else:
+                need_t = name != "y_embedder.y_proj.fc1.weight"  # input is data: no dgrad
+                self.groups[name] = MatGroup(name, o, 1, shape[0], shape[1], need_t=need_t)
+
+
+class ParamStore:
+    """Device buffers for one DiT: fp32 master + grad, bf16 copies, views."""
+
+    def __init__(self, layout: ParamLayout, device, lowp_dtype=torch.bfloat16):
+        self.layout = layout
+        self.device = torch.device(device)
+        n = layout.total
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.wb = torch.zeros(n, dtype=lowp_dtype, device=self.device)
+        self.wbt = torch.zeros(n, dtype=lowp_dtype, device=self.device)
+        self._copies_version = None
+        self.p: Dict[str, torch.Tensor] = {}  # fp32 views (reference shapes)
+        self.g: Dict[str, torch.Tensor] = {}  # grad views
+        for name, (off, shape) in layout.slots.items():
+            k = _numel(shape)
+            self.p[name] = self.flat[off:off + k].view(shape)
+            self.g[name] = self.grad[off:off + k].view(shape)
+        self.ada_bias = self.flat[layout.ada_b_offset: layout.ada_b_offset + layout.ada_rows]
+        self.g_ada_bias = self.grad[layout.ada_b_offset: layout.ada_b_offset + layout.ada_rows]
+
+    # group views ---------------------------------------------------------------------------
+    def _gview(self, buf, g: MatGroup, transposed=False):
+        t = buf[g.offset: g.offset + g.numel]
+        if transposed:
+            return t.view(g.batch, g.cols, g.rows) if g.batch > 1 else t.view(g.cols, g.rows)
+        return t.view(g.batch, g.rows, g.cols) if g.batch > 1 else t.view(g.rows, g.cols)
+
+    def W(self, name: str) -> torch.Tensor:
+        """bf16 copy in the parameter's own layout ([rows, cols] or [E, rows, cols])."""
+        return self._gview(self.wb, self.layout.groups[name])
+
+    def WT(self, name: str) -> torch.Tensor:
+        """bf16 transposed copy ([cols, rows] or [E, cols, rows])."""
+        g = self.layout.groups[name]
+        assert g.need_t, name
+        return self._gview(self.wbt, g, transposed=True)
+
+    def G(self, name: str) -> torch.Tensor:
+        """fp32 gradient view of a group in its own layout."""
+        return self._gview(self.grad, self.layout.groups[name])
+
+    def refresh_copies(self, ops, force=False) -> bool:
+        """Re-derive the bf16 operand copies if the master weights changed since the last call."""
+        v = self.flat._version
+        if not force and self._copies_version == v:
+            return False
+        for g in self.layout.groups.values():
+            src = self.flat[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
+            wb = self.wb[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
+            wbt = self.wbt[g.offset: g.offset + g.numel].view(g.batch, g.cols, g.rows) if g.need_t else None
+            ops.cast_transpose(src, wb, wbt)
+        self._copies_version = v
+        return True
