@@ -347,7 +347,7 @@ class Engine:
                       raw_t=None, cap_out=None):
         o, st, cfg = self.ops, self.store, self.cfg
         P = st.p
-        st.refresh_copies(o)
+        st.refresh_copies(o, self.weights_token() if self.weights_token is not None else None)
         B, C, Hh, Ww = lat.shape
         p, D, Dm = cfg.patch_size, cfg.dim, cfg.mixer_dim
         T = (Hh // p) * (Ww // p)
@@ -542,4 +542,5 @@ class Engine:
 
     # buffers owned by the nn.Module (pos_embed / mask_token), attached by models.dit.DiT
     pos_embed: Optional[torch.Tensor] = None
+    weights_token = None  # callable -> hashable; set by models.dit.DiT
     mask_token: Optional[torch.Tensor] = None

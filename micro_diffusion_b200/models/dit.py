@@ -124,6 +124,9 @@ class DiT(nn.Module):
         self._store = new
         self._flat_cpu_init = None
         self._engine = Engine(self.cfg, new, ops)
+        self._plist = [params[n] for n in self._param_names]
+        self._dirty = 0
+        self._engine.weights_token = self._weights_token
         self._anchor = torch.zeros(1, device=device, requires_grad=True)
         return new
 
@@ -138,6 +141,14 @@ class DiT(nn.Module):
         if self._store is not None:  # storage moved underneath us: re-flatten on the new device
             self._bind(force=True)
         return out
+
+    def _weights_token(self):
+        # every in-place write through a Parameter (optimizer step, load_state_dict, clip_grad...) bumps its
+        # autograd version counter; writes through `.data` do not -- call mark_weights_dirty() after those.
+        return (self._dirty, sum(p._version for p in self._plist))
+
+    def mark_weights_dirty(self):
+        self._dirty += 1
 
     @property
     def engine(self) -> Engine:

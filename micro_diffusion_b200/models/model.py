@@ -140,6 +140,19 @@ class LatentDiffusion(_Base):
                                 eps_noise.contiguous(), float(mask_ratio), mask_noise,
                                 y if (inplace_caption_mask and drop is not None) else None)
 
+    def edm_loss_with_draws(self, x, y, drop, rnd_normal, eps_noise, mask_noise, mask_ratio: float) -> torch.Tensor:
+        """edm_loss with the three random draws supplied by the caller (seeded replay / parity tests):
+        rnd_normal (B,), eps_noise like x (f32), mask_noise (B,T) uniform or None."""
+        dev = self.dit.store.device
+        x = x.to(dev).contiguous()
+        y = y.to(device=dev, dtype=torch.float16).contiguous()
+        if drop is not None:
+            drop = drop.to(device=dev, dtype=torch.float64).contiguous()
+        self.dit.engine
+        return _EDMLossFn.apply(self.dit._anchor, self, x, y, drop, rnd_normal.to(dev).float().reshape(-1).contiguous(),
+                                eps_noise.to(dev).float().contiguous(), float(mask_ratio),
+                                mask_noise.to(dev).float().contiguous() if mask_noise is not None else None, None)
+
     def edm_loss(self, x: torch.Tensor, y: torch.Tensor, mask_ratio: float = 0, **kwargs) -> torch.Tensor:
         """model.py:181-210 (x: latents, y: caption embeddings (B,1,L,Dc))."""
         return self._edm_loss_impl(x, y, None, mask_ratio)

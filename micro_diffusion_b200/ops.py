@@ -95,16 +95,33 @@ class CudaOps:
             fn.restype = C.c_int
             fn.argtypes = argtypes
         self.launches = 0
+        self.gemm_flops = 0      # algorithmic FLOPs of every md_gemm_bf16 launched (2*M*N*K*batch)
+        self.profile = None      # set to a list to record (name, start_event, end_event, flops) per launch
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _call(self, name, *args):
+        prof = self.profile
+        if prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = getattr(self.lib, name)(*args, self._stream())
+        if prof is not None:
+            e1.record()
+            prof.append((name, e0, e1, 0))
         self.launches += 1
         if rc != 0:
             raise MicroditLibraryError(f"{name} failed ({rc}): {self.lib.md_last_error().decode()}")
+
+    def profile_summary(self):
+        """{op: (launches, total_ms, flops)} from the recorded events (call after torch.cuda.synchronize())."""
+        out = {}
+        for name, e0, e1, fl in self.profile or []:
+            n, ms, f = out.get(name, (0, 0.0, 0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1), f + fl)
+        return out
 
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -146,7 +163,16 @@ class CudaOps:
             assert res.dtype == torch.float32 and res.stride(-1) == 1 and res.stride(-2) == C3.stride(1)
         want = torch.bfloat16 if epi in (EPI_BF16, EPI_ACT_DUAL) else torch.float32
         assert Cm.dtype == want, (Cm.dtype, epi)
+        flops = 2 * M * N * K * int(a.batch)
+        self.gemm_flops += flops
+        prof = self.profile
+        if prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = self.lib.md_gemm_bf16(C.byref(a), self._stream())
+        if prof is not None:
+            e1.record()
+            prof.append(("md_gemm_bf16/" + ("tn" if layout == TN else "nt"), e0, e1, flops))
         self.launches += 1
         if rc != 0:
             raise MicroditLibraryError(f"md_gemm_bf16 failed ({rc}): {self.lib.md_last_error().decode()} "

@@ -144,9 +144,11 @@ class ParamStore:
         """fp32 gradient view of a group in its own layout."""
         return self._gview(self.grad, self.layout.groups[name])
 
-    def refresh_copies(self, ops, force=False) -> bool:
-        """Re-derive the bf16 operand copies if the master weights changed since the last call."""
-        v = self.flat._version
+    def refresh_copies(self, ops, token=None, force=False) -> bool:
+        """Re-derive the bf16 operand copies if the master weights changed since the last call.
+        `token` is any value that changes whenever a parameter is written (models/dit.py sums the
+        parameters' autograd version counters, which every in-place optimizer / load_state_dict update bumps)."""
+        v = token if token is not None else self.flat._version
         if not force and self._copies_version == v:
             return False
         for g in self.layout.groups.values():

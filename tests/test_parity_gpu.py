@@ -1,0 +1,88 @@
+"""End-to-end parity of the CUDA path (through the C ABI) against the fp32 CPU oracle and the golden fixtures
+generated from the unmodified reference.
+
+Tolerances (bf16 tensor-core operands, fp32 accumulation -- the reference's own amp_bf16 regime):
+  loss            |d|/loss          <= 3e-3   (the reference's amp_bf16 run deviates 2e-4 .. 1.4e-3 from its fp32 run
+                                               on these cases; tests/golden/*.pt records it per case)
+  denoiser D_x    rel L2            <= 1e-2
+  parameter grads rel L2, median    <= 1.5 x the reference's amp_bf16 median + 5e-3
+                  rel L2, worst     <= 2 x the reference's amp_bf16 worst + 2e-2
+The fp32-exact restatement of the same engine meets 1e-5 (tests/test_engine_emulated.py)."""
+import os
+
+import pytest
+import torch
+
+from oracle import configs
+from tests import parity_common as pc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("name", list(configs.PARITY_CONFIGS))
+def test_cuda_path_matches_oracle_and_golden(name):
+    fx = torch.load(os.path.join(pc.GOLDEN, f"parity_{name}.pt"), weights_only=False)
+    loss, grads, den, ld = pc.product_run(name, device=DEV)
+    assert ld.dit.engine.ops.launches > 100 and not ld.dit.engine.ops.is_emulation
+    sd_cpu = {k: v.detach().cpu() for k, v in ld.dit.state_dict().items()}
+    oloss, ograds, oden, _ = pc.oracle_run(name, sd_cpu)
+    errs, med, worst = pc.grad_report(grads, ograds)
+    print(f"\n[{name}] loss cuda {loss:.6f} oracle {oloss:.6f} golden {fx['loss']:.6f} rel {abs(loss - oloss) / oloss:.2e} | "
+          f"D_x relL2 {pc.rel_l2(den, oden):.2e} | grads median {med:.2e} worst {worst:.2e} ({errs[0][1]}) | "
+          f"reference amp-bf16: loss {fx['ref_amp_bf16_loss_rel']:.2e} grads median {fx['ref_amp_bf16_grad_rel_median']:.2e} "
+          f"worst {fx['ref_amp_bf16_grad_rel_max']:.2e}")
+    assert abs(oloss - fx["loss"]) / fx["loss"] < 1e-5          # oracle == reference fixture on this box too
+    assert abs(loss - fx["loss"]) / fx["loss"] < 3e-3
+    assert pc.rel_l2(den, fx["denoised_unmasked"]) < 1e-2
+    assert med < 1.5 * fx["ref_amp_bf16_grad_rel_median"] + 5e-3
+    assert worst < 2 * fx["ref_amp_bf16_grad_rel_max"] + 2e-2, errs[:5]
+    for k, g in fx["grad_full"].items():
+        assert pc.rel_l2(grads[k], g) < 2 * fx["ref_amp_bf16_grad_rel_max"] + 2e-2, k
+
+
+def test_tiny_zoo_model_matches_oracle():
+    """MicroDiT_Tiny_2 (16 layers, d=512, head_dim 32) at res 256 / mask 0.75 / batch 4 -- BASELINE.json configs[0]."""
+    from micro_diffusion_b200.models.dit import MicroDiT_Tiny_2
+    from micro_diffusion_b200.models.model import LatentDiffusion, PrecomputedLatentStubs
+    from oracle import port, weights
+    net = MicroDiT_Tiny_2(input_size=32, in_channels=4)
+    net.load_state_dict(weights.synth_state_dict(net.state_dict(), seed=7))
+    sd_cpu = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV)
+    vae, te, tok = PrecomputedLatentStubs.make()
+    ld = LatentDiffusion(net, vae, te, tok, train_mask_ratio=0.75)
+    ld.train()
+    B = 4
+    batch = weights.synth_batch(B, 4, 32, seed=11)
+    rnd, eps, noise = weights.replay_draws(123, (B, 4, 32, 32), 256, 0.75)
+    loss = ld.edm_loss_with_draws(batch["image_latents"], batch["caption_latents"], batch["drop_caption_mask"],
+                                  rnd.reshape(-1), eps, noise, 0.75)
+    loss.backward()
+    P = {k: v.clone().requires_grad_(k not in ("pos_embed", "mask_token")) for k, v in sd_cpu.items()}
+    cfg = port.PortConfig(patch_size=2, head_dim=32, num_experts=8, expert_capacity=2.0)
+    oloss, _ = port.latent_diffusion_forward(P, cfg, batch, rnd, eps, 0.75, noise)
+    oloss.backward()
+    grads = {k: p.grad.detach().float().cpu() for k, p in net.named_parameters()}
+    ograds = {k: v.grad for k, v in P.items() if v.grad is not None}
+    errs, med, worst = pc.grad_report(grads, ograds)
+    print(f"\n[Tiny_2] loss cuda {float(loss):.6f} oracle {float(oloss):.6f} rel {abs(float(loss) - float(oloss)) / float(oloss):.2e} "
+          f"grads median {med:.2e} worst {worst:.2e} ({errs[0][1]})")
+    assert abs(float(loss) - float(oloss)) / float(oloss) < 5e-3
+    assert med < 4e-2 and worst < 0.25, errs[:5]
+
+
+def test_sampler_surface_runs():
+    """edm_sampler_loop / model_forward_wrapper with CFG run through the fused denoiser (2 Heun steps)."""
+    name = "P"
+    ld = pc.build_product(name, device=DEV)
+    ld.eval()
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(2, 4, 32, 32, device=DEV, generator=g)
+    y = torch.randn(2, 1, 77, 1024, device=DEV, generator=g).half()
+    out = ld.edm_sampler_loop(x, y, steps=2, cfg=3.0)
+    assert out.shape == x.shape and torch.isfinite(out).all()
+    out1 = ld.edm_sampler_loop(x, y, steps=2, cfg=1.0)
+    assert torch.isfinite(out1).all()
+    raw = ld.dit(x, torch.tensor([0.1], device=DEV), y)["sample"]
+    assert raw.shape == x.shape and torch.isfinite(raw).all()
