@@ -313,6 +313,12 @@ class PrecomputedLatentStubs:
         def to(self, device):
             return self
 
+    class _Tok:
+        model_max_length = 77
+
+        def tokenize(self, captions):
+            raise RuntimeError("no tokenizer: this model was built for precomputed latents only")
+
     @classmethod
     def make(cls):
-        return cls._VAE(), cls._Text(), None
+        return cls._VAE(), cls._Text(), cls._Tok()
