@@ -63,10 +63,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index=0):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self._stop = gpu_index, [], threading.Event()
+        self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                                       str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -74,10 +74,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
         reasons = set()
