@@ -126,8 +126,18 @@ def build_model(wl, device):
 
 
 # ------------------------------------------------------------------------------------------ CPU legs
-def cpu_reference_img_per_s(wl, batch, iters, threads, state_dict=None):
-    """The reference algorithm (oracle.port, fp32) forward+backward on the host cores."""
+def host_threads():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))  # torch's CPU GEMMs stop scaling (and regress) beyond ~32 threads at these sizes
+
+
+def cpu_reference_img_per_s(wl, batch, iters, threads, state_dict=None, budget_s=60.0, warmup=0):
+    """The reference algorithm (oracle.port, fp32) forward+backward on the host cores.
+    Runs `warmup` untimed passes, then up to `iters` timed passes, stopping early once `budget_s` is spent.
+    Returns (img/s, timed passes done)."""
     from oracle import port, weights
     torch.set_num_threads(threads)
     if state_dict is None:
@@ -135,7 +145,6 @@ def cpu_reference_img_per_s(wl, batch, iters, threads, state_dict=None):
         kw = (micro_dit_xl_2_kwargs if wl["arch"] == "MicroDiT_XL_2" else micro_dit_tiny_2_kwargs)(
             input_size=wl["res"], in_channels=wl["ch"], pos_interp_scale=wl["pos"])
         cfg = DiTConfig(**kw)
-        g = torch.Generator().manual_seed(18)
         state_dict = {}
         for k, s in cfg.buffer_specs() + cfg.param_specs():
             if k == "pos_embed":
@@ -144,14 +153,18 @@ def cpu_reference_img_per_s(wl, batch, iters, threads, state_dict=None):
                 state_dict[k] = torch.zeros(s)
             elif len(s) == 1:
                 state_dict[k] = torch.ones(s) if not k.endswith("bias") else torch.zeros(s)
-            else:
-                state_dict[k] = torch.randn(s, generator=g) * 0.02
+            else:  # cheap non-degenerate fill (a 1.2 B-element randn costs a minute of host time)
+                n = 1
+                for d in s:
+                    n *= d
+                state_dict[k] = (((torch.arange(n, dtype=torch.float32) * 0.6180339887) % 1.0) - 0.5).mul_(0.07).view(s)
     hd = 64 if wl["arch"] == "MicroDiT_XL_2" else 32
     pcfg = port.PortConfig(patch_size=2, head_dim=hd, num_experts=8, expert_capacity=2.0, p_mean=wl["p_mean"], p_std=wl["p_std"])
     P = {k: v.detach().float().cpu().requires_grad_(k not in ("pos_embed", "mask_token")) for k, v in state_dict.items()}
     T = (wl["res"] // 2) ** 2
     times = []
-    for it in range(iters + 1):
+    t_start = time.perf_counter()
+    for it in range(warmup + iters):
         b = weights.synth_batch(batch, wl["ch"], wl["res"], seed=100 + it)
         rnd, eps, noise = weights.replay_draws(200 + it, (batch, wl["ch"], wl["res"], wl["res"]), T, wl["mask"])
         for v in P.values():
@@ -160,30 +173,34 @@ def cpu_reference_img_per_s(wl, batch, iters, threads, state_dict=None):
         loss, _ = port.latent_diffusion_forward(P, pcfg, b, rnd, eps, wl["mask"], noise)
         loss.backward()
         dt = time.perf_counter() - t0
-        if it > 0:
+        if it >= warmup:
             times.append(dt)
-    return batch / (sum(times) / len(times)), float(loss)
+        if time.perf_counter() - t_start > budget_s and times:
+            break
+    return batch * len(times) / sum(times), len(times)
 
 
 def run_reference_arm(args, wl):
+    """`--impl reference`: the reference algorithm on the host cores (oracle.port; /root/reference and its Python
+    dependencies do not exist on the GPU box).  Each "step" is a bounded sample: forward+backward of `sample` images."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sample = 8 if wl["res"] == 32 else 2
+    threads = host_threads()
+    sample = 4 if wl["res"] == 32 else 1
     t0 = time.perf_counter()
-    # W warm-up + K timed "steps", each a bounded sample of the workload
-    vals = []
-    ips, _ = cpu_reference_img_per_s(wl, sample, max(1, args.steps), threads)
-    vals.append(ips)
+    ips, done = cpu_reference_img_per_s(wl, sample, max(1, args.steps), threads, budget_s=150.0,
+                                        warmup=1 if args.warmup > 0 else 0)
     wall = time.perf_counter() - t0
     line = {
         "impl": "reference", "metric": "training images/sec (global batch 2048)", "value": ips, "unit": "img/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample / ips,
+        "n_gpus": args.gpus, "steps": done, "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": 1000.0 * sample / ips,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "global_batch": GLOBAL_BATCH, "sample": f"{sample} images per step (fwd+bwd)"},
+        "config": {"workload": wl["name"], "global_batch": GLOBAL_BATCH,
+                   "sample": f"{sample} images per step (forward+backward), {done} of {args.steps} requested steps "
+                             f"inside the 150 s budget"},
         "cpu_baseline": {"value": ips, "unit": "img/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample}-image forward+backward x {max(1, args.steps)} after 1 warm-up, fp32, oracle.port"},
+                         "sample": f"{sample}-image forward+backward x {done}, fp32, oracle.port, {threads} threads"},
         "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
@@ -310,19 +327,30 @@ def main():
             with open(args.profile_out, "w") as f:
                 f.write(f"# per-op CUDA-event times of one {args.workload} step (per rank {per_rank} imgs, microbatch {micro})\n")
                 f.write("op,launches,total_ms,share,algorithmic_tflops\n")
+                agg = {}
+                for k, (n, ms, fl) in prof.items():
+                    kk = k.split(" ")[0]
+                    a = agg.get(kk, (0, 0.0, 0))
+                    agg[kk] = (a[0] + n, a[1] + ms, a[2] + fl)
+                for k, (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                    tf = f"{fl / (ms * 1e-3) / 1e12:.1f}" if fl else ""
+                    f.write(f"{k},{n},{ms:.3f},{ms / tot_ms:.4f},{tf}\n")
+                f.write("# GEMM launches by shape\n")
                 for k, (n, ms, fl) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+                    if " " not in k:
+                        continue
                     tf = f"{fl / (ms * 1e-3) / 1e12:.1f}" if fl else ""
                     f.write(f"{k},{n},{ms:.3f},{ms / tot_ms:.4f},{tf}\n")
         cpu_base = None
         if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
-            sample = 8 if wl["res"] == 32 else 2
+            threads = host_threads()
+            sample = 4 if wl["res"] == 32 else 1
             t0 = time.perf_counter()
             sd = {k: v.detach().cpu() for k, v in ld.dit.state_dict().items()}
-            ips, _ = cpu_reference_img_per_s(wl, sample, 1, threads, sd)
+            ips, done = cpu_reference_img_per_s(wl, sample, 1, threads, sd, budget_s=30.0, warmup=0)
             cpu_base = {"value": ips, "unit": "img/s", "cores": threads, "kind": "port",
-                        "sample": f"one {sample}-image forward+backward after a warm-up pass, fp32 oracle.port "
-                                  f"({time.perf_counter() - t0:.0f} s wall)"}
+                        "sample": f"one {sample}-image forward+backward (no warm-up pass), fp32 oracle.port, same weights "
+                                  f"as the GPU arm ({time.perf_counter() - t0:.0f} s wall incl. the weight copy)"}
         line = {
             "metric": "training images/sec (global batch 2048)", "value": value, "unit": "img/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",

@@ -203,26 +203,39 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_b
 }
 
 // -------------------------------------------------------------------------------------------- delta
-// delta[b,h,q] = sum_d dO * O; one warp per (row, head).
+// delta[b,h,q] = sum_d dO * O.  One warp per token row covering all heads with 16-byte loads issued up front;
+// a head's HD/8 chunks sit in adjacent lanes, so the per-head sum is a short shuffle reduction.
+template <int HD>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ o,
-                  long long ldo, float* __restrict__ delta, long long B, int H, int Tq, int HD) {
+                  long long ldo, float* __restrict__ delta, long long rows, int H, int Tq) {
+  constexpr int kLanesPerHead = HD / 8;  // 8 (HD=64) or 4 (HD=32)
+  constexpr int kMaxChunks = 8;          // uint4 chunks per lane: H*HD <= 2048
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total = B * Tq * H;
-  for (long long w = 1LL * blockIdx.x * 8 + warp; w < total; w += 1LL * gridDim.x * 8) {
-    const int h = static_cast<int>(w % H);
-    const long long row = w / H;  // b*Tq + q
-    float s = 0.f;
-    for (int d = lane * 2; d < HD; d += 64) {
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(dout + row * lddo + h * HD + d);
-      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(o + row * ldo + h * HD + d);
-      s += __low2float(a) * __low2float(c) + __high2float(a) * __high2float(c);
+  const int nchunks = H * kLanesPerHead;
+  for (long long row = 1LL * blockIdx.x * 8 + warp; row < rows; row += 1LL * gridDim.x * 8) {
+    uint4 a[kMaxChunks], c[kMaxChunks];
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int i = lane + 32 * j;
+      const bool ok = i < nchunks;
+      a[j] = ok ? *reinterpret_cast<const uint4*>(dout + row * lddo + 8 * i) : make_uint4(0, 0, 0, 0);
+      c[j] = ok ? *reinterpret_cast<const uint4*>(o + row * ldo + 8 * i) : make_uint4(0, 0, 0, 0);
     }
-    s = warp_sum(s);
-    if (lane == 0) {
-      const long long b = row / Tq;
-      const int qq = static_cast<int>(row % Tq);
-      delta[(b * H + h) * Tq + qq] = s;
+    const long long b = row / Tq;
+    const int qq = static_cast<int>(row % Tq);
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int i = lane + 32 * j;
+      const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a[j]);
+      const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&c[j]);
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        s += __low2float(pa[e]) * __low2float(pc[e]) + __high2float(pa[e]) * __high2float(pc[e]);
+#pragma unroll
+      for (int off = kLanesPerHead / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (i < nchunks && (lane % kLanesPerHead) == 0) delta[(b * H + i / kLanesPerHead) * Tq + qq] = s;
     }
   }
 }
@@ -425,11 +438,15 @@ extern "C" int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_
     return md_set_error(MD_ERR_INVALID, "md_attn_bwd: null pointer");
   const float scale = 1.f / sqrtf((float)hd);
   const float sl2 = 1.4426950408889634f * scale;
-  long long warps = B * Tq * H;
-  long long blocks = (warps + 7) / 8;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  attn_delta_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(o), ldo, delta, B, (int)H, (int)Tq,
-                                                              (int)hd);
+  if (H * hd > 2048) return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_bwd: H*hd must be <= 2048");
+  long long blocks = (B * Tq + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (hd == 64)
+    attn_delta_kernel<64><<<(unsigned)blocks, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(o), ldo, delta, B * Tq, (int)H,
+                                                                    (int)Tq);
+  else
+    attn_delta_kernel<32><<<(unsigned)blocks, 256, 0, ST(stream)>>>(CBF(dout), lddo, CBF(o), ldo, delta, B * Tq, (int)H,
+                                                                    (int)Tq);
   dim3 gkv((unsigned)((Tk + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
   dim3 gq((unsigned)((Tq + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
   if (hd == 64) {

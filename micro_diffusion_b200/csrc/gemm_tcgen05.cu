@@ -10,8 +10,8 @@
 //   kMN=false  "NT":  C[M,N] = sum_k A[M,k] * B[N,k]     A,B row-major with k contiguous (K-major)
 //   kMN=true   "TN":  C[P,Q] = sum_r A[r,P] * B[r,Q]     A,B row-major with the reduction index r
 //                     strided (MN-major UMMA operands) -- the weight-gradient contraction.
-// Roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-// warps4-7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31).
+// Roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps4-11 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31, column half (w-4)/4 of the tile).
 #include "gemm_tcgen05.cuh"
 
 #include <stdio.h>
@@ -23,7 +23,7 @@ namespace md {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // 4 control warps + 8 epilogue warps
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -35,6 +35,25 @@ struct GemmCfg {
   static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 256 or 512 (power of two)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+// Cheap activations for the epilogue (it shares 4 issue ports with nothing else but is on the critical path of
+// short-K tiles).  erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);  // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x, x * x, x);
+  const float e = __expf(2.0f * u);                    // tanh(u) = 1 - 2/(e^{2u}+1)
+  const float th = 1.0f - __fdividef(2.0f, e + 1.0f);
+  return 0.5f * x * (1.0f + th);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -69,7 +88,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -163,7 +182,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    const int q = warp & 3;  // TMEM lane quarter
+    // 8 warps: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 4) / 4.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kChunksPerWarp = BLOCK_N / 64;  // 32-column chunks per warp
     uint32_t acc_it = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++acc_it) {
       long long t = tile;
@@ -175,54 +197,83 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool has_k = kb0 < kb_total;  // empty split (possible when splits does not divide)
       const int as = acc_it % Cfg::kAccStages;
       const uint32_t aph = (acc_it / Cfg::kAccStages) & 1;
-      mbar_wait(&tfull_bar[as], aph);
-      tc_fence_after();
 
       const int row = mb * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const long long crow = 1LL * bz * p.strideC + 1LL * row * p.ldc;
       const long long rrow = 1LL * bz * p.strideC + 1LL * (p.res_mod > 0 ? row % p.res_mod : row) * p.ldc;
       const float* gate_row = nullptr;
-      if (p.gate != nullptr && row_ok)
-        gate_row = p.gate + 1LL * (row / p.rows_per_gate) * p.ldgate;
+      if (p.gate != nullptr && row_ok) gate_row = p.gate + 1LL * (row / p.rows_per_gate) * p.ldgate;
+      const int colbase = nb * BLOCK_N + half * (BLOCK_N / 2);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
+      const bool want_res = (p.epi == EPI_RESID_F32) && row_ok && has_k;
+
+      // residual prefetch for chunk 0 is independent of the accumulator: issue it before waiting on the MMAs
+      float4 resn[8];
+      auto load_res = [&](int c) {
+        const int col0 = colbase + c * 32;
+        const float* res = p.res + rrow + col0;
+        const bool vec = want_res && (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(res) & 15) == 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (vec) {
+            resn[j] = *reinterpret_cast<const float4*>(res + 4 * j);
+          } else {
+            float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+            if (want_res)
+              for (int e = 0; e < 4; ++e)
+                if (col0 + 4 * j + e < p.N) tmp[e] = res[4 * j + e];
+            resn[j] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+          }
+        }
+      };
+      if (p.epi == EPI_RESID_F32) load_res(0);
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      uint32_t rnext[32];
+      tmem_ld_32x32(tbase, rnext);
 
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, r);
+      for (int c = 0; c < kChunksPerWarp; ++c) {
         tmem_ld_wait();
-        const int col0 = nb * BLOCK_N + c * 32;
-        // No divergent `continue`: every lane must reach the next (warp-aligned) tcgen05.ld together.
-        if (row_ok && col0 < p.N && has_k) do {
         float v[32];
+        float4 resv[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        const int ncols = min(32, p.N - col0);
-        if (p.bias != nullptr) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rnext[j]) * p.alpha;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
+        for (int j = 0; j < 8; ++j) resv[j] = resn[j];
+        if (c + 1 < kChunksPerWarp) {  // software pipeline: next chunk's TMEM + residual loads fly during this chunk
+          tmem_ld_32x32(tbase + (c + 1) * 32, rnext);
+          if (p.epi == EPI_RESID_F32) load_res(c + 1);
         }
-        if (p.epi == EPI_ATOMIC_F32) {
-          float* dst = reinterpret_cast<float*>(p.C) + crow + col0;
-          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        const int col0 = colbase + c * 32;
+        // No divergent `continue`: every lane must reach the next (warp-aligned) tcgen05 instruction together.
+        if (row_ok && col0 < p.N && has_k) {
+          const int ncols = min(32, p.N - col0);
+          if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
-                           "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
-                           : "memory");
-          } else {
-            for (int j = 0; j < ncols; ++j) atomicAdd(dst + j, v[j]);
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
           }
-          break;
-        }
-        if (p.epi == EPI_ACT_DUAL) {
-          // C = pre-activation (bf16), C2 = gelu_erf(pre) (bf16); activation taken on the bf16-rounded
-          // pre-activation so that backward (which re-reads C) differentiates the same function.
-          __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
-          __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
-          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(d1) & 15) == 0) &&
-              ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
+          if (p.epi == EPI_ATOMIC_F32) {
+            float* dst = reinterpret_cast<float*>(p.C) + crow + col0;
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3])
+                             : "memory");
+            } else {
+              for (int j = 0; j < ncols; ++j) atomicAdd(dst + j, v[j]);
+            }
+          } else if (p.epi == EPI_ACT_DUAL) {
+            // C = pre-activation (bf16), C2 = act(pre) (bf16); the activation is taken on the bf16-rounded
+            // pre-activation so that backward (which re-reads C) differentiates the same function.
+            __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
+            __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
+            const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(d1) & 15) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(d2) & 15) == 0);
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 a, g;
@@ -230,81 +281,77 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               uint32_t* gp = reinterpret_cast<uint32_t*>(&g);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float x0 = __bfloat162float(__float2bfloat16_rn(v[j + 2 * e]));
-                const float x1 = __bfloat162float(__float2bfloat16_rn(v[j + 2 * e + 1]));
+                const float x0 = bf16_round(v[j + 2 * e]), x1 = bf16_round(v[j + 2 * e + 1]);
                 ap[e] = pack_bf16(x0, x1);
-                gp[e] = p.act ? pack_bf16(gelu_tanh_f(x0), gelu_tanh_f(x1)) : pack_bf16(gelu_erf_f(x0), gelu_erf_f(x1));
+                gp[e] = p.act ? pack_bf16(gelu_tanh_fast(x0), gelu_tanh_fast(x1))
+                              : pack_bf16(gelu_erf_fast(x0), gelu_erf_fast(x1));
               }
-              *reinterpret_cast<uint4*>(d1 + j) = a;
-              *reinterpret_cast<uint4*>(d2 + j) = g;
-            }
-          } else {
-            for (int j = 0; j < ncols; ++j) {
-              const float x0 = __bfloat162float(__float2bfloat16_rn(v[j]));
-              d1[j] = __float2bfloat16_rn(x0);
-              d2[j] = __float2bfloat16_rn(p.act ? gelu_tanh_f(x0) : gelu_erf_f(x0));
-            }
-          }
-          break;
-        }
-        if (p.epi == EPI_RESID_F32) {
-          // optional bf16 copy of the raw GEMM result (needed by backward for d(gate))
-          if (p.C2 != nullptr) {
-            __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
-            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 a;
-                uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ap[e] = pack_bf16(v[j + 2 * e], v[j + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(d2 + j) = a;
+              if (vec) {
+                *reinterpret_cast<uint4*>(d1 + j) = a;
+                *reinterpret_cast<uint4*>(d2 + j) = g;
+              } else {
+                const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&a);
+                const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&g);
+                for (int e = 0; e < 8; ++e)
+                  if (j + e < ncols) {
+                    d1[j + e] = ah[e];
+                    d2[j + e] = gh[e];
+                  }
               }
-            } else {
-              for (int j = 0; j < ncols; ++j) d2[j] = __float2bfloat16_rn(v[j]);
-            }
-          }
-          if (gate_row != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) v[j] *= gate_row[col0 + j];
-          }
-          const float* res = p.res + rrow + col0;
-          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 rr = *reinterpret_cast<const float4*>(res + j);
-              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
             }
           } else {
-            for (int j = 0; j < ncols; ++j) v[j] += res[j];
+            if (p.epi == EPI_RESID_F32) {
+              if (p.C2 != nullptr) {  // bf16 copy of the raw GEMM result (needed by backward for d(gate))
+                __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
+                if (ncols == 32 && ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 8) {
+                    uint4 a;
+                    uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ap[e] = pack_bf16(v[j + 2 * e], v[j + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(d2 + j) = a;
+                  }
+                } else {
+                  for (int j = 0; j < ncols; ++j) d2[j] = __float2bfloat16_rn(v[j]);
+                }
+              }
+              if (gate_row != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) v[j] *= gate_row[col0 + j];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += resv[j].x; v[4 * j + 1] += resv[j].y; v[4 * j + 2] += resv[j].z; v[4 * j + 3] += resv[j].w;
+              }
+            }
+            if (p.epi == EPI_STORE_BF16) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
+              if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 a;
+                  uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) ap[e] = pack_bf16(v[j + 2 * e], v[j + 2 * e + 1]);
+                  *reinterpret_cast<uint4*>(dst + j) = a;
+                }
+              } else {
+                for (int j = 0; j < ncols; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+              }
+            } else {  // EPI_STORE_F32 / EPI_RESID_F32
+              float* dst = reinterpret_cast<float*>(p.C) + crow + col0;
+              if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+                for (int j = 0; j < ncols; ++j) dst[j] = v[j];
+              }
+            }
           }
         }
-        if (p.epi == EPI_STORE_BF16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
-          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 a;
-              uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ap[e] = pack_bf16(v[j + 2 * e], v[j + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(dst + j) = a;
-            }
-          } else {
-            for (int j = 0; j < ncols; ++j) dst[j] = __float2bfloat16_rn(v[j]);
-          }
-        } else {  // EPI_STORE_F32 / EPI_RESID_F32
-          float* dst = reinterpret_cast<float*>(p.C) + crow + col0;
-          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < ncols; ++j) dst[j] = v[j];
-          }
-        }
-        } while (0);
         __syncwarp();
       }
       tc_fence_before();
@@ -445,10 +492,28 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   dev.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
 
   const bool mn = a->layout == MD_GEMM_TN;
-  // Tile-N choice: 256 when it divides well and there are enough tiles to fill the machine.
   const long long m_blocks = (a->M + kBlockM - 1) / kBlockM;
-  const long long tiles256 = a->batch * splits * m_blocks * ((a->N + 255) / 256);
-  const bool use256 = (a->N % 256 == 0 || a->N > 1024) && tiles256 >= 2LL * sm_count;
+  const long long kb_total = (a->K + kBlockK - 1) / kBlockK;
+  auto tiles_for = [&](int bn) { return a->batch * m_blocks * ((a->N + bn - 1) / bn); };
+  // Tile-N: 256 halves the B-operand smem traffic per MMA (a 128x128 tile is smem-bandwidth bound), so prefer it
+  // whenever the padding waste is small and there is enough work to spread over the SMs.
+  const long long n256 = (a->N + 255) / 256 * 256;
+  bool use256 = (a->N >= 256) && (n256 - a->N) * 8 <= a->N;  // <= 12.5 % padded columns
+  if (a->splits == 0 && a->epilogue == EPI_ATOMIC_F32) {
+    // auto split of the reduction: minimise  waves * (k-blocks per split + fixed per-tile cost)
+    const long long t = tiles_for(use256 ? 256 : 128);
+    const long long smax = kb_total / 8 > 0 ? (kb_total / 8 < 64 ? kb_total / 8 : 64) : 1;
+    double best = 1e30;
+    for (long long sp = 1; sp <= smax; ++sp) {
+      const long long units = t * sp;
+      const long long waves = (units + sm_count - 1) / sm_count;
+      const double cost = static_cast<double>(waves) * (static_cast<double>((kb_total + sp - 1) / sp) + 10.0);
+      if (cost < best - 1e-9) { best = cost; splits = static_cast<int>(sp); }
+    }
+    dev.splits = splits;
+  } else if (use256 && tiles_for(256) * splits < sm_count && tiles_for(128) * splits > tiles_for(256) * splits) {
+    use256 = false;  // too few 256-wide tiles to occupy the machine: smaller tiles win
+  }
   if (mn) return use256 ? launch<256, true>(a, dev, sm_count, stream) : launch<128, true>(a, dev, sm_count, stream);
   return use256 ? launch<256, false>(a, dev, sm_count, stream) : launch<128, false>(a, dev, sm_count, stream);
 }

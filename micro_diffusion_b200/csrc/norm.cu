@@ -7,7 +7,6 @@
 namespace md {
 
 constexpr int kMaxVec = 16;  // float4 groups per lane  -> D <= 2048
-constexpr int kRowsPerBlock = 32;
 
 __device__ __forceinline__ float4 load4(const void* base, bool bf16, long long elem_off) {
   if (bf16) {
@@ -27,140 +26,173 @@ __device__ __forceinline__ void store4_bf16(void* base, long long elem_off, floa
   *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = raw;
 }
 
+// All row kernels issue every global load of a row BEFORE the first dependent use (separate load / compute
+// loops, compile-time trip counts, no per-load predicates on the fast path): one warp then has VEC x 16-byte
+// (or more) requests in flight instead of one, which is what these latency-bound kernels need to approach the
+// HBM roofline.  EXACT: D == 128 * VEC (the model widths 512 / 768 / 1024); otherwise a predicated generic path.
+
+template <bool XBF>
+__device__ __forceinline__ float4 ld4(const void* base, long long elem_off) {
+  if constexpr (XBF) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  } else {
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+  }
+}
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
 // ------------------------------------------------------------------------------------------ ln_fwd
+template <int VEC, bool EXACT, bool XBF>
 __global__ void __launch_bounds__(128)
-ln_fwd_kernel(const void* __restrict__ x, int x_bf16, const int32_t* __restrict__ src_rows,
-              const float* __restrict__ gamma, const float* __restrict__ shift, const float* __restrict__ scale,
-              long long ldmod, long long T, void* __restrict__ y, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, long long rows, int D, float eps) {
+ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, const float* __restrict__ gamma,
+              const float* __restrict__ shift, const float* __restrict__ scale, long long ldmod, long long T,
+              void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int D,
+              float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = 1LL * blockIdx.x * 4 + warp;
-  if (row >= rows) return;
-  const long long src = src_rows ? src_rows[row] : row;
   const int nvec = D >> 2;
-  float4 v[kMaxVec];
-  float s = 0.f;
+  for (long long row = 1LL * blockIdx.x * 4 + warp; row < rows; row += 1LL * gridDim.x * 4) {
+    const long long src = src_rows ? src_rows[row] : row;
+    float4 v[VEC];
 #pragma unroll
-  for (int j = 0; j < kMaxVec; ++j) {
-    const int i = lane + 32 * j;
-    if (i < nvec) {
-      v[j] = load4(x, x_bf16, src * D + 4LL * i);
-      s += v[j].x + v[j].y + v[j].z + v[j].w;
+    for (int j = 0; j < VEC; ++j) {
+      const int i = lane + 32 * j;
+      v[j] = (EXACT || i < nvec) ? ld4<XBF>(x, src * D + 4LL * i) : f4zero();
     }
-  }
-  const float mean = warp_sum(s) / D;
-  float ss = 0.f;
+    float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxVec; ++j) {
-    const int i = lane + 32 * j;
-    if (i < nvec) {
-      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-      ss += a * a + b * b + c * c + d * d;
+    for (int j = 0; j < VEC; ++j) s += v[j].x + v[j].y + v[j].z + v[j].w;
+    const float mean = warp_sum(s) / D;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (EXACT || lane + 32 * j < nvec) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        ss += a * a + b * b + c * c + d * d;
+      }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
-  if (lane == 0) {
-    if (mean_out) mean_out[row] = mean;
-    if (rstd_out) rstd_out[row] = rstd;
-  }
-  const long long smp = row / T;
-  const float* sh = shift ? shift + smp * ldmod : nullptr;
-  const float* sc = scale ? scale + smp * ldmod : nullptr;
+    const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    const long long smp = row / T;
+    const float* sh = shift ? shift + smp * ldmod : nullptr;
+    const float* sc = scale ? scale + smp * ldmod : nullptr;
 #pragma unroll
-  for (int j = 0; j < kMaxVec; ++j) {
-    const int i = lane + 32 * j;
-    if (i < nvec) {
-      float4 o;
-      o.x = (v[j].x - mean) * rstd; o.y = (v[j].y - mean) * rstd;
-      o.z = (v[j].z - mean) * rstd; o.w = (v[j].w - mean) * rstd;
-      if (gamma) {
-        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * i);
-        o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
+    for (int j = 0; j < VEC; ++j) {
+      const int i = lane + 32 * j;
+      if (EXACT || i < nvec) {
+        float4 o;
+        o.x = (v[j].x - mean) * rstd; o.y = (v[j].y - mean) * rstd;
+        o.z = (v[j].z - mean) * rstd; o.w = (v[j].w - mean) * rstd;
+        if (gamma) {
+          const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * i);
+          o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
+        }
+        if (sc) {
+          const float4 a = *reinterpret_cast<const float4*>(sc + 4 * i);
+          o.x *= 1.f + a.x; o.y *= 1.f + a.y; o.z *= 1.f + a.z; o.w *= 1.f + a.w;
+        }
+        if (sh) {
+          const float4 a = *reinterpret_cast<const float4*>(sh + 4 * i);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        store4_bf16(y, row * D + 4LL * i, o);
       }
-      if (sc) {
-        const float4 a = *reinterpret_cast<const float4*>(sc + 4 * i);
-        o.x *= 1.f + a.x; o.y *= 1.f + a.y; o.z *= 1.f + a.z; o.w *= 1.f + a.w;
-      }
-      if (sh) {
-        const float4 a = *reinterpret_cast<const float4*>(sh + 4 * i);
-        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-      }
-      store4_bf16(y, row * D + 4LL * i, o);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------ ln_bwd
-// grid (ceil(T / 32), samples); 4 warps, each 8 rows.  Per-column partials A = sum dy, Bc = sum dy*xhat
-// over the block's rows (all of one sample, so scale is constant): dshift += A, dscale += gamma*Bc,
-// dgamma += (1+scale)*Bc.
-template <int VEC>
+// grid (ceil(T / rpb), samples); 4 warps share the block's rows.  Per-column partials A = sum dy,
+// Bc = sum dy*xhat over the block's rows (all of one sample, so scale is constant): dshift += A,
+// dscale += gamma*Bc, dgamma += (1+scale)*Bc.
+template <int VEC, bool EXACT, bool XBF>
 __global__ void __launch_bounds__(128)
-ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, int x_bf16,
-              const int32_t* __restrict__ src_rows, const float* __restrict__ gamma,
-              const float* __restrict__ scale, long long ldmod, long long T, const float* __restrict__ mean,
-              const float* __restrict__ rstd, void* __restrict__ dx, int dx_mode, float* __restrict__ dgamma,
-              float* __restrict__ dshift, float* __restrict__ dscale, long long rows, int D) {
+ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const int32_t* __restrict__ src_rows,
+              const float* __restrict__ gamma, const float* __restrict__ scale, long long ldmod, long long T,
+              const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ dx, int dx_mode,
+              float* __restrict__ dgamma, float* __restrict__ dshift, float* __restrict__ dscale, long long rows,
+              int D, int rpb) {
   extern __shared__ float red[];  // [4][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long smp = blockIdx.y;
-  const long long t0 = 1LL * blockIdx.x * kRowsPerBlock;
-  const long long t1 = min(T, t0 + kRowsPerBlock);
+  const long long t0 = 1LL * blockIdx.x * rpb;
+  const long long t1 = min(T, t0 + rpb);
   const int nvec = D >> 2;
   const float* sc = scale ? scale + smp * ldmod : nullptr;
   const bool need_cols = (dgamma != nullptr) || (dshift != nullptr) || (dscale != nullptr);
 
-  float4 accA[VEC], accB[VEC];
+  // per-column weight d xhat / d y : gamma * (1 + scale), constant over the block
+  float4 w[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    accA[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accB[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int i = lane + 32 * j;
+    w[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (EXACT || i < nvec) {
+      if (gamma) w[j] = *reinterpret_cast<const float4*>(gamma + 4 * i);
+      if (sc) {
+        const float4 a = *reinterpret_cast<const float4*>(sc + 4 * i);
+        w[j].x *= 1.f + a.x; w[j].y *= 1.f + a.y; w[j].z *= 1.f + a.z; w[j].w *= 1.f + a.w;
+      }
+    }
   }
+  float4 accA[VEC], accB[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) accA[j] = accB[j] = f4zero();
+
   for (long long t = t0 + warp; t < t1; t += 4) {
     const long long row = smp * T + t;
     if (row >= rows) break;
     const long long src = src_rows ? src_rows[row] : row;
-    const float mu = mean[row], rs = rstd[row];
-    float4 g[VEC], xh[VEC];
-    float s1 = 0.f, s2 = 0.f;
+    const long long drow = (dx_mode == 2) ? src : row;
+    float4 d[VEC], xh[VEC], old[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int i = lane + 32 * j;
-      if (i < nvec) {
-        const float4 d = load4(dy, true, row * D + 4LL * i);
-        const float4 xv = load4(x, x_bf16, src * D + 4LL * i);
-        xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        accA[j].x += d.x; accA[j].y += d.y; accA[j].z += d.z; accA[j].w += d.w;
-        accB[j].x += d.x * xh[j].x; accB[j].y += d.y * xh[j].y;
-        accB[j].z += d.z * xh[j].z; accB[j].w += d.w * xh[j].w;
-        float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (gamma) w = *reinterpret_cast<const float4*>(gamma + 4 * i);
-        if (sc) {
-          const float4 a = *reinterpret_cast<const float4*>(sc + 4 * i);
-          w.x *= 1.f + a.x; w.y *= 1.f + a.y; w.z *= 1.f + a.z; w.w *= 1.f + a.w;
-        }
-        g[j] = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);  // d loss / d xhat
-        s1 += g[j].x + g[j].y + g[j].z + g[j].w;
-        s2 += g[j].x * xh[j].x + g[j].y * xh[j].y + g[j].z * xh[j].z + g[j].w * xh[j].w;
+      const bool ok = EXACT || i < nvec;
+      d[j] = ok ? ld4<true>(dy, row * D + 4LL * i) : f4zero();
+      xh[j] = ok ? ld4<XBF>(x, src * D + 4LL * i) : f4zero();
+    }
+    if (dx != nullptr && dx_mode != 1) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int i = lane + 32 * j;
+        old[j] = (EXACT || i < nvec) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dx) + drow * D + 4LL * i)
+                                     : f4zero();
+      }
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (EXACT || lane + 32 * j < nvec) {
+        xh[j] = make_float4((xh[j].x - mu) * rs, (xh[j].y - mu) * rs, (xh[j].z - mu) * rs, (xh[j].w - mu) * rs);
+        accA[j].x += d[j].x; accA[j].y += d[j].y; accA[j].z += d[j].z; accA[j].w += d[j].w;
+        accB[j].x += d[j].x * xh[j].x; accB[j].y += d[j].y * xh[j].y;
+        accB[j].z += d[j].z * xh[j].z; accB[j].w += d[j].w * xh[j].w;
+        d[j] = make_float4(d[j].x * w[j].x, d[j].y * w[j].y, d[j].z * w[j].z, d[j].w * w[j].w);  // d loss / d xhat
+        s1 += d[j].x + d[j].y + d[j].z + d[j].w;
+        s2 += d[j].x * xh[j].x + d[j].y * xh[j].y + d[j].z * xh[j].z + d[j].w * xh[j].w;
       }
     }
     const float m1 = warp_sum(s1) / D, m2 = warp_sum(s2) / D;
     if (dx != nullptr) {
-      const long long drow = (dx_mode == 2) ? src : row;
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const int i = lane + 32 * j;
-        if (i < nvec) {
+        if (EXACT || i < nvec) {
           float4 o;
-          o.x = rs * (g[j].x - m1 - xh[j].x * m2); o.y = rs * (g[j].y - m1 - xh[j].y * m2);
-          o.z = rs * (g[j].z - m1 - xh[j].z * m2); o.w = rs * (g[j].w - m1 - xh[j].w * m2);
+          o.x = rs * (d[j].x - m1 - xh[j].x * m2); o.y = rs * (d[j].y - m1 - xh[j].y * m2);
+          o.z = rs * (d[j].z - m1 - xh[j].z * m2); o.w = rs * (d[j].w - m1 - xh[j].w * m2);
           if (dx_mode == 1) {
             store4_bf16(dx, drow * D + 4LL * i, o);
           } else {
-            float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(dx) + drow * D + 4LL * i);
-            float4 c = *p;
-            c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
-            *p = c;
+            o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w;
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(dx) + drow * D + 4LL * i) = o;
           }
         }
       }
@@ -173,7 +205,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, int x_bf1
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int i = lane + 32 * j;
-      if (i < nvec) *reinterpret_cast<float4*>(red + warp * D + 4 * i) = pass == 0 ? accA[j] : accB[j];
+      if (EXACT || i < nvec) *reinterpret_cast<float4*>(red + warp * D + 4 * i) = pass == 0 ? accA[j] : accB[j];
     }
     __syncthreads();
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
@@ -204,127 +236,143 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
   return r;
 }
-constexpr int kRnVec = 8;  // uint4 groups per lane -> W <= 2048
-
+// VEC = uint4 groups per lane (8 bf16 each): W <= 256 * VEC
+template <int VEC>
 __global__ void __launch_bounds__(128)
 rownorm_fwd_kernel(__nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ rstd_out, long long rows, int W,
                    float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = 1LL * blockIdx.x * 4 + warp;
-  if (row >= rows) return;
-  __nv_bfloat16* p = x + row * ld;
   const int nvec = W >> 3;
-  float v[kRnVec][8];
-  float s = 0.f;
+  for (long long row = 1LL * blockIdx.x * 4 + warp; row < rows; row += 1LL * gridDim.x * 4) {
+    __nv_bfloat16* p = x + row * ld;
+    uint4 raw[VEC];
 #pragma unroll
-  for (int j = 0; j < kRnVec; ++j) {
-    const int i = lane + 32 * j;
-    if (i < nvec) {
-      unpack8(*reinterpret_cast<const uint4*>(p + 8 * i), v[j]);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s += v[j][e];
+    for (int j = 0; j < VEC; ++j) {
+      const int i = lane + 32 * j;
+      raw[j] = i < nvec ? *reinterpret_cast<const uint4*>(p + 8 * i) : make_uint4(0, 0, 0, 0);
     }
-  }
-  const float mean = warp_sum(s) / W;
-  float ss = 0.f;
+    float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < kRnVec; ++j) {
-    const int i = lane + 32 * j;
-    if (i < nvec) {
+    for (int j = 0; j < VEC; ++j) {
+      float v[8];
+      unpack8(raw[j], v);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = v[j][e] - mean;
-        ss += d * d;
+      for (int e = 0; e < 8; ++e) s += v[e];
+    }
+    const float mean = warp_sum(s) / W;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (lane + 32 * j < nvec) {
+        float v[8];
+        unpack8(raw[j], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += (v[e] - mean) * (v[e] - mean);
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / W + eps);
-  if (lane == 0) rstd_out[row] = rstd;
+    const float rstd = rsqrtf(warp_sum(ss) / W + eps);
+    if (lane == 0) rstd_out[row] = rstd;
 #pragma unroll
-  for (int j = 0; j < kRnVec; ++j) {
-    const int i = lane + 32 * j;
-    if (i < nvec) {
-      float o[8];
+    for (int j = 0; j < VEC; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        float v[8];
+        unpack8(raw[j], v);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd;
-      *reinterpret_cast<uint4*>(p + 8 * i) = pack8(o);
+        for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean) * rstd;
+        *reinterpret_cast<uint4*>(p + 8 * i) = pack8(v);
+      }
     }
   }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(128)
 rownorm_bwd_kernel(__nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ xhat,
                    long long ld_x, const float* __restrict__ rstd, long long rows, int W) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = 1LL * blockIdx.x * 4 + warp;
-  if (row >= rows) return;
-  __nv_bfloat16* pd = dy + row * ld_dy;
-  const __nv_bfloat16* px = xhat + row * ld_x;
   const int nvec = W >> 3;
-  float d[kRnVec][8], xh[kRnVec][8];
-  float s1 = 0.f, s2 = 0.f;
+  for (long long row = 1LL * blockIdx.x * 4 + warp; row < rows; row += 1LL * gridDim.x * 4) {
+    __nv_bfloat16* pd = dy + row * ld_dy;
+    const __nv_bfloat16* px = xhat + row * ld_x;
+    uint4 rd[VEC], rx[VEC];
 #pragma unroll
-  for (int j = 0; j < kRnVec; ++j) {
-    const int i = lane + 32 * j;
-    if (i < nvec) {
-      unpack8(*reinterpret_cast<const uint4*>(pd + 8 * i), d[j]);
-      unpack8(*reinterpret_cast<const uint4*>(px + 8 * i), xh[j]);
+    for (int j = 0; j < VEC; ++j) {
+      const int i = lane + 32 * j;
+      rd[j] = i < nvec ? *reinterpret_cast<const uint4*>(pd + 8 * i) : make_uint4(0, 0, 0, 0);
+      rx[j] = i < nvec ? *reinterpret_cast<const uint4*>(px + 8 * i) : make_uint4(0, 0, 0, 0);
+    }
+    const float rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float d[8], xh[8];
+      unpack8(rd[j], d);
+      unpack8(rx[j], xh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        s1 += d[j][e];
-        s2 += d[j][e] * xh[j][e];
+        s1 += d[e];
+        s2 += d[e] * xh[e];
       }
     }
-  }
-  const float m1 = warp_sum(s1) / W, m2 = warp_sum(s2) / W;
-  const float rs = rstd[row];
+    const float m1 = warp_sum(s1) / W, m2 = warp_sum(s2) / W;
 #pragma unroll
-  for (int j = 0; j < kRnVec; ++j) {
-    const int i = lane + 32 * j;
-    if (i < nvec) {
-      float o[8];
+    for (int j = 0; j < VEC; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        float d[8], xh[8];
+        unpack8(rd[j], d);
+        unpack8(rx[j], xh);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = rs * (d[j][e] - m1 - xh[j][e] * m2);
-      *reinterpret_cast<uint4*>(pd + 8 * i) = pack8(o);
+        for (int e = 0; e < 8; ++e) d[e] = rs * (d[e] - m1 - xh[e] * m2);
+        *reinterpret_cast<uint4*>(pd + 8 * i) = pack8(d);
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------- gate_bwd
-template <int VEC>
+template <int VEC, bool EXACT>
 __global__ void __launch_bounds__(128)
 gate_bwd_kernel(const float* __restrict__ dres, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
                 long long ldmod, long long T, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate,
-                long long rows, int D) {
+                long long rows, int D, int rpb) {
   extern __shared__ float red[];  // [4][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long smp = blockIdx.y;
-  const long long t0 = 1LL * blockIdx.x * kRowsPerBlock;
-  const long long t1 = min(T, t0 + kRowsPerBlock);
+  const long long t0 = 1LL * blockIdx.x * rpb;
+  const long long t1 = min(T, t0 + rpb);
   const int nvec = D >> 2;
   const float* gt = gate ? gate + smp * ldmod : nullptr;
   const bool need = (dgate != nullptr) && (y != nullptr);
-  float4 acc[VEC];
+  float4 g[VEC], acc[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < VEC; ++j) {
+    const int i = lane + 32 * j;
+    acc[j] = f4zero();
+    g[j] = (gt && (EXACT || i < nvec)) ? *reinterpret_cast<const float4*>(gt + 4 * i) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
   for (long long t = t0 + warp; t < t1; t += 4) {
     const long long row = smp * T + t;
     if (row >= rows) break;
+    float4 d[VEC], yv[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int i = lane + 32 * j;
-      if (i < nvec) {
-        const float4 d = *reinterpret_cast<const float4*>(dres + row * D + 4LL * i);
+      const bool ok = EXACT || i < nvec;
+      d[j] = ok ? *reinterpret_cast<const float4*>(dres + row * D + 4LL * i) : f4zero();
+      if (need) yv[j] = ok ? ld4<true>(y, row * D + 4LL * i) : f4zero();
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int i = lane + 32 * j;
+      if (EXACT || i < nvec) {
         if (need) {
-          const float4 yv = load4(y, true, row * D + 4LL * i);
-          acc[j].x += d.x * yv.x; acc[j].y += d.y * yv.y; acc[j].z += d.z * yv.z; acc[j].w += d.w * yv.w;
+          acc[j].x += d[j].x * yv[j].x; acc[j].y += d[j].y * yv[j].y;
+          acc[j].z += d[j].z * yv[j].z; acc[j].w += d[j].w * yv[j].w;
         }
-        float4 o = d;
-        if (gt) {
-          const float4 g = *reinterpret_cast<const float4*>(gt + 4 * i);
-          o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w;
-        }
-        store4_bf16(dy, row * D + 4LL * i, o);
+        store4_bf16(dy, row * D + 4LL * i,
+                    make_float4(d[j].x * g[j].x, d[j].y * g[j].y, d[j].z * g[j].z, d[j].w * g[j].w));
       }
     }
   }
@@ -332,7 +380,7 @@ gate_bwd_kernel(const float* __restrict__ dres, const __nv_bfloat16* __restrict_
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const int i = lane + 32 * j;
-    if (i < nvec) *reinterpret_cast<float4*>(red + warp * D + 4 * i) = acc[j];
+    if (EXACT || i < nvec) *reinterpret_cast<float4*>(red + warp * D + 4 * i) = acc[j];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x)
@@ -353,14 +401,42 @@ static int check_ln_dims(const char* what, long long rows, long long D, long lon
 
 using namespace md;
 
+static int row_grid(long long rows) {
+  long long blocks = (rows + 3) / 4;
+  const long long cap = 148LL * 12;
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks < 1 ? 1 : blocks);
+}
+static int rows_per_block(long long T, long long samples) {
+  // enough CTAs to fill the machine a few times over, few enough to keep the column atomics cheap
+  int rpb = 32;
+  while (rpb > 4 && ((T + rpb - 1) / rpb) * samples < 148LL * 6) rpb >>= 1;
+  return rpb;
+}
+
 extern "C" int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const float* gamma, const float* shift,
                          const float* scale, int64_t ldmod, int64_t T, void* y, float* mean, float* rstd,
                          int64_t rows, int64_t D, float eps, void* stream) {
   if (int rc = check_ln_dims("md_ln_fwd", rows, D, T)) return rc;
   if (rows == 0) return 0;
   if (!x || !y) return md_set_error(MD_ERR_INVALID, "md_ln_fwd: null pointer");
-  ln_fwd_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, x_bf16, src_rows, gamma, shift, scale, ldmod, T, y, mean, rstd, rows, static_cast<int>(D), eps);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = row_grid(rows);
+#define LN_FWD(VEC, EXACT)                                                                                             \
+  do {                                                                                                                 \
+    if (x_bf16)                                                                                                        \
+      ln_fwd_kernel<VEC, EXACT, true><<<grid, 128, 0, st>>>(x, src_rows, gamma, shift, scale, ldmod, T, y, mean, rstd, \
+                                                            rows, static_cast<int>(D), eps);                          \
+    else                                                                                                               \
+      ln_fwd_kernel<VEC, EXACT, false><<<grid, 128, 0, st>>>(x, src_rows, gamma, shift, scale, ldmod, T, y, mean,     \
+                                                             rstd, rows, static_cast<int>(D), eps);                   \
+  } while (0)
+  if (D == 1024) LN_FWD(8, true);
+  else if (D == 768) LN_FWD(6, true);
+  else if (D == 512) LN_FWD(4, true);
+  else if (D <= 1024) LN_FWD(8, false);
+  else LN_FWD(16, false);
+#undef LN_FWD
   return check_launch("md_ln_fwd");
 }
 
@@ -374,26 +450,42 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
   if (rows % T != 0) return md_set_error(MD_ERR_INVALID, "md_ln_bwd: rows must be a multiple of T");
   if (dx_mode < 0 || dx_mode > 2 || (dx_mode == 2 && !src_rows))
     return md_set_error(MD_ERR_INVALID, "md_ln_bwd: bad dx_mode");
-  dim3 grid(static_cast<unsigned>((T + kRowsPerBlock - 1) / kRowsPerBlock), static_cast<unsigned>(rows / T));
+  const int rpb = rows_per_block(T, rows / T);
+  dim3 grid(static_cast<unsigned>((T + rpb - 1) / rpb), static_cast<unsigned>(rows / T));
   const size_t smem = 4 * D * sizeof(float);
-  if (D <= 1024)
-    ln_bwd_kernel<8><<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dy, x, x_bf16, src_rows, gamma, scale, ldmod, T, mean, rstd, dx, dx_mode, dgamma, dshift, dscale, rows,
-        static_cast<int>(D));
-  else
-    ln_bwd_kernel<16><<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dy, x, x_bf16, src_rows, gamma, scale, ldmod, T, mean, rstd, dx, dx_mode, dgamma, dshift, dscale, rows,
-        static_cast<int>(D));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define LN_BWD(VEC, EXACT)                                                                                            \
+  do {                                                                                                                \
+    if (x_bf16)                                                                                                       \
+      ln_bwd_kernel<VEC, EXACT, true><<<grid, 128, smem, st>>>(dy, x, src_rows, gamma, scale, ldmod, T, mean, rstd,  \
+                                                               dx, dx_mode, dgamma, dshift, dscale, rows,            \
+                                                               static_cast<int>(D), rpb);                            \
+    else                                                                                                              \
+      ln_bwd_kernel<VEC, EXACT, false><<<grid, 128, smem, st>>>(dy, x, src_rows, gamma, scale, ldmod, T, mean, rstd, \
+                                                                dx, dx_mode, dgamma, dshift, dscale, rows,           \
+                                                                static_cast<int>(D), rpb);                           \
+  } while (0)
+  if (D == 1024) LN_BWD(8, true);
+  else if (D == 768) LN_BWD(6, true);
+  else if (D == 512) LN_BWD(4, true);
+  else if (D <= 1024) LN_BWD(8, false);
+  else LN_BWD(16, false);
+#undef LN_BWD
   return check_launch("md_ln_bwd");
 }
 
 extern "C" int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, float eps, void* stream) {
   if (rows == 0) return 0;
   if (!x || !rstd) return md_set_error(MD_ERR_INVALID, "md_rownorm_fwd: null pointer");
-  if (W % 8 != 0 || W > 8 * 32 * kRnVec || ld % 8 != 0)
+  if (W % 8 != 0 || W > 2048 || ld % 8 != 0)
     return md_set_error(MD_ERR_UNSUPPORTED, "md_rownorm_fwd: need W % 8 == 0, W <= 2048, ld % 8 == 0");
-  rownorm_fwd_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(x), ld, rstd, rows, static_cast<int>(W), eps);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (W <= 1024)
+    rownorm_fwd_kernel<4><<<row_grid(rows), 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, rstd, rows,
+                                                          static_cast<int>(W), eps);
+  else
+    rownorm_fwd_kernel<8><<<row_grid(rows), 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, rstd, rows,
+                                                          static_cast<int>(W), eps);
   return check_launch("md_rownorm_fwd");
 }
 
@@ -401,11 +493,17 @@ extern "C" int md_rownorm_bwd(void* dy, int64_t ld_dy, const void* xhat, int64_t
                               int64_t W, void* stream) {
   if (rows == 0) return 0;
   if (!dy || !xhat || !rstd) return md_set_error(MD_ERR_INVALID, "md_rownorm_bwd: null pointer");
-  if (W % 8 != 0 || W > 8 * 32 * kRnVec || ld_dy % 8 != 0 || ld_x % 8 != 0)
+  if (W % 8 != 0 || W > 2048 || ld_dy % 8 != 0 || ld_x % 8 != 0)
     return md_set_error(MD_ERR_UNSUPPORTED, "md_rownorm_bwd: need W % 8 == 0, W <= 2048, ld % 8 == 0");
-  rownorm_bwd_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(dy), ld_dy, reinterpret_cast<const __nv_bfloat16*>(xhat), ld_x, rstd, rows,
-      static_cast<int>(W));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (W <= 1024)
+    rownorm_bwd_kernel<4><<<row_grid(rows), 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(dy), ld_dy,
+                                                          reinterpret_cast<const __nv_bfloat16*>(xhat), ld_x, rstd, rows,
+                                                          static_cast<int>(W));
+  else
+    rownorm_bwd_kernel<8><<<row_grid(rows), 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(dy), ld_dy,
+                                                          reinterpret_cast<const __nv_bfloat16*>(xhat), ld_x, rstd, rows,
+                                                          static_cast<int>(W));
   return check_launch("md_rownorm_bwd");
 }
 
@@ -415,15 +513,19 @@ extern "C" int md_gate_bwd(const float* dres, const void* y, const float* gate, 
   if (rows == 0) return 0;
   if (!dres || !dy) return md_set_error(MD_ERR_INVALID, "md_gate_bwd: null pointer");
   if (rows % T != 0) return md_set_error(MD_ERR_INVALID, "md_gate_bwd: rows must be a multiple of T");
-  dim3 grid(static_cast<unsigned>((T + kRowsPerBlock - 1) / kRowsPerBlock), static_cast<unsigned>(rows / T));
+  const int rpb = rows_per_block(T, rows / T);
+  dim3 grid(static_cast<unsigned>((T + rpb - 1) / rpb), static_cast<unsigned>(rows / T));
   const size_t smem = 4 * D * sizeof(float);
-  if (D <= 1024)
-    gate_bwd_kernel<8><<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dres, reinterpret_cast<const __nv_bfloat16*>(y), gate, ldmod, T, reinterpret_cast<__nv_bfloat16*>(dy), dgate,
-        rows, static_cast<int>(D));
-  else
-    gate_bwd_kernel<16><<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dres, reinterpret_cast<const __nv_bfloat16*>(y), gate, ldmod, T, reinterpret_cast<__nv_bfloat16*>(dy), dgate,
-        rows, static_cast<int>(D));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(y);
+  __nv_bfloat16* dyb = reinterpret_cast<__nv_bfloat16*>(dy);
+#define GATE(VEC, EXACT) \
+  gate_bwd_kernel<VEC, EXACT><<<grid, 128, smem, st>>>(dres, yb, gate, ldmod, T, dyb, dgate, rows, static_cast<int>(D), rpb)
+  if (D == 1024) GATE(8, true);
+  else if (D == 768) GATE(6, true);
+  else if (D == 512) GATE(4, true);
+  else if (D <= 1024) GATE(8, false);
+  else GATE(16, false);
+#undef GATE
   return check_launch("md_gate_bwd");
 }

@@ -34,16 +34,9 @@ class Engine:
 
     # ================================================================== helpers
     def _wgrad(self, dY, X, G):
-        """G[P,Q] (+)= dY[r,P]^T X[r,Q]  (reduction over rows), split over the rows to fill the SMs."""
-        if dY.dim() == 3:
-            batch, R, Pd = dY.shape
-            Q = X.shape[2]
-        else:
-            batch, (R, Pd), Q = 1, dY.shape, X.shape[1]
-        tiles = batch * ((Pd + 127) // 128) * ((Q + 127) // 128)
-        want = max(1, (2 * self.sm_count + tiles - 1) // tiles)
-        splits = max(1, min(want, R // 512 if R >= 512 else 1))
-        self.ops.gemm(dY, X, G, layout=TN, epi=EPI_ATOMIC, splits=splits)
+        """G[P,Q] (+)= dY[r,P]^T X[r,Q]  (reduction over the rows r); the library picks the split of the
+        reduction that fills the SMs (splits=0)."""
+        self.ops.gemm(dY, X, G, layout=TN, epi=EPI_ATOMIC, splits=0)
 
     def _mods(self, key, D, mod):
         o = self.store.layout.ada_offset[key]
@@ -270,8 +263,8 @@ class Engine:
         o.cast_bf16(dmod, dmod_bf)
         self._wgrad(dmod_bf, s.cact, st.G("ada"))
         o.colsum(dmod, st.g_ada_bias)
-        dcact = o.empty((B, D), F32)
-        o.gemm(dmod_bf, st.WT("ada"), dcact, epi=EPI_F32)
+        dcact = o.zeros((B, D), F32)  # K = sum(6D) ~ 2e5 with only a handful of output tiles: split the reduction
+        o.gemm(dmod_bf, st.WT("ada"), dcact, epi=EPI_ATOMIC, splits=0)
         dc = o.empty((B, D), F32)
         o.gelu_tanh_f32_bwd(dcact, s.c, dc, False)
         dc_bf = o.empty((B, D), BF16)

@@ -172,7 +172,7 @@ class CudaOps:
         rc = self.lib.md_gemm_bf16(C.byref(a), self._stream())
         if prof is not None:
             e1.record()
-            prof.append(("md_gemm_bf16/" + ("tn" if layout == TN else "nt"), e0, e1, flops))
+            prof.append((f"md_gemm_bf16/{'tn' if layout == TN else 'nt'} M={M} N={N} K={K} b={int(a.batch)} epi={epi} s={splits}", e0, e1, flops))
         self.launches += 1
         if rc != 0:
             raise MicroditLibraryError(f"md_gemm_bf16 failed ({rc}): {self.lib.md_last_error().decode()} "
