@@ -12,9 +12,18 @@
 //                     strided (MN-major UMMA operands) -- the weight-gradient contraction.
 // Roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
 // warps4-11 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31, column half (w-4)/4 of the tile).
+//
+// kCtas = 2 is the Blackwell CTA-pair mode: two CTAs of a cluster (adjacent SMs) run ONE tcgen05.mma.cta_group::2
+// with M = 256 (128 rows of D in each CTA's TMEM); every CTA stages its own 128 rows of A and only HALF of the B
+// tile, so shared-memory traffic per flop drops by a third and the pair reads B once from L2.  Measured on B200
+// the 1-CTA 128x256 mainloop is shared-memory-bandwidth bound (TMA writes + UMMA reads ~192 B/clk vs 128 B/clk).
+// Protocol: both CTAs issue their TMA loads with .cta_group::2 so the bytes are credited to the LEADER's (even
+// CTA's) full barrier; only the leader issues MMAs; tcgen05.commit multicasts the stage-free / accumulator-ready
+// arrivals to both CTAs; both epilogues arrive on the leader's accumulator-free barrier.
 #include "gemm_tcgen05.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -25,12 +34,12 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 384;  // 4 control warps + 8 epilogue warps
 
-template <int BLOCK_N>
+template <int BLOCK_N, int kCtas = 1>
 struct GemmCfg {
   static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
-  static constexpr int kStageBytesB = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytesB = (BLOCK_N / kCtas) * kBlockK * 2;  // a CTA of a pair stages half of B
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int kStages = (kStageBytes > 40 * 1024) ? 4 : (kStageBytes > 30 * 1024 ? 6 : 7);
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 256 or 512 (power of two)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -60,11 +69,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BLOCK_N, bool kMN>
+template <int BLOCK_N, bool kMN, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmDev p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, kCtas>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -88,28 +97,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 8 * kCtas);  // one arrive per epilogue warp (of both CTAs in pair mode)
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (kCtas == 2) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int cta_rank = (kCtas == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool is_leader = cta_rank == 0;
 
   // Tile enumeration: n fastest so that CTAs resident together share the same A rows through L2.
-  const int m_blocks = (p.M + kBlockM - 1) / kBlockM;
+  // In pair mode a "tile" is 256 x BLOCK_N: m_blocks counts 256-row units and this CTA owns rows
+  // (mb * kCtas + cta_rank) * 128 .. +127 of it (an odd tail is an all-out-of-bounds 128-row block: TMA zero-fills,
+  // the epilogue skips it, the protocol stays symmetric).
+  const int m_blocks = (p.M + kBlockM * kCtas - 1) / (kBlockM * kCtas);
   const int n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int kb_total = (p.K + kBlockK - 1) / kBlockK;
   const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
   const long long tiles = 1LL * p.batch * p.splits * m_blocks * n_blocks;
+  const long long tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (long long tile = tile0; tile < tiles; tile += tile_step) {
         long long t = tile;
         const int nb = t % n_blocks; t /= n_blocks;
         const int mb = t % m_blocks; t /= m_blocks;
@@ -123,28 +142,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kStageBytesA;
-          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          const int m0 = (mb * kCtas + cta_rank) * kBlockM;                 // this CTA's 128 rows of A / D
+          const int n0 = nb * BLOCK_N + cta_rank * (BLOCK_N / kCtas);       // this CTA's share of the B tile
+          if (is_leader) mbar_expect_tx(&full_bar[s], Cfg::kStageBytes * kCtas);
+          auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1) {
+            if constexpr (kCtas == 2) tma_load_3d_2sm(tm, &full_bar[s], dst, c0, c1, bz);
+            else tma_load_3d(tm, &full_bar[s], dst, c0, c1, bz);
+          };
           if constexpr (!kMN) {
-            tma_load_3d(&tmA, &full_bar[s], sa, kb * kBlockK, mb * kBlockM, bz);
-            tma_load_3d(&tmB, &full_bar[s], sb, kb * kBlockK, nb * BLOCK_N, bz);
+            load(&tmA, sa, kb * kBlockK, m0);
+            load(&tmB, sb, kb * kBlockK, n0);
           } else {
             // boxes of 64 (MN, contiguous) x 64 (reduction rows); one box per 64 MN elements
 #pragma unroll
-            for (int j = 0; j < kBlockM / 64; ++j)
-              tma_load_3d(&tmA, &full_bar[s], sa + j * (kBlockK * 128), mb * kBlockM + j * 64,
-                          kb * kBlockK, bz);
+            for (int j = 0; j < kBlockM / 64; ++j) load(&tmA, sa + j * (kBlockK * 128), m0 + j * 64, kb * kBlockK);
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_3d(&tmB, &full_bar[s], sb + j * (kBlockK * 128), nb * BLOCK_N + j * 64,
-                          kb * kBlockK, bz);
+            for (int j = 0; j < BLOCK_N / kCtas / 64; ++j)
+              load(&tmB, sb + j * (kBlockK * 128), n0 + j * 64, kb * kBlockK);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, kMN, kMN);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * kCtas, BLOCK_N, kMN, kMN);
       // K-major: 8-row groups 1024 B apart (SBO), LBO unused (1).  MN-major: 64-element MN groups one
       // whole box apart (LBO = 64 rows * 128 B), 8-row reduction groups 1024 B apart (SBO).
       constexpr uint32_t lbo = kMN ? (kBlockK * 128) : 16;
@@ -152,7 +174,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t kstep = kMN ? (kUmmaK * 128) : (kUmmaK * 2);  // bytes per UMMA_K advance
       uint32_t it = 0;
       uint32_t acc_it = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++acc_it) {
+      for (long long tile = tile0; tile < tiles; tile += tile_step, ++acc_it) {
         long long t = tile / (1LL * n_blocks * m_blocks);
         const int sp = t % p.splits;
         const int kb0 = sp * kb_per_split;
@@ -173,11 +195,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = umma_smem_desc(sa + k * kstep, lbo, sbo);
             const uint64_t db = umma_smem_desc(sb + k * kstep, lbo, sbo);
-            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (kCtas == 2) umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (kCtas == 2) umma_commit_2sm(&empty_bar[s], 3);
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete
+        // accumulator complete (signalled to both epilogues of a pair)
+        if constexpr (kCtas == 2) umma_commit_2sm(&tfull_bar[as], 3);
+        else umma_commit(&tfull_bar[as]);
       }
     }
   } else if (warp >= 4) {
@@ -187,7 +214,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 4) >> 2;
     constexpr int kChunksPerWarp = BLOCK_N / 64;  // 32-column chunks per warp
     uint32_t acc_it = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++acc_it) {
+    for (long long tile = tile0; tile < tiles; tile += tile_step, ++acc_it) {
       long long t = tile;
       const int nb = t % n_blocks; t /= n_blocks;
       const int mb = t % m_blocks; t /= m_blocks;
@@ -198,7 +225,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int as = acc_it % Cfg::kAccStages;
       const uint32_t aph = (acc_it / Cfg::kAccStages) & 1;
 
-      const int row = mb * kBlockM + q * 32 + lane;
+      const int row = (mb * kCtas + cta_rank) * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
       const long long crow = 1LL * bz * p.strideC + 1LL * row * p.ldc;
       const long long rrow = 1LL * bz * p.strideC + 1LL * (p.res_mod > 0 ? row % p.res_mod : row) * p.ldc;
@@ -356,15 +383,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if constexpr (kCtas == 2) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();  // nobody exits / frees TMEM while the peer can still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (kCtas == 2) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -412,15 +444,15 @@ static int make_map(CUtensorMap* map, const void* ptr, long long cols, long long
   return 0;
 }
 
-template <int BLOCK_N, bool kMN>
+template <int BLOCK_N, bool kMN, int kCtas>
 static int launch(const md_gemm_args* a, const GemmDev& dev, int sm_count, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, kCtas>;
   CUtensorMap tmA, tmB;
   int rc;
   if (!kMN) {
     rc = make_map(&tmA, a->A, a->K, a->M, a->batch, a->lda, a->strideA, kBlockM);
     if (rc) return rc;
-    rc = make_map(&tmB, a->B, a->K, a->N, a->batch, a->ldb, a->strideB, BLOCK_N);
+    rc = make_map(&tmB, a->B, a->K, a->N, a->batch, a->ldb, a->strideB, BLOCK_N / kCtas);
     if (rc) return rc;
   } else {
     rc = make_map(&tmA, a->A, a->M, a->K, a->batch, a->lda, a->strideA, kBlockK);
@@ -428,19 +460,31 @@ static int launch(const md_gemm_args* a, const GemmDev& dev, int sm_count, cudaS
     rc = make_map(&tmB, a->B, a->N, a->K, a->batch, a->ldb, a->strideB, kBlockK);
     if (rc) return rc;
   }
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, kMN>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, kMN, kCtas>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
     attr_set = true;
   }
-  const long long m_blocks = (a->M + kBlockM - 1) / kBlockM;
+  const long long m_blocks = (a->M + kBlockM * kCtas - 1) / (kBlockM * kCtas);
   const long long n_blocks = (a->N + BLOCK_N - 1) / BLOCK_N;
   const long long tiles = a->batch * dev.splits * m_blocks * n_blocks;
-  const int grid = static_cast<int>(tiles < sm_count ? tiles : sm_count);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, dev);
-  cudaError_t e = cudaGetLastError();
+  const long long slots = sm_count / kCtas;  // CTAs (1-CTA mode) or CTA pairs resident at once
+  const int grid = static_cast<int>((tiles < slots ? tiles : slots) * kCtas);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, dev);
   if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
   return 0;
 }
@@ -514,6 +558,17 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   } else if (use256 && tiles_for(256) * splits < sm_count && tiles_for(128) * splits > tiles_for(256) * splits) {
     use256 = false;  // too few 256-wide tiles to occupy the machine: smaller tiles win
   }
-  if (mn) return use256 ? launch<256, true>(a, dev, sm_count, stream) : launch<128, true>(a, dev, sm_count, stream);
-  return use256 ? launch<256, false>(a, dev, sm_count, stream) : launch<128, false>(a, dev, sm_count, stream);
+  // CTA pairs (cta_group::2, 256-row tiles) whenever there are at least two 128-row blocks; MD_GEMM_CTAS=1|2 overrides.
+  static int ctas_forced = -1;
+  if (ctas_forced == -1) {
+    const char* e = getenv("MD_GEMM_CTAS");
+    ctas_forced = e ? atoi(e) : 0;
+  }
+  const bool pair = ctas_forced == 2 || (ctas_forced == 0 && a->M > kBlockM);
+  if (pair) {
+    if (mn) return use256 ? launch<256, true, 2>(a, dev, sm_count, stream) : launch<128, true, 2>(a, dev, sm_count, stream);
+    return use256 ? launch<256, false, 2>(a, dev, sm_count, stream) : launch<128, false, 2>(a, dev, sm_count, stream);
+  }
+  if (mn) return use256 ? launch<256, true, 1>(a, dev, sm_count, stream) : launch<128, true, 1>(a, dev, sm_count, stream);
+  return use256 ? launch<256, false, 1>(a, dev, sm_count, stream) : launch<128, false, 1>(a, dev, sm_count, stream);
 }

@@ -8,6 +8,7 @@
 namespace md {
 
 constexpr int kMaxE = 16;
+constexpr int kChunk = 4;  // 16-byte chunks a lane keeps in flight (D <= 1024 in one slab)
 
 __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
@@ -39,15 +40,28 @@ moe_gate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
     float acc[kMaxE];
 #pragma unroll
     for (int e = 0; e < kMaxE; ++e) acc[e] = 0.f;
-    for (int i = lane; i < nvec; i += 32) {
-      float xv[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + row * D + 8 * i), xv);
+    for (int base = 0; base < nvec; base += 32 * kChunk) {
+      uint4 raw[kChunk];
 #pragma unroll
-      for (int e = 0; e < kMaxE; ++e) {
-        if (e < E) {
-          const float* w = swg + e * D + 8 * i;
+      for (int j = 0; j < kChunk; ++j) {  // all loads of this slab first
+        const int i = base + lane + 32 * j;
+        raw[j] = i < nvec ? *reinterpret_cast<const uint4*>(x + row * D + 8 * i) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[e] += xv[q] * w[q];
+      for (int j = 0; j < kChunk; ++j) {
+        const int i = base + lane + 32 * j;
+        if (i < nvec) {
+          float xv[8];
+          unpack8(raw[j], xv);
+#pragma unroll
+          for (int e = 0; e < kMaxE; ++e) {
+            if (e < E) {
+              const float4 w0 = *reinterpret_cast<const float4*>(swg + e * D + 8 * i);
+              const float4 w1 = *reinterpret_cast<const float4*>(swg + e * D + 8 * i + 4);
+              acc[e] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x + xv[5] * w1.y +
+                        xv[6] * w1.z + xv[7] * w1.w;
+            }
+          }
         }
       }
     }
@@ -140,6 +154,7 @@ moe_gather_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict
 
 // ------------------------------------------------------------------------------------- combine fwd
 // warp per token: ymoe = sum_e g*h2[slot]; xout = xres + gate*ymoe
+template <int ME>
 __global__ void __launch_bounds__(256)
 moe_combine_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ gval,
                        const int32_t* __restrict__ inv, const float* __restrict__ xres, const float* __restrict__ gate,
@@ -150,10 +165,10 @@ moe_combine_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __rest
   const int nvec = D >> 3;
   for (long long row = 1LL * blockIdx.x * 8 + warp; row < rows; row += 1LL * gridDim.x * 8) {
     const long long b = row / T;
-    int slot[kMaxE];
-    float g[kMaxE];
+    int slot[ME];
+    float g[ME];
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e) {
+    for (int e = 0; e < ME; ++e) {
       slot[e] = -1;
       g[e] = 0.f;
       if (e < E) {
@@ -166,11 +181,16 @@ moe_combine_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __rest
       float acc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      uint4 raw[ME];
 #pragma unroll
-      for (int e = 0; e < kMaxE; ++e) {
+      for (int e = 0; e < ME; ++e)  // every selected expert's row chunk in flight before the first use
+        if (e < E && slot[e] >= 0)
+          raw[e] = *reinterpret_cast<const uint4*>(h2 + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i);
+#pragma unroll
+      for (int e = 0; e < ME; ++e) {
         if (e < E && slot[e] >= 0) {
           float hv[8];
-          unpack8(*reinterpret_cast<const uint4*>(h2 + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i), hv);
+          unpack8(raw[e], hv);
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc[q] += g[e] * hv[q];
         }
@@ -227,6 +247,7 @@ moe_combine_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
 // ------------------------------------------------------------------------------------------ dx bwd
 // warp per token: dscores (softmax backward of the selected gate values) and
 // dx = sum_e dxin[slot] + dscores . Wg
+template <int ME>
 __global__ void __launch_bounds__(256)
 moe_dx_bwd_kernel(const __nv_bfloat16* __restrict__ dxin, const int32_t* __restrict__ inv,
                   const float* __restrict__ dgval, const float* __restrict__ probs, const float* __restrict__ wg,
@@ -239,11 +260,11 @@ moe_dx_bwd_kernel(const __nv_bfloat16* __restrict__ dxin, const int32_t* __restr
   const int nvec = D >> 3;
   for (long long row = 1LL * blockIdx.x * 8 + warp; row < rows; row += 1LL * gridDim.x * 8) {
     const long long b = row / T;
-    int slot[kMaxE];
-    float ds[kMaxE];
+    int slot[ME];
+    float ds[ME];
     float dot = 0.f;
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e) {
+    for (int e = 0; e < ME; ++e) {
       slot[e] = -1;
       ds[e] = 0.f;
       if (e < E) {
@@ -255,26 +276,32 @@ moe_dx_bwd_kernel(const __nv_bfloat16* __restrict__ dxin, const int32_t* __restr
       }
     }
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e)
+    for (int e = 0; e < ME; ++e)
       if (e < E) ds[e] = probs[row * E + e] * (ds[e] - dot);
     if (lane == 0) {
 #pragma unroll
-      for (int e = 0; e < kMaxE; ++e)
+      for (int e = 0; e < ME; ++e)
         if (e < E) dscores[row * E + e] = ds[e];
     }
     for (int i = lane; i < nvec; i += 32) {
       float acc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      uint4 raw[ME];
 #pragma unroll
-      for (int e = 0; e < kMaxE; ++e) {
+      for (int e = 0; e < ME; ++e)
+        if (e < E && slot[e] >= 0)
+          raw[e] = *reinterpret_cast<const uint4*>(dxin + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i);
+#pragma unroll
+      for (int e = 0; e < ME; ++e) {
         if (e < E) {
-          const float* w = swg + e * D + 8 * i;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] += ds[e] * w[q];
+          const float4 w0 = *reinterpret_cast<const float4*>(swg + e * D + 8 * i);
+          const float4 w1 = *reinterpret_cast<const float4*>(swg + e * D + 8 * i + 4);
+          acc[0] += ds[e] * w0.x; acc[1] += ds[e] * w0.y; acc[2] += ds[e] * w0.z; acc[3] += ds[e] * w0.w;
+          acc[4] += ds[e] * w1.x; acc[5] += ds[e] * w1.y; acc[6] += ds[e] * w1.z; acc[7] += ds[e] * w1.w;
           if (slot[e] >= 0) {
             float dv[8];
-            unpack8(*reinterpret_cast<const uint4*>(dxin + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i), dv);
+            unpack8(raw[e], dv);
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] += dv[q];
           }
@@ -299,11 +326,18 @@ moe_gate_wgrad_kernel(const float* __restrict__ dscores, const __nv_bfloat16* __
     float acc[kMaxE];
 #pragma unroll
     for (int e = 0; e < kMaxE; ++e) acc[e] = 0.f;
-    for (int r = 0; r < nr; ++r) {
-      const float xv = __bfloat162float(x[(r0 + r) * D + c]);
+    for (int r = 0; r < nr; r += 8) {
+      float xv[8];
 #pragma unroll
-      for (int e = 0; e < kMaxE; ++e)
-        if (e < E) acc[e] += sds[r * E + e] * xv;
+      for (int u = 0; u < 8; ++u) xv[u] = (r + u < nr) ? __bfloat162float(x[(r0 + r + u) * D + c]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (r + u < nr) {
+#pragma unroll
+          for (int e = 0; e < kMaxE; ++e)
+            if (e < E) acc[e] += sds[(r + u) * E + e] * xv[u];
+        }
+      }
     }
 #pragma unroll
     for (int e = 0; e < kMaxE; ++e)
@@ -379,8 +413,12 @@ extern "C" int md_moe_combine_fwd(const void* h2, const float* gval, const int32
   if (int rc = check_moe("md_moe_combine_fwd", D, E)) return rc;
   if (B * T == 0) return 0;
   if (!h2 || !gval || !inv || (xout && !xres)) return md_set_error(MD_ERR_INVALID, "md_moe_combine_fwd: null pointer");
-  moe_combine_fwd_kernel<<<warp_grid(B * T), 256, 0, ST(stream)>>>(CBF(h2), gval, inv, xres, gate, ldmod, xout, BF(ymoe),
-                                                                   (int)B, (int)T, (int)E, (int)k, (int)D);
+  if (E <= 8)
+    moe_combine_fwd_kernel<8><<<warp_grid(B * T), 256, 0, ST(stream)>>>(CBF(h2), gval, inv, xres, gate, ldmod, xout,
+                                                                        BF(ymoe), (int)B, (int)T, (int)E, (int)k, (int)D);
+  else
+    moe_combine_fwd_kernel<16><<<warp_grid(B * T), 256, 0, ST(stream)>>>(CBF(h2), gval, inv, xres, gate, ldmod, xout,
+                                                                         BF(ymoe), (int)B, (int)T, (int)E, (int)k, (int)D);
   return check_launch("md_moe_combine_fwd");
 }
 
@@ -406,11 +444,16 @@ extern "C" int md_moe_dx_bwd(const void* dxin, const int32_t* inv, const float* 
   if (smem > 200 * 1024) return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_dx_bwd: E*D too large for shared memory");
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(moe_dx_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_dx_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_dx_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  moe_dx_bwd_kernel<<<warp_grid(B * T), 256, smem, ST(stream)>>>(CBF(dxin), inv, dgval, probs, wg, dscores, BF(dx),
-                                                                 (int)B, (int)T, (int)E, (int)k, (int)D);
+  if (E <= 8)
+    moe_dx_bwd_kernel<8><<<warp_grid(B * T), 256, smem, ST(stream)>>>(CBF(dxin), inv, dgval, probs, wg, dscores, BF(dx),
+                                                                      (int)B, (int)T, (int)E, (int)k, (int)D);
+  else
+    moe_dx_bwd_kernel<16><<<warp_grid(B * T), 256, smem, ST(stream)>>>(CBF(dxin), inv, dgval, probs, wg, dscores, BF(dx),
+                                                                       (int)B, (int)T, (int)E, (int)k, (int)D);
   return check_launch("md_moe_dx_bwd");
 }
 
