@@ -42,11 +42,11 @@ struct Smem {
 };
 
 // Load rows [row0, row0+64) x HD columns (starting at column col0) of a [*, ld] bf16 matrix; rows >= nrows -> 0.
-template <int HD>
+template <int HD, int ROWS = kTile>
 __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, long long ld, long long row0,
                                           long long nrows, int col0) {
   constexpr int kChunks = HD / 8;
-  for (int i = threadIdx.x; i < kTile * kChunks; i += blockDim.x) {
+  for (int i = threadIdx.x; i < ROWS * kChunks; i += blockDim.x) {
     const int r = i / kChunks, c = (i % kChunks) * 8;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (row0 + r < nrows) v = *reinterpret_cast<const uint4*>(g + (row0 + r) * ld + col0 + c);
@@ -62,12 +62,12 @@ __device__ __forceinline__ void load_a_frags(uint32_t (&a)[HD / 16][4], const __
     ldsm_x4(a[ks], s + (r0 + (lane & 15)) * Smem<HD>::kPitch + ks * 16 + (lane >> 4) * 8);
 }
 
-// acc[nt] (16 x 64, nt = 8 tiles of 8 columns) = A(16 x HD) . M^T where M is a 64 x HD smem tile ([n][k]).
-template <int HD>
-__device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&a)[HD / 16][4], const __nv_bfloat16* m,
+// acc[nt] (16 x KT, nt = KT/8 tiles of 8 columns) = A(16 x HD) . M^T where M is a KT x HD smem tile ([n][k]).
+template <int HD, int KT = kTile>
+__device__ __forceinline__ void mma_a_bt(float (&acc)[KT / 8][4], const uint32_t (&a)[HD / 16][4], const __nv_bfloat16* m,
                                          int lane) {
 #pragma unroll
-  for (int np = 0; np < 4; ++np) {
+  for (int np = 0; np < KT / 16; ++np) {
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks) {
       uint32_t b[4];
@@ -79,12 +79,12 @@ __device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&a)
   }
 }
 
-// out[dt] (16 x HD) += P(16 x 64, given as 4 k-steps of A fragments) . M where M is a 64 x HD smem tile ([k][n]).
-template <int HD>
-__device__ __forceinline__ void mma_p_m(float (&out)[HD / 8][4], const uint32_t (&pa)[4][4], const __nv_bfloat16* m,
+// out[dt] (16 x HD) += P(16 x KT, given as KT/16 k-steps of A fragments) . M where M is a KT x HD smem tile ([k][n]).
+template <int HD, int KT = kTile>
+__device__ __forceinline__ void mma_p_m(float (&out)[HD / 8][4], const uint32_t (&pa)[KT / 16][4], const __nv_bfloat16* m,
                                         int lane) {
 #pragma unroll
-  for (int kt = 0; kt < 4; ++kt) {
+  for (int kt = 0; kt < KT / 16; ++kt) {
 #pragma unroll
     for (int dp = 0; dp < HD / 16; ++dp) {
       uint32_t b[4];
@@ -96,9 +96,10 @@ __device__ __forceinline__ void mma_p_m(float (&out)[HD / 8][4], const uint32_t 
   }
 }
 
-__device__ __forceinline__ void acc_to_afrag(uint32_t (&pa)[4][4], const float (&s)[8][4]) {
+template <int KS = 4>
+__device__ __forceinline__ void acc_to_afrag(uint32_t (&pa)[KS][4], const float (&s)[2 * KS][4]) {
 #pragma unroll
-  for (int kt = 0; kt < 4; ++kt) {
+  for (int kt = 0; kt < KS; ++kt) {
     pa[kt][0] = pack2(s[2 * kt][0], s[2 * kt][1]);
     pa[kt][1] = pack2(s[2 * kt][2], s[2 * kt][3]);
     pa[kt][2] = pack2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
@@ -107,15 +108,15 @@ __device__ __forceinline__ void acc_to_afrag(uint32_t (&pa)[4][4], const float (
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <int HD>
+template <int HD, int KT>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ k, long long ldk,
                 const __nv_bfloat16* __restrict__ v, long long ldv, __nv_bfloat16* __restrict__ o, long long ldo,
                 float* __restrict__ lse, int H, int Tq, int Tk, float scale_log2) {
   constexpr int P = Smem<HD>::kPitch;
   __shared__ __align__(16) __nv_bfloat16 sq[kTile * P];
-  __shared__ __align__(16) __nv_bfloat16 sk[kTile * P];
-  __shared__ __align__(16) __nv_bfloat16 sv[kTile * P];
+  __shared__ __align__(16) __nv_bfloat16 sk[KT * P];
+  __shared__ __align__(16) __nv_bfloat16 sv[KT * P];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y;
@@ -134,20 +135,20 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_b
     for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
 
-  for (int k0 = 0; k0 < Tk; k0 += kTile) {
+  for (int k0 = 0; k0 < Tk; k0 += KT) {
     __syncthreads();
-    load_tile<HD>(sk, k + b * Tk * ldk, ldk, k0, Tk, h * HD);
-    load_tile<HD>(sv, v + b * Tk * ldv, ldv, k0, Tk, h * HD);
+    load_tile<HD, KT>(sk, k + b * Tk * ldk, ldk, k0, Tk, h * HD);
+    load_tile<HD, KT>(sv, v + b * Tk * ldv, ldv, k0, Tk, h * HD);
     __syncthreads();
-    float s[8][4];
+    float s[KT / 8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < KT / 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
-    mma_a_bt<HD>(s, qa, sk, lane);
+    mma_a_bt<HD, KT>(s, qa, sk, lane);
     float mx[2] = {mrow[0], mrow[1]};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < KT / 8; ++nt)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int key = k0 + nt * 8 + 2 * t + (j & 1);
@@ -163,7 +164,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_b
 #pragma unroll
     for (int r = 0; r < 2; ++r) corr[r] = exp2f(mrow[r] - mx[r]);  // first tile: exp2(-inf) = 0
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < KT / 8; ++nt)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         s[nt][j] = exp2f(s[nt][j] - mx[j >> 1]);
@@ -179,9 +180,9 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_b
       oacc[i][0] *= corr[0]; oacc[i][1] *= corr[0];
       oacc[i][2] *= corr[1]; oacc[i][3] *= corr[1];
     }
-    uint32_t pa[4][4];
-    acc_to_afrag(pa, s);
-    mma_p_m<HD>(oacc, pa, sv, lane);
+    uint32_t pa[KT / 16][4];
+    acc_to_afrag<KT / 16>(pa, s);
+    mma_p_m<HD, KT>(oacc, pa, sv, lane);
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -395,6 +396,145 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const
   }
 }
 
+// --------------------------------------------------------------------- fused backward, short sequences
+// Tq <= 64 and Tk <= KT (64 or 80): one CTA per (sample, head) does the whole backward in a single pass --
+// S and dP once (the generic path computes them twice), delta = rowsum(P*dP) on the fly (no delta kernel, no O
+// read), dQ straight from registers, and dK / dV from P^T / dS^T read back transposed (ldmatrix.trans) from a
+// shared-memory copy.  This is the backbone regime of the benchmark (64 tokens after 75 % masking, 77 caption
+// tokens), where the generic kernels are latency- rather than math-bound.
+template <int HD, int KT>
+__global__ void __launch_bounds__(128)
+attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ q,
+                      long long ldq, const __nv_bfloat16* __restrict__ k, long long ldk,
+                      const __nv_bfloat16* __restrict__ v, long long ldv, const float* __restrict__ lse,
+                      __nv_bfloat16* __restrict__ dq, long long lddq, __nv_bfloat16* __restrict__ dk, long long lddk,
+                      __nv_bfloat16* __restrict__ dv, long long lddv, int H, int Tq, int Tk, float scale,
+                      float scale_log2) {
+  constexpr int P = Smem<HD>::kPitch;
+  constexpr int PP = KT + 8;  // pitch of the P / dS copies ([query][key])
+  extern __shared__ __align__(16) unsigned char smem_small[];
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_small);
+  __nv_bfloat16* sdo = sq + kTile * P;
+  __nv_bfloat16* sk = sdo + kTile * P;
+  __nv_bfloat16* sv = sk + KT * P;
+  __nv_bfloat16* sp = sv + KT * P;        // P  [64][PP]
+  __nv_bfloat16* sds = sp + kTile * PP;   // dS [64][PP]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.x;
+  const long long b = blockIdx.y;
+
+  load_tile<HD>(sq, q + b * Tq * ldq, ldq, 0, Tq, h * HD);
+  load_tile<HD>(sdo, dout + b * Tq * lddo, lddo, 0, Tq, h * HD);
+  load_tile<HD, KT>(sk, k + b * Tk * ldk, ldk, 0, Tk, h * HD);
+  load_tile<HD, KT>(sv, v + b * Tk * ldv, ldv, 0, Tk, h * HD);
+  float lrow[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = warp * 16 + g + r * 8;
+    lrow[r] = row < Tq ? lse[(b * H + h) * Tq + row] : INFINITY;  // +inf -> P = 0 for padded queries
+  }
+  __syncthreads();
+
+  uint32_t qa[HD / 16][4], doa[HD / 16][4];
+  load_a_frags<HD>(qa, sq, warp * 16, lane);
+  load_a_frags<HD>(doa, sdo, warp * 16, lane);
+  float s[KT / 8][4], dp[KT / 8][4];
+#pragma unroll
+  for (int i = 0; i < KT / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.f;
+  mma_a_bt<HD, KT>(s, qa, sk, lane);    // S  = Q . K^T
+  mma_a_bt<HD, KT>(dp, doa, sv, lane);  // dP = dO . V^T
+  float dsum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int nt = 0; nt < KT / 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int key = nt * 8 + 2 * t + (j & 1);
+      const float p = key < Tk ? exp2f(s[nt][j] * scale_log2 - lrow[j >> 1]) : 0.f;
+      s[nt][j] = p;
+      dsum[j >> 1] += p * dp[nt][j];
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {  // delta[row] = sum_keys P * dP  (== sum_d dO * O)
+    dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 1);
+    dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 2);
+  }
+#pragma unroll
+  for (int nt = 0; nt < KT / 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dp[nt][j] = s[nt][j] * (dp[nt][j] - dsum[j >> 1]);  // dS
+  // bf16 copies of P and dS for the transposed contractions
+#pragma unroll
+  for (int nt = 0; nt < KT / 8; ++nt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = warp * 16 + g + r * 8;
+      *reinterpret_cast<uint32_t*>(sp + row * PP + nt * 8 + 2 * t) = pack2(s[nt][2 * r], s[nt][2 * r + 1]);
+      *reinterpret_cast<uint32_t*>(sds + row * PP + nt * 8 + 2 * t) = pack2(dp[nt][2 * r], dp[nt][2 * r + 1]);
+    }
+  // dQ = dS . K  (A straight from the accumulator registers)
+  {
+    uint32_t pa[KT / 16][4];
+    acc_to_afrag<KT / 16>(pa, dp);
+    float dqacc[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dqacc[i][j] = 0.f;
+    mma_p_m<HD, KT>(dqacc, pa, sk, lane);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = warp * 16 + g + r * 8;
+      if (row < Tq) {
+        __nv_bfloat16* dst = dq + (b * Tq + row) * lddq + h * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i)
+          *reinterpret_cast<uint32_t*>(dst + i * 8 + 2 * t) = pack2(dqacc[i][2 * r] * scale, dqacc[i][2 * r + 1] * scale);
+      }
+    }
+  }
+  __syncthreads();
+  // dV = P^T . dO and dK = dS^T . Q : 16 keys per warp-iteration, reduction over the 64 queries.
+  for (int kb = warp; kb < KT / 16; kb += 4) {
+    uint32_t pta[4][4], dsta[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {  // A[m = key][k = query] = X[query][key]: transposed load
+      const int mi = lane >> 3;
+      const int rowq = ks * 16 + (lane & 7) + (mi >> 1) * 8;
+      const int colk = kb * 16 + (mi & 1) * 8;
+      ldsm_x4_t(pta[ks], sp + rowq * PP + colk);
+      ldsm_x4_t(dsta[ks], sds + rowq * PP + colk);
+    }
+    float dvacc[HD / 8][4], dkacc[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dvacc[i][j] = dkacc[i][j] = 0.f;
+    mma_p_m<HD, 64>(dvacc, pta, sdo, lane);
+    mma_p_m<HD, 64>(dkacc, dsta, sq, lane);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = kb * 16 + g + r * 8;
+      if (key < Tk) {
+        __nv_bfloat16* pk = dk + (b * Tk + key) * lddk + h * HD;
+        __nv_bfloat16* pv = dv + (b * Tk + key) * lddv + h * HD;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          *reinterpret_cast<uint32_t*>(pk + i * 8 + 2 * t) = pack2(dkacc[i][2 * r] * scale, dkacc[i][2 * r + 1] * scale);
+          *reinterpret_cast<uint32_t*>(pv + i * 8 + 2 * t) = pack2(dvacc[i][2 * r], dvacc[i][2 * r + 1]);
+        }
+      }
+    }
+  }
+}
+
+template <int HD, int KT>
+static size_t small_bwd_smem() {
+  return sizeof(__nv_bfloat16) * (2 * kTile * Smem<HD>::kPitch + 2 * KT * Smem<HD>::kPitch + 2 * kTile * (KT + 8));
+}
+
 static int check_attn(const char* what, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd, int64_t ld_min) {
   if (hd != 32 && hd != 64) return md_set_error(MD_ERR_UNSUPPORTED, "attention: head_dim must be 32 or 64");
   if (B < 0 || H <= 0 || Tq <= 0 || Tk <= 0 || H > 65535 || B > 65535)
@@ -418,12 +558,13 @@ extern "C" int md_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   if (!q || !k || !v || !o || !lse) return md_set_error(MD_ERR_INVALID, "md_attn_fwd: null pointer");
   const float sl2 = 1.4426950408889634f / sqrtf((float)hd);
   dim3 grid((unsigned)((Tq + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
-  if (hd == 64)
-    attn_fwd_kernel<64><<<grid, 128, 0, ST(stream)>>>(CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, BF(o), ldo, lse, (int)H,
-                                                      (int)Tq, (int)Tk, sl2);
-  else
-    attn_fwd_kernel<32><<<grid, 128, 0, ST(stream)>>>(CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, BF(o), ldo, lse, (int)H,
-                                                      (int)Tq, (int)Tk, sl2);
+  const bool kt80 = Tk > 64 && Tk <= 80;  // the 77 caption tokens: one 80-key tile instead of 64 + a 13-key stub
+#define FWD(HD_, KT_)                                                                                              \
+  attn_fwd_kernel<HD_, KT_><<<grid, 128, 0, ST(stream)>>>(CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, BF(o), ldo, lse, \
+                                                          (int)H, (int)Tq, (int)Tk, sl2)
+  if (hd == 64) { if (kt80) FWD(64, 80); else FWD(64, 64); }
+  else { if (kt80) FWD(32, 80); else FWD(32, 64); }
+#undef FWD
   return check_launch("md_attn_fwd");
 }
 
@@ -438,6 +579,25 @@ extern "C" int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_
     return md_set_error(MD_ERR_INVALID, "md_attn_bwd: null pointer");
   const float scale = 1.f / sqrtf((float)hd);
   const float sl2 = 1.4426950408889634f * scale;
+  if (Tq <= kTile && Tk <= 80) {  // single-pass fused backward
+    dim3 gs((unsigned)H, (unsigned)B);
+#define BWD_SMALL(HD_, KT_)                                                                                          \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    const size_t sm = small_bwd_smem<HD_, KT_>();                                                                    \
+    if (!attr) {                                                                                                     \
+      cudaFuncSetAttribute(attn_bwd_small_kernel<HD_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);  \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    attn_bwd_small_kernel<HD_, KT_><<<gs, 128, sm, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v),  \
+                                                                 ldv, lse, BF(dq), lddq, BF(dk), lddk, BF(dv), lddv, \
+                                                                 (int)H, (int)Tq, (int)Tk, scale, sl2);              \
+  } while (0)
+    if (hd == 64) { if (Tk <= 64) BWD_SMALL(64, 64); else BWD_SMALL(64, 80); }
+    else { if (Tk <= 64) BWD_SMALL(32, 64); else BWD_SMALL(32, 80); }
+#undef BWD_SMALL
+    return check_launch("md_attn_bwd");
+  }
   if (H * hd > 2048) return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_bwd: H*hd must be <= 2048");
   long long blocks = (B * Tq + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
