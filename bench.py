@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 GLOBAL_BATCH = 2048
 # algorithmic training GFLOP per image (3 x forward; SURVEY.md section 8d / BASELINE.md section 3)
 WORKLOADS = {
-    "c2": dict(arch="MicroDiT_XL_2", res=32, ch=4, mask=0.75, pos=1.0, p_mean=-0.6, p_std=1.2, micro=256, gf=282.30,
+    "c2": dict(arch="MicroDiT_XL_2", res=32, ch=4, mask=0.75, pos=1.0, p_mean=-0.6, p_std=1.2, micro=512, gf=282.30,
                name="MicroDiT_XL_2 res_256_pretrain mask=0.75 (32x32x4 latents)"),
     "c3": dict(arch="MicroDiT_XL_2", res=32, ch=4, mask=0.0, pos=1.0, p_mean=-0.6, p_std=1.2, micro=128, gf=714.41,
                name="MicroDiT_XL_2 res_256_finetune mask=0 (32x32x4 latents)"),
@@ -239,8 +239,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
     W, K = max(3, args.warmup), max(1, args.steps)
-    micro = args.microbatch or wl["micro"]
     per_rank = args.global_batch // world
+    micro = min(args.microbatch or wl["micro"], per_rank)
 
     ld = build_model(wl, device)
     opt = FlatAdamW(ld.dit, lr=2.4e-4, weight_decay=0.1, clip_norm=0.25)
@@ -361,6 +361,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "loss": last_loss},
             "gpu_launches": launches,
+            "peak_hbm_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (md_gemm_bf16)",
                          "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
