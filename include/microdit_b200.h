@@ -81,10 +81,13 @@ MD_API int md_gemm_bf16(const md_gemm_args* args, void* stream);
  * modulate utils.py:28-30; call sites dit.py:236-238, utils.py:238).  x: f32 (x_bf16=0) or bf16 (1),
  * [rows, D]; src_rows (optional, int32 [rows]) gathers input rows (mask_out_token utils.py:406-414 fused
  * into the patch_mixer_map_xout norm, dit.py:504-508).  gamma / shift / scale may be NULL.  y bf16 [rows,D];
- * mean, rstd f32 [rows].  D % 8 == 0, D <= 2048. */
-MD_API int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const float* gamma,
-                     const float* shift, const float* scale, int64_t ldmod, int64_t T, void* y, float* mean,
-                     float* rstd, int64_t rows, int64_t D, float eps, void* stream);
+ * mean, rstd f32 [rows].  D % 8 == 0, D <= 2048.
+ * y_add (optional, bf16 [rows_src, D]): the pending gated residual update of the previous sub-block is applied first,
+ * x_new[src] = x[src] + gate_add[sample] * y_add[src] (dit.py:236-238), written to x_new (f32) and then normalised --
+ * the branch GEMM then stores plain bf16 instead of doing the fp32 read-modify-write in its epilogue. */
+MD_API int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const void* y_add, const float* gate_add,
+                     float* x_new, const float* gamma, const float* shift, const float* scale, int64_t ldmod,
+                     int64_t T, void* y, float* mean, float* rstd, int64_t rows, int64_t D, float eps, void* stream);
 /* Backward of the above.  dy bf16 [rows, D].  dx_mode: 0 = dx(f32)[r] += , 1 = dx(bf16)[r] = ,
  * 2 = dx(f32)[src_rows[r]] += (scatter).  dgamma f32 [D] += (atomic); dshift / dscale f32 [samples, D]
  * pitched by ldmod, += (atomic; caller zeroes them once per step).  NULL outputs are skipped. */

@@ -417,8 +417,11 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, co
   __nv_bfloat16* sdo = sq + kTile * P;
   __nv_bfloat16* sk = sdo + kTile * P;
   __nv_bfloat16* sv = sk + KT * P;
-  __nv_bfloat16* sp = sv + KT * P;        // P  [64][PP]
-  __nv_bfloat16* sds = sp + kTile * PP;   // dS [64][PP]
+  // P and dS copies ([64][PP]) reuse the K and V tiles, which are dead once dQ has been formed: 41 KB instead of
+  // 64 KB per CTA -> five CTAs per SM, which is what this latency-bound regime needs.
+  static_assert(kTile * (KT + 8) <= KT * Smem<HD>::kPitch || HD == 32, "P copy must fit in the K tile");
+  __nv_bfloat16* sp = (HD == 64) ? sk : sv + KT * P;
+  __nv_bfloat16* sds = (HD == 64) ? sv : sp + kTile * PP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int h = blockIdx.x;
@@ -465,15 +468,6 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, co
   for (int nt = 0; nt < KT / 8; ++nt)
 #pragma unroll
     for (int j = 0; j < 4; ++j) dp[nt][j] = s[nt][j] * (dp[nt][j] - dsum[j >> 1]);  // dS
-  // bf16 copies of P and dS for the transposed contractions
-#pragma unroll
-  for (int nt = 0; nt < KT / 8; ++nt)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int row = warp * 16 + g + r * 8;
-      *reinterpret_cast<uint32_t*>(sp + row * PP + nt * 8 + 2 * t) = pack2(s[nt][2 * r], s[nt][2 * r + 1]);
-      *reinterpret_cast<uint32_t*>(sds + row * PP + nt * 8 + 2 * t) = pack2(dp[nt][2 * r], dp[nt][2 * r + 1]);
-    }
   // dQ = dS . K  (A straight from the accumulator registers)
   {
     uint32_t pa[KT / 16][4];
@@ -495,6 +489,16 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, co
       }
     }
   }
+  __syncthreads();  // every warp is done reading K / V
+  // bf16 copies of P and dS for the transposed contractions
+#pragma unroll
+  for (int nt = 0; nt < KT / 8; ++nt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = warp * 16 + g + r * 8;
+      *reinterpret_cast<uint32_t*>(sp + row * PP + nt * 8 + 2 * t) = pack2(s[nt][2 * r], s[nt][2 * r + 1]);
+      *reinterpret_cast<uint32_t*>(sds + row * PP + nt * 8 + 2 * t) = pack2(dp[nt][2 * r], dp[nt][2 * r + 1]);
+    }
   __syncthreads();
   // dV = P^T . dO and dK = dS^T . Q : 16 keys per warp-iteration, reduction over the 64 queries.
   for (int kb = warp; kb < KT / 16; kb += 4) {
@@ -532,7 +536,8 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, co
 
 template <int HD, int KT>
 static size_t small_bwd_smem() {
-  return sizeof(__nv_bfloat16) * (2 * kTile * Smem<HD>::kPitch + 2 * KT * Smem<HD>::kPitch + 2 * kTile * (KT + 8));
+  const size_t base = 2 * kTile * Smem<HD>::kPitch + 2 * KT * Smem<HD>::kPitch;
+  return sizeof(__nv_bfloat16) * (HD == 64 ? base : base + 2 * kTile * (KT + 8));
 }
 
 static int check_attn(const char* what, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd, int64_t ld_min) {

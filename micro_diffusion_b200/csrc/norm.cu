@@ -47,7 +47,8 @@ __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0
 // ------------------------------------------------------------------------------------------ ln_fwd
 template <int VEC, bool EXACT, bool XBF>
 __global__ void __launch_bounds__(128)
-ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, const float* __restrict__ gamma,
+ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, const __nv_bfloat16* __restrict__ yadd,
+              const float* __restrict__ gadd, float* __restrict__ xnew, const float* __restrict__ gamma,
               const float* __restrict__ shift, const float* __restrict__ scale, long long ldmod, long long T,
               void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int D,
               float eps) {
@@ -60,6 +61,25 @@ ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, 
     for (int j = 0; j < VEC; ++j) {
       const int i = lane + 32 * j;
       v[j] = (EXACT || i < nvec) ? ld4<XBF>(x, src * D + 4LL * i) : f4zero();
+    }
+    if (yadd != nullptr) {  // fused residual update  x_new = x + gate[sample] * y  (dit.py:236-238), written back
+      float4 ya[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int i = lane + 32 * j;
+        ya[j] = (EXACT || i < nvec) ? ld4<true>(yadd, src * D + 4LL * i) : f4zero();
+      }
+      const float* gt = gadd ? gadd + (row / T) * ldmod : nullptr;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int i = lane + 32 * j;
+        if (EXACT || i < nvec) {
+          float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (gt) g = *reinterpret_cast<const float4*>(gt + 4 * i);
+          v[j].x += g.x * ya[j].x; v[j].y += g.y * ya[j].y; v[j].z += g.z * ya[j].z; v[j].w += g.w * ya[j].w;
+          *reinterpret_cast<float4*>(xnew + src * D + 4LL * i) = v[j];
+        }
+      }
     }
     float s = 0.f;
 #pragma unroll
@@ -414,22 +434,25 @@ static int rows_per_block(long long T, long long samples) {
   return rpb;
 }
 
-extern "C" int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const float* gamma, const float* shift,
-                         const float* scale, int64_t ldmod, int64_t T, void* y, float* mean, float* rstd,
-                         int64_t rows, int64_t D, float eps, void* stream) {
+extern "C" int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const void* y_add, const float* gate_add,
+                         float* x_new, const float* gamma, const float* shift, const float* scale, int64_t ldmod,
+                         int64_t T, void* y, float* mean, float* rstd, int64_t rows, int64_t D, float eps,
+                         void* stream) {
   if (int rc = check_ln_dims("md_ln_fwd", rows, D, T)) return rc;
   if (rows == 0) return 0;
   if (!x || !y) return md_set_error(MD_ERR_INVALID, "md_ln_fwd: null pointer");
+  if (y_add != nullptr && (x_new == nullptr || x_bf16)) return md_set_error(MD_ERR_INVALID, "md_ln_fwd: residual add needs x_new and f32 x");
+  const __nv_bfloat16* yadd = reinterpret_cast<const __nv_bfloat16*>(y_add);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = row_grid(rows);
 #define LN_FWD(VEC, EXACT)                                                                                             \
   do {                                                                                                                 \
     if (x_bf16)                                                                                                        \
-      ln_fwd_kernel<VEC, EXACT, true><<<grid, 128, 0, st>>>(x, src_rows, gamma, shift, scale, ldmod, T, y, mean, rstd, \
-                                                            rows, static_cast<int>(D), eps);                          \
+      ln_fwd_kernel<VEC, EXACT, true><<<grid, 128, 0, st>>>(x, src_rows, yadd, gate_add, x_new, gamma, shift, scale,  \
+                                                            ldmod, T, y, mean, rstd, rows, static_cast<int>(D), eps); \
     else                                                                                                               \
-      ln_fwd_kernel<VEC, EXACT, false><<<grid, 128, 0, st>>>(x, src_rows, gamma, shift, scale, ldmod, T, y, mean,     \
-                                                             rstd, rows, static_cast<int>(D), eps);                   \
+      ln_fwd_kernel<VEC, EXACT, false><<<grid, 128, 0, st>>>(x, src_rows, yadd, gate_add, x_new, gamma, shift, scale, \
+                                                             ldmod, T, y, mean, rstd, rows, static_cast<int>(D), eps);\
   } while (0)
   if (D == 1024) LN_FWD(8, true);
   else if (D == 768) LN_FWD(6, true);

@@ -43,17 +43,38 @@ class Engine:
         return [mod[:, o + i * D: o + (i + 1) * D] for i in range(6)]
 
     # ================================================================== block forward
-    def _block_fwd(self, bs: BlockSpec, x, ykv, B, T, L, mod, keep: bool):
+    def _ln_add(self, x, pend, out, mean, rstd, *, gamma, shift=None, scale=None, T, src_rows=None, rows_all=None):
+        """LayerNorm of (x + pending gated residual).  `pend` = (y bf16, gate view | None) left by the previous
+        sub-block, applied here instead of in that sub-block's GEMM epilogue.  Returns the updated stream."""
+        o = self.ops
+        if pend is None:
+            o.ln_fwd(x, out, mean, rstd, gamma=gamma, shift=shift, scale=scale, T=T, src_rows=src_rows, eps=self.cfg.norm_eps)
+            return x
+        xn = o.empty(tuple(x.shape), F32)
+        o.ln_fwd(x, out, mean, rstd, gamma=gamma, shift=shift, scale=scale, T=T, src_rows=src_rows, eps=self.cfg.norm_eps,
+                 y_add=pend[0], gate_add=pend[1], x_new=xn)
+        return xn
+
+    def _materialize(self, x, pend, T):
+        """Apply a pending residual where a plain tensor is needed (only reached by non-zoo configurations)."""
+        if pend is None:
+            return x
+        o = self.ops
+        scratch = o.empty(tuple(x.shape), BF16)
+        return self._ln_add(x, pend, scratch, None, None, gamma=None, T=T)
+
+    def _block_fwd(self, bs: BlockSpec, x, pend, ykv, B, T, L, mod, keep: bool):
+        """One DiTBlock (dit.py:232-239).  `x` + `pend` is the block input; returns (stream, pending, saved)."""
         o, st, cfg = self.ops, self.store, self.cfg
         P = st.p
         n, D, h, f, hd = bs.name, bs.dim, bs.attn_dim, bs.ffn_dim, cfg.head_dim
         M = B * T
         eps = cfg.norm_eps
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = self._mods(n, D, mod)
-        sv = NS(x=x)
+        sv = NS()
         # ---- self attention (dit.py:236, utils.py:178-196)
         sv.xm = o.empty((M, D), BF16); sv.mean1 = o.empty((M,), F32); sv.rstd1 = o.empty((M,), F32)
-        o.ln_fwd(x, sv.xm, sv.mean1, sv.rstd1, gamma=P[n + ".norm1.weight"], shift=sh_a, scale=sc_a, T=T, eps=eps)
+        sv.x = self._ln_add(x, pend, sv.xm, sv.mean1, sv.rstd1, gamma=P[n + ".norm1.weight"], shift=sh_a, scale=sc_a, T=T)
         sv.qkv = o.empty((M, 3 * h), BF16)
         o.gemm(sv.xm, st.W(n + ".attn.qkv.weight"), sv.qkv)
         sv.rq = o.empty((M,), F32); sv.rk = o.empty((M,), F32)
@@ -61,11 +82,11 @@ class Engine:
         o.rownorm_fwd(sv.qkv[:, h:2 * h], sv.rk, eps)
         sv.att = o.empty((M, h), BF16); sv.lse = o.empty((B, bs.heads, T), F32)
         o.attn_fwd(sv.qkv[:, :h], sv.qkv[:, h:2 * h], sv.qkv[:, 2 * h:], sv.att, sv.lse, B, bs.heads, T, T, hd)
-        sv.x1 = o.empty((M, D), F32); sv.ya = o.empty((M, D), BF16)
-        o.gemm(sv.att, st.W(n + ".attn.proj.weight"), sv.x1, epi=EPI_RESID, res=x, gate=g_a, rows_per_gate=T, C2=sv.ya)
+        sv.ya = o.empty((M, D), BF16)
+        o.gemm(sv.att, st.W(n + ".attn.proj.weight"), sv.ya)
         # ---- cross attention to the caption tokens (dit.py:237, utils.py:116-136)
         sv.xn2 = o.empty((M, D), BF16); sv.mean2 = o.empty((M,), F32); sv.rstd2 = o.empty((M,), F32)
-        o.ln_fwd(sv.x1, sv.xn2, sv.mean2, sv.rstd2, gamma=P[n + ".norm2.weight"], T=T, eps=eps)
+        sv.x1 = self._ln_add(sv.x, (sv.ya, g_a), sv.xn2, sv.mean2, sv.rstd2, gamma=P[n + ".norm2.weight"], T=T)
         sv.qx = o.empty((M, D), BF16)
         o.gemm(sv.xn2, st.W(n + ".cross_attn.q_linear.weight"), sv.qx)
         sv.kv = o.empty((B * L, 2 * D), BF16)
@@ -75,19 +96,21 @@ class Engine:
         o.rownorm_fwd(sv.kv[:, :D], sv.rk2, eps)
         sv.att2 = o.empty((M, D), BF16); sv.lse2 = o.empty((B, bs.xheads, T), F32)
         o.attn_fwd(sv.qx, sv.kv[:, :D], sv.kv[:, D:], sv.att2, sv.lse2, B, bs.xheads, T, L, hd)
-        sv.x2 = o.empty((M, D), F32)
-        o.gemm(sv.att2, st.W(n + ".cross_attn.proj.weight"), sv.x2, epi=EPI_RESID, res=sv.x1)
+        yx = o.empty((M, D), BF16)
+        o.gemm(sv.att2, st.W(n + ".cross_attn.proj.weight"), yx)
         # ---- feed-forward (dit.py:238)
         sv.xm3 = o.empty((M, D), BF16); sv.mean3 = o.empty((M,), F32); sv.rstd3 = o.empty((M,), F32)
-        o.ln_fwd(sv.x2, sv.xm3, sv.mean3, sv.rstd3, gamma=P[n + ".norm3.weight"], shift=sh_m, scale=sc_m, T=T, eps=eps)
-        x3 = o.empty((M, D), F32); sv.ym = o.empty((M, D), BF16)
-        if not bs.moe:  # SwiGLU (dit.py:88-89)
+        sv.x2 = self._ln_add(sv.x1, (yx, None), sv.xm3, sv.mean3, sv.rstd3, gamma=P[n + ".norm3.weight"], shift=sh_m,
+                             scale=sc_m, T=T)
+        sv.ym = o.empty((M, D), BF16)
+        if not bs.moe:  # SwiGLU (dit.py:88-89); its gated residual is left pending for the next LayerNorm
             sv.u = o.empty((M, 2 * f), BF16)
             o.gemm(sv.xm3, st.W(n + ".mlp.w12"), sv.u)
             sv.hact = o.empty((M, f), BF16)
             o.swiglu_fwd(sv.u, sv.hact)
-            o.gemm(sv.hact, st.W(n + ".mlp.w3.weight"), x3, epi=EPI_RESID, res=sv.x2, gate=g_m, rows_per_gate=T, C2=sv.ym)
-        else:  # expert-choice MoE (dit.py:126-143)
+            o.gemm(sv.hact, st.W(n + ".mlp.w3.weight"), sv.ym)
+            out, pend_out = sv.x2, (sv.ym, g_m)
+        else:  # expert-choice MoE (dit.py:126-143): the combine kernel applies the gated residual itself
             E = cfg.num_experts
             k = int(cfg.expert_capacity * T / E)
             sv.k = k
@@ -101,8 +124,10 @@ class Engine:
             o.gemm(sv.xin, st.WT(n + ".mlp.w1"), sv.hpre, epi=EPI_ACT_DUAL, C2=sv.hact, act=ACT_ERF)
             sv.h2 = o.empty((E, B * k, D), BF16)
             o.gemm(sv.hact, st.WT(n + ".mlp.w2"), sv.h2)
-            o.moe_combine_fwd(sv.h2, sv.gval, sv.inv, sv.x2, g_m, x3, sv.ym, B, T, E, k)
-        return x3, (sv if keep else None)
+            out = o.empty((M, D), F32)
+            o.moe_combine_fwd(sv.h2, sv.gval, sv.inv, sv.x2, g_m, out, sv.ym, B, T, E, k)
+            pend_out = None
+        return out, pend_out, (sv if keep else None)
 
     # ================================================================== block backward
     def _block_bwd(self, bs: BlockSpec, sv, dx, ykv, dykv, B, T, L, mod, dmod):
@@ -382,12 +407,12 @@ class Engine:
             else:
                 xm, c.ymix = x0, s.ybf
             c.x0 = x0
+            pend = None
             for bs in cfg.mixer_blocks:
-                xm, sv = self._block_fwd(bs, xm, c.ymix, B, T, L, mod, keep)
+                xm, pend, sv = self._block_fwd(bs, xm, pend, c.ymix, B, T, L, mod, keep)
                 c.mixer_sv.append(sv)
         else:
-            xm = x0
-        c.xm_out = xm
+            xm, pend = x0, None
         # ---- random patch masking (dit.py:495-504, utils.py:382-414)
         if mask_ratio > 0:
             Tk = int(T * (1 - mask_ratio))
@@ -399,27 +424,29 @@ class Engine:
         c.Tk = Tk
         if cfg.has_mixer_maps:  # LN + Linear back to the backbone width, applied after masking (dit.py:506-508)
             c.xk_n = o.empty((B * Tk, Dm), BF16); c.m_xo = o.empty((B * Tk,), F32); c.r_xo = o.empty((B * Tk,), F32)
-            o.ln_fwd(xm, c.xk_n, c.m_xo, c.r_xo, gamma=P["patch_mixer_map_xout.0.weight"], T=Tk, src_rows=c.keep_rows,
-                     eps=cfg.norm_eps)
+            c.xm_out = self._ln_add(xm, pend, c.xk_n, c.m_xo, c.r_xo, gamma=P["patch_mixer_map_xout.0.weight"], T=Tk,
+                                    src_rows=c.keep_rows)
             xb = o.empty((B * Tk, D), F32)
             o.gemm(c.xk_n, st.W("patch_mixer_map_xout.1.weight"), xb, epi=EPI_F32)
+            pend = None
         elif mask_ratio > 0:
+            xm = self._materialize(xm, pend, T)
             xb = o.empty((B * Tk, xm.shape[1]), F32)
             o.gather_rows(xm, c.keep_rows, xb)
+            pend = None
         else:
             xb = xm
         # ---- backbone (dit.py:510-511)
         c.block_sv = []
         for bs in cfg.blocks:
-            xb, sv = self._block_fwd(bs, xb, s.ybf, B, Tk, L, mod, keep)
+            xb, pend, sv = self._block_fwd(bs, xb, pend, s.ybf, B, Tk, L, mod, keep)
             c.block_sv.append(sv)
         # ---- final layer (utils.py:236-240)
         fo = st.layout.ada_offset["final_layer"]
         sh_f, sc_f = mod[:, fo:fo + D], mod[:, fo + D:fo + 2 * D]
-        c.xlast = xb
         c.xf = o.empty((B * Tk, D), BF16); c.m_f = o.empty((B * Tk,), F32); c.r_f = o.empty((B * Tk,), F32)
-        o.ln_fwd(xb, c.xf, c.m_f, c.r_f, gamma=P["final_layer.norm_final.weight"], shift=sh_f, scale=sc_f, T=Tk,
-                 eps=cfg.norm_eps)
+        c.xlast = self._ln_add(xb, pend, c.xf, c.m_f, c.r_f, gamma=P["final_layer.norm_final.weight"], shift=sh_f,
+                               scale=sc_f, T=Tk)
         c.ftok = o.empty((B * Tk, cfg.patch_dim), F32)
         o.gemm(c.xf, st.W("final_layer.linear.weight"), c.ftok, epi=EPI_F32, bias=P["final_layer.linear.bias"])
         return c

@@ -25,7 +25,7 @@ _P = C.c_void_p
 _I = C.c_int
 
 _PROTOS = {
-    "md_ln_fwd": [_P, _I, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I64, _F, _P],
+    "md_ln_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I64, _F, _P],
     "md_ln_bwd": [_P, _P, _I, _P, _P, _P, _I64, _I64, _P, _P, _P, _I, _P, _P, _P, _I64, _I64, _P],
     "md_rownorm_fwd": [_P, _I64, _P, _I64, _I64, _F, _P],
     "md_rownorm_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _P],
@@ -179,12 +179,15 @@ class CudaOps:
                                        f"[M={M} N={N} K={K} layout={layout} epi={epi}]")
 
     # ------------------------------------------------------------------ norms
-    def ln_fwd(self, x, y, mean, rstd, *, gamma=None, shift=None, scale=None, T, src_rows=None, eps=1e-6):
+    def ln_fwd(self, x, y, mean, rstd, *, gamma=None, shift=None, scale=None, T, src_rows=None, eps=1e-6,
+               y_add=None, gate_add=None, x_new=None):
         rows, D = y.shape
         sh, ld1 = _mod(shift)
         sc, ld2 = _mod(scale)
-        self._call("md_ln_fwd", x.data_ptr(), int(x.dtype == torch.bfloat16), _ptr(src_rows), _ptr(gamma), sh, sc,
-                   ld1 or ld2, T, y.data_ptr(), _ptr(mean), _ptr(rstd), rows, D, eps)
+        ga, ld3 = _mod(gate_add)
+        self._call("md_ln_fwd", x.data_ptr(), int(x.dtype == torch.bfloat16), _ptr(src_rows), _ptr(y_add), ga,
+                   _ptr(x_new), _ptr(gamma), sh, sc, ld1 or ld2 or ld3, T, y.data_ptr(), _ptr(mean), _ptr(rstd), rows,
+                   D, eps)
 
     def ln_bwd(self, dy, x, mean, rstd, *, gamma=None, scale=None, T, src_rows=None, dx=None, dx_mode=0,
                dgamma=None, dshift=None, dscale=None):

@@ -103,12 +103,24 @@ class EmuOps:
             raise ValueError(epi)
 
     # ------------------------------------------------------------------ norms
-    def ln_fwd(self, x, y, mean, rstd, *, gamma=None, shift=None, scale=None, T, src_rows=None, eps=1e-6):
+    def ln_fwd(self, x, y, mean, rstd, *, gamma=None, shift=None, scale=None, T, src_rows=None, eps=1e-6,
+               y_add=None, gate_add=None, x_new=None):
         self.launches += 1
         rows, D = y.shape
         xv = _f(x).reshape(-1, D)
         if src_rows is not None:
             xv = xv[src_rows.long()]
+        if y_add is not None:
+            ya = _f(y_add).reshape(-1, D)
+            if src_rows is not None:
+                ya = ya[src_rows.long()]
+            if gate_add is not None:
+                ya = ya * _expand_mod(gate_add, T, rows)
+            xv = xv + ya
+            if src_rows is not None:
+                x_new[src_rows.long()] = xv
+            else:
+                x_new.copy_(xv)
         mu = xv.mean(1, keepdim=True)
         var = ((xv - mu) ** 2).mean(1, keepdim=True)
         rs = torch.rsqrt(var + eps)

@@ -76,8 +76,8 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     lib.md_last_error.restype = ctypes.c_char_p
     lib.md_ln_fwd.restype = ctypes.c_int
-    rc = lib.md_ln_fwd(None, 0, None, None, None, None, ctypes.c_int64(0), ctypes.c_int64(1), None, None, None,
-                       ctypes.c_int64(4), ctypes.c_int64(100), ctypes.c_float(1e-6), None)
+    rc = lib.md_ln_fwd(None, 0, None, None, None, None, None, None, None, ctypes.c_int64(0), ctypes.c_int64(1), None,
+                       None, None, ctypes.c_int64(4), ctypes.c_int64(100), ctypes.c_float(1e-6), None)
     assert rc == -3 and b"D=100" in lib.md_last_error()
     args = _lib.GemmArgs()
     assert lib.md_gemm_bf16(ctypes.byref(args), None) == -1
