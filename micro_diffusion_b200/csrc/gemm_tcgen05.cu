@@ -69,6 +69,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Tile order inside one (batch, split) slice: bands of kBand n-blocks, n fastest inside a band, then m, then the
+// next band.  Co-resident CTAs share A rows (as before), and a band's B tiles (<= 4 MB) stay in L2 while the sweep
+// over m reuses them -- without this a wide-N GEMM (the stacked K/V projection, N = 57k) re-streams B from HBM for
+// every row block.
+constexpr int kBand = 8;
+__device__ __forceinline__ void decode_tile(int r, int m_blocks, int n_blocks, int& mb, int& nb) {
+  const int per_band = kBand * m_blocks;
+  const int band = r / per_band;
+  const int bw = min(kBand, n_blocks - band * kBand);
+  const int rr = r - band * per_band;
+  mb = rr / bw;
+  nb = band * kBand + rr % bw;
+}
+
 template <int BLOCK_N, bool kMN, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -130,8 +144,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t it = 0;
       for (long long tile = tile0; tile < tiles; tile += tile_step) {
         long long t = tile;
-        const int nb = t % n_blocks; t /= n_blocks;
-        const int mb = t % m_blocks; t /= m_blocks;
+        const long long mn = 1LL * n_blocks * m_blocks;
+        int mb, nb;
+        decode_tile(static_cast<int>(t % mn), m_blocks, n_blocks, mb, nb);
+        t /= mn;
         const int sp = t % p.splits; t /= p.splits;
         const int bz = static_cast<int>(t);
         const int kb0 = sp * kb_per_split;
@@ -216,8 +232,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_it = 0;
     for (long long tile = tile0; tile < tiles; tile += tile_step, ++acc_it) {
       long long t = tile;
-      const int nb = t % n_blocks; t /= n_blocks;
-      const int mb = t % m_blocks; t /= m_blocks;
+      const long long mn = 1LL * n_blocks * m_blocks;
+      int mb, nb;
+      decode_tile(static_cast<int>(t % mn), m_blocks, n_blocks, mb, nb);
+      t /= mn;
       const int sp = t % p.splits; t /= p.splits;
       const int bz = static_cast<int>(t);
       const int kb0 = sp * kb_per_split;

@@ -42,6 +42,20 @@ class Engine:
         o = self.store.layout.ada_offset[key]
         return [mod[:, o + i * D: o + (i + 1) * D] for i in range(6)]
 
+    # ================================================================== stage-wide caption K/V projection
+    def _kv_fwd(self, group, ykv, nblk, D2):
+        """kv_linear of every block of a stage in one GEMM: [B*L, Dy] x [nblk*2D, Dy]^T (utils.py:118)."""
+        o, st = self.ops, self.store
+        kv_all = o.empty((ykv.shape[0], nblk * D2), BF16)
+        o.gemm(ykv, st.W(group), kv_all)
+        return kv_all
+
+    def _kv_bwd(self, group, dkv_all, ykv, dykv):
+        """Weight gradient of the stacked kv_linear and the gradient flowing into the caption tokens."""
+        o, st = self.ops, self.store
+        self._wgrad(dkv_all, ykv, st.G(group))
+        o.gemm(dkv_all, st.WT(group), dykv, epi=EPI_RESID, res=dykv)
+
     # ================================================================== block forward
     def _ln_add(self, x, pend, out, mean, rstd, *, gamma, shift=None, scale=None, T, src_rows=None, rows_all=None):
         """LayerNorm of (x + pending gated residual).  `pend` = (y bf16, gate view | None) left by the previous
@@ -63,7 +77,7 @@ class Engine:
         scratch = o.empty(tuple(x.shape), BF16)
         return self._ln_add(x, pend, scratch, None, None, gamma=None, T=T)
 
-    def _block_fwd(self, bs: BlockSpec, x, pend, ykv, B, T, L, mod, keep: bool):
+    def _block_fwd(self, bs: BlockSpec, x, pend, kv, B, T, L, mod, keep: bool):
         """One DiTBlock (dit.py:232-239).  `x` + `pend` is the block input; returns (stream, pending, saved)."""
         o, st, cfg = self.ops, self.store, self.cfg
         P = st.p
@@ -89,8 +103,7 @@ class Engine:
         sv.x1 = self._ln_add(sv.x, (sv.ya, g_a), sv.xn2, sv.mean2, sv.rstd2, gamma=P[n + ".norm2.weight"], T=T)
         sv.qx = o.empty((M, D), BF16)
         o.gemm(sv.xn2, st.W(n + ".cross_attn.q_linear.weight"), sv.qx)
-        sv.kv = o.empty((B * L, 2 * D), BF16)
-        o.gemm(ykv, st.W(n + ".cross_attn.kv_linear.weight"), sv.kv)
+        sv.kv = kv  # this block's [B*L, 2D] column slice of the stage-wide K/V projection
         sv.rq2 = o.empty((M,), F32); sv.rk2 = o.empty((B * L,), F32)
         o.rownorm_fwd(sv.qx, sv.rq2, eps)
         o.rownorm_fwd(sv.kv[:, :D], sv.rk2, eps)
@@ -130,9 +143,9 @@ class Engine:
         return out, pend_out, (sv if keep else None)
 
     # ================================================================== block backward
-    def _block_bwd(self, bs: BlockSpec, sv, dx, ykv, dykv, B, T, L, mod, dmod):
+    def _block_bwd(self, bs: BlockSpec, sv, dx, dkv, B, T, L, mod, dmod):
         """dx (f32 [M,D]): in = grad wrt the block output, out = grad wrt the block input (in place).
-        dykv (f32 [B*L, Dy]) accumulates the gradient flowing into the caption tokens."""
+        dkv (bf16 [B*L, 2D] column slice of the stage-wide buffer) receives d loss / d (K, V) of this block."""
         o, st, cfg = self.ops, self.store, self.cfg
         P, G = st.p, st.g
         n, D, h, f, hd = bs.name, bs.dim, bs.attn_dim, bs.ffn_dim, cfg.head_dim
@@ -173,14 +186,12 @@ class Engine:
         datt2 = o.empty((M, D), BF16)
         o.gemm(dy, st.WT(n + ".cross_attn.proj.weight"), datt2)
         self._wgrad(dy, sv.att2, st.G(n + ".cross_attn.proj.weight"))
-        dqx = o.empty((M, D), BF16); dkv = o.empty((B * L, 2 * D), BF16)
+        dqx = o.empty((M, D), BF16)
         delta = o.empty((B, bs.xheads, T), F32)
         o.attn_bwd(datt2, sv.qx, sv.kv[:, :D], sv.kv[:, D:], sv.att2, sv.lse2, delta, dqx, dkv[:, :D], dkv[:, D:], B,
                    bs.xheads, T, L, hd)
         o.rownorm_bwd(dqx, sv.qx, sv.rq2)
         o.rownorm_bwd(dkv[:, :D], sv.kv[:, :D], sv.rk2)
-        self._wgrad(dkv, ykv, st.G(n + ".cross_attn.kv_linear.weight"))
-        o.gemm(dkv, st.WT(n + ".cross_attn.kv_linear.weight"), dykv, epi=EPI_RESID, res=dykv)
         dxn2 = o.empty((M, D), BF16)
         o.gemm(dqx, st.WT(n + ".cross_attn.q_linear.weight"), dxn2)
         self._wgrad(dqx, sv.xn2, st.G(n + ".cross_attn.q_linear.weight"))
@@ -408,8 +419,10 @@ class Engine:
                 xm, c.ymix = x0, s.ybf
             c.x0 = x0
             pend = None
-            for bs in cfg.mixer_blocks:
-                xm, pend, sv = self._block_fwd(bs, xm, pend, c.ymix, B, T, L, mod, keep)
+            D2m = 2 * Dm
+            kv_m = self._kv_fwd("kv.patch_mixer", c.ymix, len(cfg.mixer_blocks), D2m)
+            for i, bs in enumerate(cfg.mixer_blocks):
+                xm, pend, sv = self._block_fwd(bs, xm, pend, kv_m[:, i * D2m:(i + 1) * D2m], B, T, L, mod, keep)
                 c.mixer_sv.append(sv)
         else:
             xm, pend = x0, None
@@ -438,8 +451,9 @@ class Engine:
             xb = xm
         # ---- backbone (dit.py:510-511)
         c.block_sv = []
-        for bs in cfg.blocks:
-            xb, pend, sv = self._block_fwd(bs, xb, pend, s.ybf, B, Tk, L, mod, keep)
+        kv_b = self._kv_fwd("kv.blocks", s.ybf, len(cfg.blocks), 2 * D)
+        for i, bs in enumerate(cfg.blocks):
+            xb, pend, sv = self._block_fwd(bs, xb, pend, kv_b[:, i * 2 * D:(i + 1) * 2 * D], B, Tk, L, mod, keep)
             c.block_sv.append(sv)
         # ---- final layer (utils.py:236-240)
         fo = st.layout.ada_offset["final_layer"]
@@ -507,8 +521,13 @@ class Engine:
                  dx_mode=0, dgamma=G["final_layer.norm_final.weight"], dshift=dmod[:, fo:fo + D],
                  dscale=dmod[:, fo + D:fo + 2 * D])
         # ---- backbone
-        for bs, sv in zip(reversed(cfg.blocks), reversed(c.block_sv)):
-            self._block_bwd(bs, sv, dx, s.ybf, dy2, B, Tk, L, mod, dmod)
+        nb = len(cfg.blocks)
+        dkv_b = o.empty((B * L, nb * 2 * D), BF16)
+        for i in range(nb - 1, -1, -1):
+            self._block_bwd(cfg.blocks[i], c.block_sv[i], dx, dkv_b[:, i * 2 * D:(i + 1) * 2 * D], B, Tk, L, mod, dmod)
+            c.block_sv[i] = None  # release this block's saved activations
+        self._kv_bwd("kv.blocks", dkv_b, s.ybf, dy2)
+        del dkv_b
         # ---- un-mask / mixer-out map
         if cfg.has_mixer_maps:
             dxb = o.empty((B * Tk, D), BF16)
@@ -528,8 +547,14 @@ class Engine:
         # ---- patch mixer
         if cfg.use_patch_mixer:
             dymix = o.zeros((B * L, Dm), F32) if cfg.has_mixer_maps else dy2
-            for bs, sv in zip(reversed(cfg.mixer_blocks), reversed(c.mixer_sv)):
-                self._block_bwd(bs, sv, dxm, c.ymix, dymix, B, T, L, mod, dmod)
+            nm = len(cfg.mixer_blocks)
+            dkv_m = o.empty((B * L, nm * 2 * Dm), BF16)
+            for i in range(nm - 1, -1, -1):
+                self._block_bwd(cfg.mixer_blocks[i], c.mixer_sv[i], dxm, dkv_m[:, i * 2 * Dm:(i + 1) * 2 * Dm], B, T, L,
+                                mod, dmod)
+                c.mixer_sv[i] = None
+            self._kv_bwd("kv.patch_mixer", dkv_m, c.ymix, dymix)
+            del dkv_m
             if cfg.has_mixer_maps:
                 # caption map: y_mixer = Linear(LN(y))
                 dymb = o.empty((B * L, Dm), BF16)

@@ -53,8 +53,13 @@ class ParamLayout:
         specs = cfg.param_specs()
         ada_w = [s for s in specs if s[0].endswith("adaLN_modulation.1.weight")]
         ada_b = [s for s in specs if s[0].endswith("adaLN_modulation.1.bias")]
-        rest = [s for s in specs if "adaLN_modulation.1." not in s[0]]
-        self.order: List[Tuple[str, Tuple[int, ...]]] = ada_w + ada_b + rest
+        # cross-attention K/V projections of all blocks of a stage act on the SAME caption tokens (dit.py:237,
+        # utils.py:118): stacking their weights turns 28 (+6) medium GEMMs per direction into one large one.
+        kv_m = [s for s in specs if s[0].startswith("patch_mixer.") and s[0].endswith("cross_attn.kv_linear.weight")]
+        kv_b = [s for s in specs if s[0].startswith("blocks.") and s[0].endswith("cross_attn.kv_linear.weight")]
+        special = {s[0] for s in ada_w + ada_b + kv_m + kv_b}
+        rest = [s for s in specs if s[0] not in special]
+        self.order: List[Tuple[str, Tuple[int, ...]]] = ada_w + ada_b + kv_m + kv_b + rest
         self.reference_order = [s[0] for s in specs]
         self.slots: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         off = 0
@@ -80,12 +85,23 @@ class ParamLayout:
 
         self.groups: Dict[str, MatGroup] = {}
         self.groups["ada"] = MatGroup("ada", self.ada_w_offset, 1, self.ada_rows, cfg.dim)
+        for gname, lst in (("kv.patch_mixer", kv_m), ("kv.blocks", kv_b)):
+            if not lst:
+                continue
+            o0 = self.slots[lst[0][0]][0]
+            rows = sum(s[1][0] for s in lst)
+            cols = lst[0][1][1]
+            assert all(s[1][1] == cols for s in lst)
+            assert self.slots[lst[-1][0]][0] + _numel(lst[-1][1]) - o0 == rows * cols, "kv stack must be contiguous"
+            self.groups[gname] = MatGroup(gname, o0, 1, rows, cols)
         for name, shape in rest:
             if len(shape) < 2:
                 continue
             o = self.slots[name][0]
             if name.endswith("mlp.gate.weight"):
                 continue  # expert gate stays fp32 (read by md_moe_gate_fwd directly)
+            if name.endswith("cross_attn.kv_linear.weight"):
+                continue  # part of a kv.* stack
             if len(shape) == 3:  # expert banks [E, in, out]
                 self.groups[name] = MatGroup(name, o, shape[0], shape[1], shape[2])
             elif len(shape) == 4:  # patch-embed conv as [D, C*p*p]; its input is data: no dgrad
