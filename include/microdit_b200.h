@@ -122,6 +122,9 @@ MD_API int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_t ld
 /* SwiGLU (dit.py:88-89): u bf16 [rows, 2f] = [w1 x | w2 x];  h = silu(u[:, :f]) * u[:, f:]. */
 MD_API int md_swiglu_fwd(const void* u, void* h, int64_t rows, int64_t f, void* stream);
 MD_API int md_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int64_t f, void* stream);
+/* act = act(pre), bf16 -> bf16 (the expert GELU, dit.py:136, as its own HBM-bound pass: in the GEMM epilogue it
+ * made the expert GEMM epilogue-bound) */
+MD_API int md_act_fwd(const void* pre, void* out, int64_t n, int act, void* stream);
 /* dpre = dact * act'(pre), bf16 (act: 0 gelu-erf dit.py:136, 1 gelu-tanh utils.py:65). */
 MD_API int md_act_bwd(const void* dact, const void* pre, void* dpre, int64_t n, int act, void* stream);
 /* c_act(bf16) = gelu_tanh(c f32)  (the nn.GELU in every adaLN_modulation, dit.py:227-230);

@@ -72,6 +72,18 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __
   }
 }
 
+// ---------------------------------------------------------------------------------------- act fwd
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out, long long nvec,
+                               int act) {
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 1LL * gridDim.x * blockDim.x) {
+    float x[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(pre + 8 * i), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = act ? gelu_tanh_f(x[e]) : gelu_erf_f(x[e]);
+    *reinterpret_cast<uint4*>(out + 8 * i) = pack8(o);
+  }
+}
+
 // ---------------------------------------------------------------------------------------- act bwd
 __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const __nv_bfloat16* __restrict__ pre,
                                __nv_bfloat16* __restrict__ dpre, long long nvec, int act) {
@@ -295,6 +307,12 @@ extern "C" int md_swiglu_bwd(const void* dh, const void* u, void* du, int64_t ro
   if (!dh || !u || !du || f % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_swiglu_bwd: null pointer or f % 8 != 0");
   swiglu_bwd_kernel<<<grid_for(rows * (f / 8), 256), 256, 0, ST(stream)>>>(CBF(dh), CBF(u), BF(du), rows, (int)f);
   return check_launch("md_swiglu_bwd");
+}
+extern "C" int md_act_fwd(const void* pre, void* out, int64_t n, int act, void* stream) {
+  if (n == 0) return 0;
+  if (!pre || !out || n % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_act_fwd: null pointer or n % 8 != 0");
+  act_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>(CBF(pre), BF(out), n / 8, act);
+  return check_launch("md_act_fwd");
 }
 extern "C" int md_act_bwd(const void* dact, const void* pre, void* dpre, int64_t n, int act, void* stream) {
   if (n == 0) return 0;

@@ -134,7 +134,8 @@ class Engine:
             sv.xin = o.empty((E, B * k, D), BF16)
             o.moe_gather(sv.xm3, sv.idx, sv.xin, B, T, E, k)
             sv.hpre = o.empty((E, B * k, f), BF16); sv.hact = o.empty((E, B * k, f), BF16)
-            o.gemm(sv.xin, st.WT(n + ".mlp.w1"), sv.hpre, epi=EPI_ACT_DUAL, C2=sv.hact, act=ACT_ERF)
+            o.gemm(sv.xin, st.WT(n + ".mlp.w1"), sv.hpre)
+            o.act_fwd(sv.hpre, sv.hact, ACT_ERF)
             sv.h2 = o.empty((E, B * k, D), BF16)
             o.gemm(sv.hact, st.WT(n + ".mlp.w2"), sv.h2)
             out = o.empty((M, D), F32)

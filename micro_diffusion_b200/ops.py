@@ -35,6 +35,7 @@ _PROTOS = {
                     _I64, _I64, _I64, _I64, _I64, _P],
     "md_swiglu_fwd": [_P, _P, _I64, _I64, _P],
     "md_swiglu_bwd": [_P, _P, _P, _I64, _I64, _P],
+    "md_act_fwd": [_P, _P, _I64, _I, _P],
     "md_act_bwd": [_P, _P, _P, _I64, _I, _P],
     "md_gelu_tanh_f32_fwd": [_P, _P, _I64, _P],
     "md_gelu_tanh_f32_bwd": [_P, _P, _P, _I, _I64, _P],
@@ -231,6 +232,9 @@ class CudaOps:
 
     def swiglu_bwd(self, dh, u, du):
         self._call("md_swiglu_bwd", dh.data_ptr(), u.data_ptr(), du.data_ptr(), dh.shape[0], dh.shape[1])
+
+    def act_fwd(self, pre, out, act):
+        self._call("md_act_fwd", pre.data_ptr(), out.data_ptr(), pre.numel(), act)
 
     def act_bwd(self, dact, pre, dpre, act):
         self._call("md_act_bwd", dact.data_ptr(), pre.data_ptr(), dpre.data_ptr(), dact.numel(), act)

@@ -166,6 +166,10 @@ def test_swiglu_act():
     cpu, cu = both(lambda o, dh, u, du: o.swiglu_bwd(dh, u, du), [dh, u, du])
     close(cu[2], cpu[2], "swiglu bwd")
     for act in (0, 1):
+        pre = rnd((rows, f), 3, BF16, 2.0); outa = torch.zeros(rows, f, dtype=BF16)
+        cpu, cu = both(lambda o, pre, outa: o.act_fwd(pre, outa, act), [pre, outa])
+        close(cu[1], cpu[1], f"act fwd {act}")
+    for act in (0, 1):
         pre = rnd((rows, f), 3, BF16, 2.0); dp = torch.zeros(rows, f, dtype=BF16)
         cpu, cu = both(lambda o, dh, pre, dp: o.act_bwd(dh, pre, dp, act), [dh, pre, dp])
         close(cu[2], cpu[2], f"act bwd {act}")
