@@ -244,7 +244,7 @@ def main():
 
     ld = build_model(wl, device)
     opt = FlatAdamW(ld.dit, lr=2.4e-4, weight_decay=0.1, clip_norm=0.25)
-    reducer = GradReducer(ld.dit.store.grad) if world > 1 else None
+    reducer = GradReducer(ld.dit.store) if world > 1 else None
     ops = ld.dit.engine.ops
 
     host = synth_host_batch(per_rank, wl, seed=18 + rank, pinned=True)

@@ -160,27 +160,63 @@ __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long 
 }
 
 // ---------------------------------------------------------------------------------- cast_transpose
-// 32x32 tiles through padded smem: coalesced fp32 reads, coalesced bf16 writes in both orientations.
-__global__ void cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb,
-                                      __nv_bfloat16* __restrict__ wbt, long long rows, long long cols) {
-  __shared__ float tile[32][33];
+// 64x64 tiles, 256 threads: 16-byte fp32 loads, 8-byte bf16 stores in both orientations (the transposed one through
+// a padded smem tile).  HBM-bound: 4 B read + 2 x 2 B written per element.
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wbt,
+                      long long rows, long long cols) {
+  __shared__ float tile[64][65];
   const long long bz = blockIdx.z;
   const float* wsrc = w + bz * rows * cols;
-  const long long c0 = 1LL * blockIdx.x * 32, r0 = 1LL * blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const long long r = r0 + i, c = c0 + threadIdx.x;
-    float v = 0.f;
-    if (r < rows && c < cols) {
-      v = wsrc[r * cols + c];
-      if (wb) wb[bz * rows * cols + r * cols + c] = __float2bfloat16_rn(v);
+  const long long c0 = 1LL * blockIdx.x * 64, r0 = 1LL * blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 columns each, 4 row passes
+  const bool vec = ((cols & 3) == 0) && ((rows & 3) == 0);
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const long long r = r0 + ty + 16 * pass, c = c0 + 4 * tx;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+      if (vec && c + 3 < cols) {
+        const float4 f = *reinterpret_cast<const float4*>(wsrc + r * cols + c);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        if (wb) {
+          __nv_bfloat162 a = __floats2bfloat162_rn(f.x, f.y), b2 = __floats2bfloat162_rn(f.z, f.w);
+          uint2 raw;
+          raw.x = *reinterpret_cast<uint32_t*>(&a);
+          raw.y = *reinterpret_cast<uint32_t*>(&b2);
+          *reinterpret_cast<uint2*>(wb + bz * rows * cols + r * cols + c) = raw;
+        }
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (c + e < cols) {
+            v[e] = wsrc[r * cols + c + e];
+            if (wb) wb[bz * rows * cols + r * cols + c + e] = __float2bfloat16_rn(v[e]);
+          }
+      }
     }
-    tile[i][threadIdx.x] = v;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tile[ty + 16 * pass][4 * tx + e] = v[e];
   }
   __syncthreads();
-  if (wbt) {
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const long long c = c0 + i, r = r0 + threadIdx.x;  // output row = original column
-      if (c < cols && r < rows) wbt[bz * rows * cols + c * rows + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  if (wbt == nullptr) return;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const long long c = c0 + ty + 16 * pass;  // output row = original column
+    const long long r = r0 + 4 * tx;          // output columns = original rows r .. r+3
+    if (c >= cols) continue;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = tile[4 * tx + e][ty + 16 * pass];
+    __nv_bfloat16* dst = wbt + bz * rows * cols + c * rows + r;
+    if (vec && r + 3 < rows) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b2 = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 raw;
+      raw.x = *reinterpret_cast<uint32_t*>(&a);
+      raw.y = *reinterpret_cast<uint32_t*>(&b2);
+      *reinterpret_cast<uint2*>(dst) = raw;
+    } else {
+      for (int e = 0; e < 4; ++e)
+        if (r + e < rows) dst[e] = __float2bfloat16_rn(v[e]);
     }
   }
 }
@@ -364,8 +400,8 @@ extern "C" int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t ba
                                  void* stream) {
   if (batch * rows * cols == 0) return 0;
   if (!w) return md_set_error(MD_ERR_INVALID, "md_cast_transpose: null pointer");
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch);
-  cast_transpose_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(w, BF(wb), BF(wbt), rows, cols);
+  dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64), (unsigned)batch);
+  cast_transpose_kernel<<<grid, 256, 0, ST(stream)>>>(w, BF(wb), BF(wbt), rows, cols);
   return check_launch("md_cast_transpose");
 }
 extern "C" int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, void* stream) {

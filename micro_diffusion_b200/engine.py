@@ -529,6 +529,10 @@ class Engine:
             c.block_sv[i] = None  # release this block's saved activations
         self._kv_bwd("kv.blocks", dkv_b, s.ybf, dy2)
         del dkv_b
+        if self.on_backbone_grads_ready is not None:
+            # every gradient of blocks.* / final_layer.* / the stacked kv.blocks is final from here on: the
+            # data-parallel reducer can start moving ~3/4 of the bytes while the mixer and stem backward still run
+            self.on_backbone_grads_ready()
         # ---- un-mask / mixer-out map
         if cfg.has_mixer_maps:
             dxb = o.empty((B * Tk, D), BF16)
@@ -589,4 +593,5 @@ class Engine:
     # buffers owned by the nn.Module (pos_embed / mask_token), attached by models.dit.DiT
     pos_embed: Optional[torch.Tensor] = None
     weights_token = None  # callable -> hashable; set by models.dit.DiT
+    on_backbone_grads_ready = None  # optional callable, see backward()
     mask_token: Optional[torch.Tensor] = None

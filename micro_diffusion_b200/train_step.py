@@ -47,32 +47,76 @@ class FlatAdamW:
 
 
 class GradReducer:
-    """Data-parallel mean of the flat gradient over the default process group (NCCL on GPUs, gloo in CPU tests)."""
+    """Data-parallel mean of the flat gradient over the default process group (NCCL on GPUs, gloo in CPU tests).
 
-    def __init__(self, flat_grad: torch.Tensor, buckets: int = 4, group=None):
-        self.grad = flat_grad
+    The flat layout ends with blocks.* and final_layer.* (params.ParamLayout keeps the reference order for them), and
+    backward finishes those first.  `early_ranges` (element ranges that are final once the backbone backward is done)
+    are therefore all-reduced on a side stream while the patch-mixer and stem backward still run; `reduce()` then
+    handles the remainder and joins the streams."""
+
+    def __init__(self, store, buckets: int = 4, group=None):
+        self.store = store
+        self.grad = store.grad
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        n = flat_grad.numel()
-        per = (n + buckets - 1) // buckets
-        per = (per + 1023) // 1024 * 1024
-        self.bounds = [(i, min(n, i + per)) for i in range(0, n, per)]
-        self.stream = torch.cuda.Stream(device=flat_grad.device) if flat_grad.is_cuda else None
+        lay = store.layout
+        n = self.grad.numel()
+        # early part 1: everything from the first blocks.* parameter to the end of the buffer
+        first = min(off for name, (off, _) in lay.slots.items()
+                    if (name.startswith("blocks.") or name.startswith("final_layer."))
+                    and not name.endswith("adaLN_modulation.1.weight") and not name.endswith("adaLN_modulation.1.bias")
+                    and not name.endswith("cross_attn.kv_linear.weight"))
+        self.early = [(first, n)]
+        if "kv.blocks" in lay.groups:
+            g = lay.groups["kv.blocks"]
+            self.early.append((g.offset, g.offset + g.numel))
+        # late = the complement
+        cuts = sorted(self.early)
+        self.late, pos = [], 0
+        for a, b in cuts:
+            if a > pos:
+                self.late.append((pos, a))
+            pos = max(pos, b)
+        if pos < n:
+            self.late.append((pos, n))
+        self.buckets = buckets
+        self.stream = torch.cuda.Stream(device=self.grad.device) if self.grad.is_cuda else None
+        self._early_done = False
 
-    def reduce(self):
-        """All-reduce (mean) every bucket; on CUDA the collectives run on a side stream ordered after the producer."""
-        if self.world == 1:
-            return
+    def _split(self, ranges):
+        out = []
+        for a, b in ranges:
+            per = max(1, (b - a + self.buckets - 1) // self.buckets)
+            per = (per + 1023) // 1024 * 1024
+            out += [(i, min(b, i + per)) for i in range(a, b, per)]
+        return out
+
+    def _allreduce(self, ranges):
         if self.stream is None:
-            for a, b in self.bounds:
+            for a, b in self._split(ranges):
                 dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.SUM, group=self.group)
-            self.grad.div_(self.world)
+                self.grad[a:b].div_(self.world)
             return
         self.stream.wait_stream(torch.cuda.current_stream(self.grad.device))
         with torch.cuda.stream(self.stream):
-            for a, b in reversed(self.bounds):  # backward fills the buffer from the back
+            for a, b in self._split(ranges):
                 dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.AVG, group=self.group)
-        torch.cuda.current_stream(self.grad.device).wait_stream(self.stream)
+
+    def reduce_early(self):
+        """Called from inside the LAST microbatch's backward once the backbone gradients are final."""
+        if self.world == 1:
+            return
+        self._allreduce(self.early)
+        self._early_done = True
+
+    def reduce(self):
+        """All-reduce (mean) whatever has not been reduced yet and make the result visible to the compute stream."""
+        if self.world == 1:
+            return
+        self._allreduce(self.late if self._early_done else [(0, self.grad.numel())])
+        self._early_done = False
+        if self.stream is not None:
+            torch.cuda.current_stream(self.grad.device).wait_stream(self.stream)
 
 
 def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, reducer: Optional[GradReducer] = None,
@@ -80,11 +124,16 @@ def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, redu
     """One optimisation step over `batch` (this rank's share of the global batch): returns the mean loss (device)."""
     B = batch["image_latents"].shape[0]
     total = None
-    for s in range(0, B, microbatch):
+    eng = model.dit.engine
+    starts = list(range(0, B, microbatch))
+    for s in starts:
         mb = {k: v[s:s + microbatch] for k, v in batch.items()}
         n = mb["image_latents"].shape[0]
         loss = model(mb)[0]
+        last = s == starts[-1]
+        eng.on_backbone_grads_ready = reducer.reduce_early if (reducer is not None and last) else None
         (loss * (n / B)).backward()  # Composer's microbatch loss scaling
+        eng.on_backbone_grads_ready = None
         total = loss.detach() * (n / B) if total is None else total + loss.detach() * (n / B)
     if reducer is not None:
         reducer.reduce()

@@ -36,13 +36,17 @@ def _worker(rank, world, port, out_path):
     from micro_diffusion_b200.train_step import FlatAdamW, GradReducer, train_step
     ld = _build("P")
     opt = FlatAdamW(ld.dit, lr=1e-3, clip_norm=0.25, eps=1e-2)
-    red = GradReducer(ld.dit.store.grad, buckets=3)
+    red = GradReducer(ld.dit.store, buckets=3)
     full = _batch(4, 5)
     mine = {k: v[rank * 2:(rank + 1) * 2].clone() for k, v in full.items()}
     torch.manual_seed(100 + rank)
-    # gradient of this rank's half, then the mean over ranks
+    # gradient of this rank's half, then the mean over ranks (backbone part reduced from inside backward)
+    eng = ld.dit.engine
     loss = ld(mine)[0]
+    eng.on_backbone_grads_ready = red.reduce_early
     loss.backward()
+    eng.on_backbone_grads_ready = None
+    assert red._early_done and red.late and red.early
     red.reduce()
     g = ld.dit.store.grad.clone()
     opt.step()

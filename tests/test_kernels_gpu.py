@@ -287,9 +287,10 @@ def test_small_utilities():
     xs = rnd((700, 200), 6, BF16); cs = rnd((200,), 7)
     cpu, cu = both(lambda o, xs, cs: o.colsum(xs, cs), [xs, cs])
     close(cu[1], cpu[1], "colsum", 1e-4)
-    w = rnd((3, 100, 72), 8); wb = torch.zeros(3, 100, 72, dtype=BF16); wbt = torch.zeros(3, 72, 100, dtype=BF16)
-    cpu, cu = both(lambda o, w, wb, wbt: o.cast_transpose(w, wb, wbt), [w, wb, wbt])
-    assert torch.equal(cu[1].cpu(), cpu[1]) and torch.equal(cu[2].cpu(), cpu[2])
+    for shp in ((3, 100, 72), (2, 50, 37), (1, 768, 2048), (1, 130, 8)):
+        w = rnd(shp, 8); wb = torch.zeros(shp, dtype=BF16); wbt = torch.zeros(shp[0], shp[2], shp[1], dtype=BF16)
+        cpu, cu = both(lambda o, w, wb, wbt: o.cast_transpose(w, wb, wbt), [w, wb, wbt])
+        assert torch.equal(cu[1].cpu(), cpu[1]) and torch.equal(cu[2].cpu(), cpu[2]), shp
     n = 100003
     p_ = rnd((n,), 9); g_ = rnd((n,), 10); m_ = rnd((n,), 11, scale=0.1); v_ = rnd((n,), 12).abs() * 0.01; ss = torch.zeros(1)
     cpu, cu = both(lambda o, g_, ss: o.sumsq(g_, ss), [g_, ss])
