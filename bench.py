@@ -34,11 +34,11 @@ GLOBAL_BATCH = 2048
 WORKLOADS = {
     "c2": dict(arch="MicroDiT_XL_2", res=32, ch=4, mask=0.75, pos=1.0, p_mean=-0.6, p_std=1.2, micro=512, gf=282.30,
                name="MicroDiT_XL_2 res_256_pretrain mask=0.75 (32x32x4 latents)"),
-    "c3": dict(arch="MicroDiT_XL_2", res=32, ch=4, mask=0.0, pos=1.0, p_mean=-0.6, p_std=1.2, micro=128, gf=714.41,
+    "c3": dict(arch="MicroDiT_XL_2", res=32, ch=4, mask=0.0, pos=1.0, p_mean=-0.6, p_std=1.2, micro=256, gf=714.41,
                name="MicroDiT_XL_2 res_256_finetune mask=0 (32x32x4 latents)"),
-    "c4": dict(arch="MicroDiT_XL_2", res=64, ch=4, mask=0.75, pos=2.0, p_mean=0.0, p_std=0.6, micro=64, gf=1069.36,
+    "c4": dict(arch="MicroDiT_XL_2", res=64, ch=4, mask=0.75, pos=2.0, p_mean=0.0, p_std=0.6, micro=128, gf=1069.36,
                name="MicroDiT_XL_2 res_512_pretrain mask=0.75 (64x64x4 latents)"),
-    "c5": dict(arch="MicroDiT_XL_2", res=64, ch=16, mask=0.0, pos=2.0, p_mean=0.0, p_std=0.6, micro=32, gf=3003.38,
+    "c5": dict(arch="MicroDiT_XL_2", res=64, ch=16, mask=0.0, pos=2.0, p_mean=0.0, p_std=0.6, micro=64, gf=3003.38,
                name="MicroDiT_XL_2 res_512 mask=0 (64x64x16 latents)"),
     "tiny": dict(arch="MicroDiT_Tiny_2", res=32, ch=4, mask=0.75, pos=1.0, p_mean=-0.6, p_std=1.2, micro=256, gf=None,
                  name="MicroDiT_Tiny_2 res_256 mask=0.75"),
