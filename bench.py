@@ -283,10 +283,12 @@ def main():
         sampler.start()
     l0 = ops.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed steps
     e0.record()
     for _ in range(K):
         loss_t = step_resident()
     e1.record()
+    torch.cuda.profiler.stop()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = (ops.launches - l0)

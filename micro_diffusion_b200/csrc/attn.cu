@@ -54,6 +54,32 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
   }
 }
 
+// cp.async variants: the next tile streams into the other buffer while the tensor cores work on this one.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))),
+               "l"(gmem), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))),
+               "l"(gmem), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int HD, int ROWS = kTile>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, long long ld, long long row0,
+                                                long long nrows, int col0) {
+  constexpr int kChunks = HD / 8;
+  for (int i = threadIdx.x; i < ROWS * kChunks; i += blockDim.x) {
+    const int r = i / kChunks, c = (i % kChunks) * 8;
+    const bool ok = row0 + r < nrows;
+    cp_async16(s + r * Smem<HD>::kPitch + c, ok ? g + (row0 + r) * ld + col0 + c : g, ok ? 16 : 0);  // 0 -> zero fill
+  }
+}
+
 // A fragments of a 16 x HD row block starting at smem row r0.
 template <int HD>
 __device__ __forceinline__ void load_a_frags(uint32_t (&a)[HD / 16][4], const __nv_bfloat16* s, int r0, int lane) {
@@ -114,15 +140,20 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_b
                 const __nv_bfloat16* __restrict__ v, long long ldv, __nv_bfloat16* __restrict__ o, long long ldo,
                 float* __restrict__ lse, int H, int Tq, int Tk, float scale_log2) {
   constexpr int P = Smem<HD>::kPitch;
-  __shared__ __align__(16) __nv_bfloat16 sq[kTile * P];
-  __shared__ __align__(16) __nv_bfloat16 sk[KT * P];
-  __shared__ __align__(16) __nv_bfloat16 sv[KT * P];
+  extern __shared__ __align__(16) unsigned char smem_fwd[];
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_fwd);
+  __nv_bfloat16* skv = sq + kTile * P;  // [2 buffers][K | V][KT * P]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y;
   const long long b = blockIdx.z;
   const int q0 = blockIdx.x * kTile;
+  const __nv_bfloat16* kg = k + b * Tk * ldk;
+  const __nv_bfloat16* vg = v + b * Tk * ldv;
 
+  load_tile_async<HD, KT>(skv, kg, ldk, 0, Tk, h * HD);
+  load_tile_async<HD, KT>(skv + KT * P, vg, ldv, 0, Tk, h * HD);
+  cp_async_commit();
   load_tile<HD>(sq, q + b * Tq * ldq, ldq, q0, Tq, h * HD);
   __syncthreads();
   uint32_t qa[HD / 16][4];
@@ -135,10 +166,18 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_b
     for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
 
-  for (int k0 = 0; k0 < Tk; k0 += KT) {
-    __syncthreads();
-    load_tile<HD, KT>(sk, k + b * Tk * ldk, ldk, k0, Tk, h * HD);
-    load_tile<HD, KT>(sv, v + b * Tk * ldv, ldv, k0, Tk, h * HD);
+  for (int k0 = 0, it = 0; k0 < Tk; k0 += KT, ++it) {
+    __nv_bfloat16* sk = skv + (it & 1) * (2 * KT * P);
+    __nv_bfloat16* sv = sk + KT * P;
+    if (k0 + KT < Tk) {  // prefetch the next K/V tile into the other buffer
+      __nv_bfloat16* nk = skv + ((it + 1) & 1) * (2 * KT * P);
+      load_tile_async<HD, KT>(nk, kg, ldk, k0 + KT, Tk, h * HD);
+      load_tile_async<HD, KT>(nk + KT * P, vg, ldv, k0 + KT, Tk, h * HD);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float s[KT / 8][4];
 #pragma unroll
@@ -183,6 +222,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_b
     uint32_t pa[KT / 16][4];
     acc_to_afrag<KT / 16>(pa, s);
     mma_p_m<HD, KT>(oacc, pa, sv, lane);
+    __syncthreads();  // all warps are done with this buffer before the prefetch of tile it+2 lands in it
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -253,14 +293,30 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, con
   constexpr int P = Smem<HD>::kPitch;
   __shared__ __align__(16) __nv_bfloat16 sk[kTile * P];
   __shared__ __align__(16) __nv_bfloat16 sv[kTile * P];
-  __shared__ __align__(16) __nv_bfloat16 sq[kTile * P];
-  __shared__ __align__(16) __nv_bfloat16 sdo[kTile * P];
-  __shared__ float slse[kTile], sdelta[kTile];
+  extern __shared__ __align__(16) unsigned char smem_dkdv[];
+  __nv_bfloat16* sqdo = reinterpret_cast<__nv_bfloat16*>(smem_dkdv);                 // [2 buffers][Q | dO][64 * P]
+  float* sstat = reinterpret_cast<float*>(sqdo + 4 * kTile * P);                       // [2 buffers][lse | delta][64]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y;
   const long long b = blockIdx.z;
   const int k0 = blockIdx.x * kTile;
+  const __nv_bfloat16* qg = q + b * Tq * ldq;
+  const __nv_bfloat16* dog = dout + b * Tq * lddo;
+  const float* lseg = lse + (b * H + h) * Tq;
+  const float* delg = delta + (b * H + h) * Tq;
+  auto prefetch = [&](int q0, int buf) {
+    __nv_bfloat16* dstq = sqdo + buf * (2 * kTile * P);
+    load_tile_async<HD>(dstq, qg, ldq, q0, Tq, h * HD);
+    load_tile_async<HD>(dstq + kTile * P, dog, lddo, q0, Tq, h * HD);
+    if (threadIdx.x < kTile) {  // padded queries: zero-filled stats are harmless here (their Q and dO rows are zero)
+      const bool ok = q0 + threadIdx.x < Tq;
+      cp_async4(sstat + buf * 2 * kTile + threadIdx.x, ok ? lseg + q0 + threadIdx.x : lseg, ok ? 4 : 0);
+      cp_async4(sstat + buf * 2 * kTile + kTile + threadIdx.x, ok ? delg + q0 + threadIdx.x : delg, ok ? 4 : 0);
+    }
+    cp_async_commit();
+  };
+  prefetch(0, 0);
 
   load_tile<HD>(sk, k + b * Tk * ldk, ldk, k0, Tk, h * HD);
   load_tile<HD>(sv, v + b * Tk * ldv, ldv, k0, Tk, h * HD);
@@ -275,14 +331,16 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, con
 #pragma unroll
     for (int j = 0; j < 4; ++j) dkacc[i][j] = dvacc[i][j] = 0.f;
 
-  for (int q0 = 0; q0 < Tq; q0 += kTile) {
-    __syncthreads();
-    load_tile<HD>(sq, q + b * Tq * ldq, ldq, q0, Tq, h * HD);
-    load_tile<HD>(sdo, dout + b * Tq * lddo, lddo, q0, Tq, h * HD);
-    if (threadIdx.x < kTile) {
-      const int qq = q0 + threadIdx.x;
-      slse[threadIdx.x] = qq < Tq ? lse[(b * H + h) * Tq + qq] : INFINITY;  // +inf -> P = 0
-      sdelta[threadIdx.x] = qq < Tq ? delta[(b * H + h) * Tq + qq] : 0.f;
+  for (int q0 = 0, it = 0; q0 < Tq; q0 += kTile, ++it) {
+    const __nv_bfloat16* sq = sqdo + (it & 1) * (2 * kTile * P);
+    const __nv_bfloat16* sdo = sq + kTile * P;
+    const float* slse = sstat + (it & 1) * 2 * kTile;
+    const float* sdelta = slse + kTile;
+    if (q0 + kTile < Tq) {
+      prefetch(q0 + kTile, (it + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     float st[8][4], dpt[8][4];
@@ -306,6 +364,7 @@ attn_bwd_dkdv_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, con
     mma_p_m<HD>(dvacc, pa, sdo, lane);  // dV += P^T . dO
     acc_to_afrag(pa, dpt);
     mma_p_m<HD>(dkacc, pa, sq, lane);   // dK += dS^T . Q
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -333,14 +392,19 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const
   constexpr int P = Smem<HD>::kPitch;
   __shared__ __align__(16) __nv_bfloat16 sq[kTile * P];
   __shared__ __align__(16) __nv_bfloat16 sdo[kTile * P];
-  __shared__ __align__(16) __nv_bfloat16 sk[kTile * P];
-  __shared__ __align__(16) __nv_bfloat16 sv[kTile * P];
+  extern __shared__ __align__(16) unsigned char smem_dq[];
+  __nv_bfloat16* skv = reinterpret_cast<__nv_bfloat16*>(smem_dq);  // [2 buffers][K | V][64 * P]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y;
   const long long b = blockIdx.z;
   const int q0 = blockIdx.x * kTile;
+  const __nv_bfloat16* kg = k + b * Tk * ldk;
+  const __nv_bfloat16* vg = v + b * Tk * ldv;
 
+  load_tile_async<HD>(skv, kg, ldk, 0, Tk, h * HD);
+  load_tile_async<HD>(skv + kTile * P, vg, ldv, 0, Tk, h * HD);
+  cp_async_commit();
   load_tile<HD>(sq, q + b * Tq * ldq, ldq, q0, Tq, h * HD);
   load_tile<HD>(sdo, dout + b * Tq * lddo, lddo, q0, Tq, h * HD);
   __syncthreads();
@@ -360,10 +424,18 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const
 #pragma unroll
     for (int j = 0; j < 4; ++j) dqacc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < Tk; k0 += kTile) {
-    __syncthreads();
-    load_tile<HD>(sk, k + b * Tk * ldk, ldk, k0, Tk, h * HD);
-    load_tile<HD>(sv, v + b * Tk * ldv, ldv, k0, Tk, h * HD);
+  for (int k0 = 0, it = 0; k0 < Tk; k0 += kTile, ++it) {
+    __nv_bfloat16* sk = skv + (it & 1) * (2 * kTile * P);
+    __nv_bfloat16* sv = sk + kTile * P;
+    if (k0 + kTile < Tk) {
+      __nv_bfloat16* nk = skv + ((it + 1) & 1) * (2 * kTile * P);
+      load_tile_async<HD>(nk, kg, ldk, k0 + kTile, Tk, h * HD);
+      load_tile_async<HD>(nk + kTile * P, vg, ldv, k0 + kTile, Tk, h * HD);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     float s[8][4], dp[8][4];
 #pragma unroll
@@ -383,6 +455,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const
     uint32_t pa[4][4];
     acc_to_afrag(pa, s);
     mma_p_m<HD>(dqacc, pa, sk, lane);  // dQ += dS . K
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -564,9 +637,17 @@ extern "C" int md_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   const float sl2 = 1.4426950408889634f / sqrtf((float)hd);
   dim3 grid((unsigned)((Tq + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
   const bool kt80 = Tk > 64 && Tk <= 80;  // the 77 caption tokens: one 80-key tile instead of 64 + a 13-key stub
-#define FWD(HD_, KT_)                                                                                              \
-  attn_fwd_kernel<HD_, KT_><<<grid, 128, 0, ST(stream)>>>(CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, BF(o), ldo, lse, \
-                                                          (int)H, (int)Tq, (int)Tk, sl2)
+#define FWD(HD_, KT_)                                                                                                \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    const size_t sm = (size_t)(kTile + 4 * KT_) * Smem<HD_>::kPitch * sizeof(__nv_bfloat16);                         \
+    if (!attr) {                                                                                                     \
+      cudaFuncSetAttribute(attn_fwd_kernel<HD_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    attn_fwd_kernel<HD_, KT_><<<grid, 128, sm, ST(stream)>>>(CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, BF(o), ldo, lse, \
+                                                             (int)H, (int)Tq, (int)Tk, sl2);                         \
+  } while (0)
   if (hd == 64) { if (kt80) FWD(64, 80); else FWD(64, 64); }
   else { if (kt80) FWD(32, 80); else FWD(32, 64); }
 #undef FWD
@@ -614,18 +695,24 @@ extern "C" int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_
                                                                     (int)Tq);
   dim3 gkv((unsigned)((Tk + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
   dim3 gq((unsigned)((Tq + kTile - 1) / kTile), (unsigned)H, (unsigned)B);
-  if (hd == 64) {
-    attn_bwd_dkdv_kernel<64><<<gkv, 128, 0, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, lse,
-                                                          delta, BF(dk), lddk, BF(dv), lddv, (int)H, (int)Tq, (int)Tk,
-                                                          scale, sl2);
-    attn_bwd_dq_kernel<64><<<gq, 128, 0, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, lse,
-                                                       delta, BF(dq), lddq, (int)H, (int)Tq, (int)Tk, scale, sl2);
-  } else {
-    attn_bwd_dkdv_kernel<32><<<gkv, 128, 0, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, lse,
-                                                          delta, BF(dk), lddk, BF(dv), lddv, (int)H, (int)Tq, (int)Tk,
-                                                          scale, sl2);
-    attn_bwd_dq_kernel<32><<<gq, 128, 0, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv, lse,
-                                                       delta, BF(dq), lddq, (int)H, (int)Tq, (int)Tk, scale, sl2);
-  }
+#define BWD_GENERIC(HD_)                                                                                             \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    const size_t sm_dq = (size_t)4 * kTile * Smem<HD_>::kPitch * sizeof(__nv_bfloat16);                              \
+    const size_t sm_kv = sm_dq + 4 * kTile * sizeof(float);                                                          \
+    if (!attr) {                                                                                                     \
+      cudaFuncSetAttribute(attn_bwd_dkdv_kernel<HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_kv);     \
+      cudaFuncSetAttribute(attn_bwd_dq_kernel<HD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq);       \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    attn_bwd_dkdv_kernel<HD_><<<gkv, 128, sm_kv, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v),    \
+                                                               ldv, lse, delta, BF(dk), lddk, BF(dv), lddv, (int)H,  \
+                                                               (int)Tq, (int)Tk, scale, sl2);                        \
+    attn_bwd_dq_kernel<HD_><<<gq, 128, sm_dq, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v), ldv,  \
+                                                            lse, delta, BF(dq), lddq, (int)H, (int)Tq, (int)Tk,      \
+                                                            scale, sl2);                                             \
+  } while (0)
+  if (hd == 64) BWD_GENERIC(64); else BWD_GENERIC(32);
+#undef BWD_GENERIC
   return check_launch("md_attn_bwd");
 }
