@@ -125,7 +125,7 @@ class DiT(nn.Module):
         self._flat_cpu_init = None
         self._engine = Engine(self.cfg, new, ops)
         self._plist = [params[n] for n in self._param_names]
-        self._dirty = 0
+        self._dirty = self.__dict__.get("_dirty", 0) + 1
         self._engine.weights_token = self._weights_token
         self._anchor = torch.zeros(1, device=device, requires_grad=True)
         return new
@@ -148,7 +148,7 @@ class DiT(nn.Module):
         return (self._dirty, sum(p._version for p in self._plist))
 
     def mark_weights_dirty(self):
-        self._dirty += 1
+        self._dirty = self.__dict__.get("_dirty", 0) + 1  # legal before the first bind
 
     @property
     def engine(self) -> Engine:

@@ -120,8 +120,9 @@ class GradReducer:
 
 
 def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, reducer: Optional[GradReducer] = None,
-               microbatch: int = 256) -> torch.Tensor:
-    """One optimisation step over `batch` (this rank's share of the global batch): returns the mean loss (device)."""
+               microbatch: int = 256, lr: Optional[float] = None) -> torch.Tensor:
+    """One optimisation step over `batch` (this rank's share of the global batch) at learning rate `lr` (default: the
+    optimizer's base rate): returns the mean loss (device)."""
     B = batch["image_latents"].shape[0]
     total = None
     eng = model.dit.engine
@@ -137,6 +138,6 @@ def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, redu
         total = loss.detach() * (n / B) if total is None else total + loss.detach() * (n / B)
     if reducer is not None:
         reducer.reduce()
-    optimizer.step()
+    optimizer.step(lr)
     optimizer.zero_grad()
     return total

@@ -130,7 +130,7 @@ def dit_block(P, pre: str, x: Tensor, y: Tensor, c: Tensor, cfg: PortConfig) -> 
 def timestep_embedding(t: Tensor, dim: int) -> Tensor:
     """utils.py:265-281 ([cos | sin], max_period 10000)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     a = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
 
@@ -156,7 +156,7 @@ def random_mask(noise: Tensor, mask_ratio: float):
     keep = int(t * (1 - mask_ratio))
     shuffle = torch.argsort(noise, dim=1)
     restore = torch.argsort(shuffle, dim=1)
-    mask = torch.ones(b, t)
+    mask = torch.ones(b, t, device=noise.device)
     mask[:, :keep] = 0
     mask = torch.gather(mask, 1, restore)
     return shuffle[:, :keep], restore, mask
