@@ -77,7 +77,7 @@ class Engine:
         scratch = o.empty(tuple(x.shape), BF16)
         return self._ln_add(x, pend, scratch, None, None, gamma=None, T=T)
 
-    def _block_fwd(self, bs: BlockSpec, x, pend, kv, B, T, L, mod, keep: bool):
+    def _block_fwd(self, bs: BlockSpec, x, pend, kv, B, T, L, mod, keep: bool, kv_normed: bool = False):
         """One DiTBlock (dit.py:232-239).  `x` + `pend` is the block input; returns (stream, pending, saved)."""
         o, st, cfg = self.ops, self.store, self.cfg
         P = st.p
@@ -106,7 +106,8 @@ class Engine:
         sv.kv = kv  # this block's [B*L, 2D] column slice of the stage-wide K/V projection
         sv.rq2 = o.empty((M,), F32); sv.rk2 = o.empty((B * L,), F32)
         o.rownorm_fwd(sv.qx, sv.rq2, eps)
-        o.rownorm_fwd(sv.kv[:, :D], sv.rk2, eps)
+        if not kv_normed:  # a PromptCache holds K already normalised
+            o.rownorm_fwd(sv.kv[:, :D], sv.rk2, eps)
         sv.att2 = o.empty((M, D), BF16); sv.lse2 = o.empty((B, bs.xheads, T), F32)
         o.attn_fwd(sv.qx, sv.kv[:, :D], sv.kv[:, D:], sv.att2, sv.lse2, B, bs.xheads, T, L, hd)
         yx = o.empty((M, D), BF16)
@@ -217,7 +218,11 @@ class Engine:
 
     # ================================================================== conditioning stem
     def _stem_fwd(self, cap, drop, cnoise, B, keep: bool, cap_out=None):
-        """dit.py:480-485 + the stacked adaLN linear.  Returns (ybf [B*L,D] bf16, ytok f32, c f32, mod f32, saved)."""
+        """dit.py:480-485 + the stacked adaLN linear: caption half, then the time-dependent half."""
+        return self._time_fwd(self._caption_fwd(cap, drop, B, cap_out), cnoise, B)
+
+    def _caption_fwd(self, cap, drop, B, cap_out=None):
+        """Everything of the conditioning stem that depends on the caption only (dit.py:481-484)."""
         o, st, cfg = self.ops, self.store, self.cfg
         P = st.p
         D, hd, eps = cfg.dim, cfg.head_dim, cfg.norm_eps
@@ -269,7 +274,13 @@ class Engine:
                bias=P["pooled_y_emb_process.fc1.bias"], act=ACT_TANH)
         s.p1n = o.empty((B, D), BF16); s.m_p = o.empty((B,), F32); s.r_p = o.empty((B,), F32)
         o.ln_fwd(s.p1, s.p1n, s.m_p, s.r_p, gamma=P["pooled_y_emb_process.norm.weight"], T=1, eps=eps)
-        # TimestepEmbedder on c_noise (utils.py:283-285; dit.py:480)
+        return s
+
+    def _time_fwd(self, s, cnoise, B):
+        """TimestepEmbedder on c_noise (utils.py:283-285; dit.py:480), c = t + pooled caption, all adaLN vectors."""
+        o, st, cfg = self.ops, self.store, self.cfg
+        P = st.p
+        D = cfg.dim
         s.tfreq = o.empty((B, cfg.freq_dim), BF16)
         o.timestep_embed(cnoise, s.tfreq)
         s.t1pre = o.empty((B, D), BF16); s.t1 = o.empty((B, D), BF16)
@@ -373,8 +384,40 @@ class Engine:
         self._wgrad(da1pre, s.ycap, st.G("y_embedder.y_proj.fc1.weight"))
 
     # ================================================================== denoiser forward
+    def prompt_cache(self, cap):
+        """Sampler fast path: everything the denoiser derives from the caption alone -- the caption
+        stem (dit.py:481-484), the mixer's caption map (dit.py:491) and the K/V projections of all 34 cross-attention
+        layers with K already QK-normalised (utils.py:122-129) -- computed once per prompt batch instead of once per
+        denoiser call (59 calls for a 30-step Heun run).  Inference only; tied to the current weights."""
+        o, st, cfg = self.ops, self.store, self.cfg
+        P = st.p
+        token = self.weights_token() if self.weights_token is not None else None
+        st.refresh_copies(o, token)
+        B, D, Dm, eps = cap.shape[0], cfg.dim, cfg.mixer_dim, cfg.norm_eps
+        pc = NS(B=B, token=token)
+        s = self._caption_fwd(cap, None, B)
+        L = s.L
+        pc.s = s
+        if cfg.use_patch_mixer:
+            if cfg.has_mixer_maps:
+                y_n = o.empty((B * L, D), BF16); m = o.empty((B * L,), F32); r = o.empty((B * L,), F32)
+                o.ln_fwd(s.y2, y_n, m, r, gamma=P["patch_mixer_map_y.0.weight"], T=L, eps=eps)
+                pc.ymix = o.empty((B * L, Dm), BF16)
+                o.gemm(y_n, st.W("patch_mixer_map_y.1.weight"), pc.ymix)
+            else:
+                pc.ymix = s.ybf
+            pc.kv_m = self._kv_fwd("kv.patch_mixer", pc.ymix, len(cfg.mixer_blocks), 2 * Dm)
+            rk = o.empty((B * L,), F32)
+            for i in range(len(cfg.mixer_blocks)):
+                o.rownorm_fwd(pc.kv_m[:, i * 2 * Dm:i * 2 * Dm + Dm], rk, eps)
+        pc.kv_b = self._kv_fwd("kv.blocks", s.ybf, len(cfg.blocks), 2 * D)
+        rk = o.empty((B * L,), F32)
+        for i in range(len(cfg.blocks)):
+            o.rownorm_fwd(pc.kv_b[:, i * 2 * D:i * 2 * D + D], rk, eps)
+        return pc
+
     def _denoiser_fwd(self, lat, eps_noise, rnd, sigma_in, cap, drop, mask_ratio, mask_noise, edm, keep: bool,
-                      raw_t=None, cap_out=None):
+                      raw_t=None, cap_out=None, prompt=None):
         o, st, cfg = self.ops, self.store, self.cfg
         P = st.p
         st.refresh_copies(o, self.weights_token() if self.weights_token is not None else None)
@@ -400,7 +443,14 @@ class Engine:
         o.gemm(c.patches, st.W("x_embedder.proj.weight"), x0, epi=EPI_RESID, res=self.pos_embed.reshape(T, D),
                res_mod=T, bias=P["x_embedder.proj.bias"])
         # ---- conditioning
-        s = self._stem_fwd(cap, drop, cnoise, B, keep, cap_out)
+        if prompt is not None:
+            assert not keep and prompt.B == B, "a PromptCache serves inference calls of the batch it was built for"
+            if self.weights_token is not None and prompt.token != self.weights_token():
+                raise RuntimeError("PromptCache is stale: the weights changed since it was built")
+            s = self._time_fwd(NS(**vars(prompt.s)), cnoise, B)
+        else:
+            s = self._stem_fwd(cap, drop, cnoise, B, keep, cap_out)
+        kvn = prompt is not None
         c.stem = s
         L = s.L
         mod = s.mod
@@ -412,18 +462,19 @@ class Engine:
                 o.ln_fwd(x0, c.xin_n, c.m_xin, c.r_xin, gamma=P["patch_mixer_map_xin.0.weight"], T=T, eps=cfg.norm_eps)
                 xm = o.empty((B * T, Dm), F32)
                 o.gemm(c.xin_n, st.W("patch_mixer_map_xin.1.weight"), xm, epi=EPI_F32)
-                c.y_n = o.empty((B * L, D), BF16); c.m_y = o.empty((B * L,), F32); c.r_y = o.empty((B * L,), F32)
-                o.ln_fwd(s.y2, c.y_n, c.m_y, c.r_y, gamma=P["patch_mixer_map_y.0.weight"], T=L, eps=cfg.norm_eps)
-                c.ymix = o.empty((B * L, Dm), BF16)
-                o.gemm(c.y_n, st.W("patch_mixer_map_y.1.weight"), c.ymix)
+                if prompt is None:
+                    c.y_n = o.empty((B * L, D), BF16); c.m_y = o.empty((B * L,), F32); c.r_y = o.empty((B * L,), F32)
+                    o.ln_fwd(s.y2, c.y_n, c.m_y, c.r_y, gamma=P["patch_mixer_map_y.0.weight"], T=L, eps=cfg.norm_eps)
+                    c.ymix = o.empty((B * L, Dm), BF16)
+                    o.gemm(c.y_n, st.W("patch_mixer_map_y.1.weight"), c.ymix)
             else:
                 xm, c.ymix = x0, s.ybf
             c.x0 = x0
             pend = None
             D2m = 2 * Dm
-            kv_m = self._kv_fwd("kv.patch_mixer", c.ymix, len(cfg.mixer_blocks), D2m)
+            kv_m = prompt.kv_m if kvn else self._kv_fwd("kv.patch_mixer", c.ymix, len(cfg.mixer_blocks), D2m)
             for i, bs in enumerate(cfg.mixer_blocks):
-                xm, pend, sv = self._block_fwd(bs, xm, pend, kv_m[:, i * D2m:(i + 1) * D2m], B, T, L, mod, keep)
+                xm, pend, sv = self._block_fwd(bs, xm, pend, kv_m[:, i * D2m:(i + 1) * D2m], B, T, L, mod, keep, kvn)
                 c.mixer_sv.append(sv)
         else:
             xm, pend = x0, None
@@ -452,9 +503,9 @@ class Engine:
             xb = xm
         # ---- backbone (dit.py:510-511)
         c.block_sv = []
-        kv_b = self._kv_fwd("kv.blocks", s.ybf, len(cfg.blocks), 2 * D)
+        kv_b = prompt.kv_b if kvn else self._kv_fwd("kv.blocks", s.ybf, len(cfg.blocks), 2 * D)
         for i, bs in enumerate(cfg.blocks):
-            xb, pend, sv = self._block_fwd(bs, xb, pend, kv_b[:, i * 2 * D:(i + 1) * 2 * D], B, Tk, L, mod, keep)
+            xb, pend, sv = self._block_fwd(bs, xb, pend, kv_b[:, i * 2 * D:(i + 1) * 2 * D], B, Tk, L, mod, keep, kvn)
             c.block_sv.append(sv)
         # ---- final layer (utils.py:236-240)
         fo = st.layout.ada_offset["final_layer"]
@@ -477,11 +528,13 @@ class Engine:
         o.edm_loss_fwd(c.ftok, c.keep_rows, lat, c.xn, c.coef, c.per_sample, c.loss, self.cfg.patch_size, c.Tk)
         return c
 
-    def denoise(self, x_noisy, sigma, cap, mask_ratio=0.0, mask_noise=None, edm=None, want_raw=False):
-        """model_forward_wrapper (model.py:144-179) without gradients: D_x (and optionally F_x, mask)."""
+    def denoise(self, x_noisy, sigma, cap, mask_ratio=0.0, mask_noise=None, edm=None, want_raw=False, prompt=None):
+        """model_forward_wrapper (model.py:144-179) without gradients: D_x (and optionally F_x, mask).
+        `prompt` = prompt_cache(cap) skips the caption-only work."""
         o = self.ops
         zero = o.zeros(tuple(x_noisy.shape), F32)
-        c = self._denoiser_fwd(x_noisy, zero, None, sigma, cap, None, mask_ratio, mask_noise, edm, keep=False)
+        c = self._denoiser_fwd(x_noisy, zero, None, sigma, cap, None, mask_ratio, mask_noise, edm, keep=False,
+                               prompt=prompt)
         B, C, Hh, Ww = x_noisy.shape
         dx = o.empty((B, C, Hh, Ww), F32)
         fx = o.empty((B, C, Hh, Ww), F32) if want_raw else None

@@ -86,6 +86,8 @@ class LatentDiffusion(_Base):
             pass
         self.dit._fsdp_wrap = True
         self.last_per_sample_loss = None
+        self.cache_prompt = True  # sampler fast path: caption-only work once per edm_sampler_loop (engine.prompt_cache)
+        self._prompt_memo = None
 
     def _edm_scalars(self):
         e = self.edm_config
@@ -173,11 +175,18 @@ class LatentDiffusion(_Base):
                 eng = self.dit.engine
                 xin = x.float().contiguous()
                 cap = self.dit._caption_f16(y)
+                memo = self.__dict__.get("_prompt_memo")  # set by edm_sampler_loop for the duration of one run
+                if memo is not None and (memo["y"] is not y or memo["cfg"] != cfg):
+                    memo = None
                 if cfg != 1.0:  # DiT.forward_with_cfg (dit.py:521-550) around the fused denoiser
                     xin2 = torch.cat([xin, xin], 0)
-                    cap2 = torch.cat([cap, torch.zeros_like(cap)], 0)
                     sg2 = torch.cat([sigma_b, sigma_b], 0)
-                    _, fx, _ = eng.denoise(xin2, sg2, cap2, 0.0, None, self._edm_scalars(), want_raw=True)
+                    if memo is not None and memo["pc"] is None:
+                        memo["cap"] = torch.cat([cap, torch.zeros_like(cap)], 0)
+                        memo["pc"] = eng.prompt_cache(memo["cap"])
+                    cap2 = memo["cap"] if memo is not None else torch.cat([cap, torch.zeros_like(cap)], 0)
+                    _, fx, _ = eng.denoise(xin2, sg2, cap2, 0.0, None, self._edm_scalars(), want_raw=True,
+                                           prompt=memo["pc"] if memo is not None else None)
                     cond, unc = torch.split(fx, B, dim=0)
                     f = unc + cfg * (cond - unc)
                     sd = self.edm_config.sigma_data
@@ -185,7 +194,10 @@ class LatentDiffusion(_Base):
                     d = (sd ** 2 / (sg ** 2 + sd ** 2)) * xin + (sg * sd / (sg ** 2 + sd ** 2).sqrt()) * f
                     return {"sample": d}
                 noise = torch.rand(B, self.dit.cfg.num_patches, device=x.device) if mask_ratio > 0 else None
-                d, _, mask = eng.denoise(xin, sigma_b, cap, mask_ratio, noise, self._edm_scalars())
+                if memo is not None and memo["pc"] is None:
+                    memo["pc"] = eng.prompt_cache(cap)
+                d, _, mask = eng.denoise(xin, sigma_b, cap, mask_ratio, noise, self._edm_scalars(),
+                                         prompt=memo["pc"] if memo is not None else None)
                 return {"sample": d, "mask": mask}
         sd = self.edm_config.sigma_data
         sg = sigma_b.to(x.dtype).reshape(-1, 1, 1, 1)
@@ -223,6 +235,16 @@ class LatentDiffusion(_Base):
         t_steps = (e.sigma_max ** (1 / e.rho) + i / (n - 1) * (e.sigma_min ** (1 / e.rho) - e.sigma_max ** (1 / e.rho))) ** e.rho
         t_steps = torch.cat([torch.as_tensor(t_steps), torch.zeros_like(t_steps[:1])])
         x_next = x.to(torch.float64) * t_steps[0]
+        # the caption is the same tensor for all 2n-1 denoiser calls: its stem and the 34 cross-attention K/V projections
+        # are computed once (engine.prompt_cache) -- the reference recomputes them per call (dit.py:481-485, utils.py:116-129)
+        self._prompt_memo = {"y": y, "cfg": cfg if cfg > 1.0 else 1.0, "pc": None, "cap": None} if self.cache_prompt else None
+        try:
+            return self._heun(x_next, t_steps, y, fwd, n, **kwargs)
+        finally:
+            self._prompt_memo = None
+
+    def _heun(self, x_next, t_steps, y, fwd, n, **kwargs):
+        e = self.edm_config
         for k, (t_cur, t_next) in enumerate(zip(t_steps[:-1], t_steps[1:])):
             x_cur = x_next
             gamma = min(e.S_churn / n, np.sqrt(2) - 1) if e.S_min <= t_cur <= e.S_max else 0

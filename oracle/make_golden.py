@@ -87,5 +87,41 @@ def main():
               f"({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+SAMPLER_SEED, SAMPLER_STEPS = 31, 3
+
+
+def sampler_inputs(name):
+    """Start noise and captions of the sampler fixture: pure functions of the seed."""
+    c = configs.PARITY_CONFIGS[name]
+    ct = c["ctor"]
+    g = torch.Generator().manual_seed(SAMPLER_SEED)
+    x = torch.randn(2, ct["in_channels"], ct["input_size"], ct["input_size"], generator=g)
+    y = torch.randn(2, 1, 77, ct.get("caption_channels", 1024), generator=g).half().float()
+    return x, y
+
+
+def main_sampler(names=("P", "S")):
+    """tests/golden/sampler_<cfg>.pt: edm_sampler_loop (model.py:232-297) of the unmodified reference, fp32, 3 Heun
+    steps, with and without classifier-free guidance."""
+    ref_dit, ref_model, _ = ref_import.load_reference()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for name in names:
+        c = configs.PARITY_CONFIGS[name]
+        ct = c["ctor"]
+        net = ref_dit.DiT(**ct)
+        net.load_state_dict(weights.synth_state_dict(net.state_dict(), seed=WEIGHT_SEED))
+        ld = ref_import.build_reference_latent_diffusion(net, c["p_mean"], c["p_std"], c["mask_ratio"], ct["input_size"])
+        ld.eval()
+        x, y = sampler_inputs(name)
+        fx = {"steps": SAMPLER_STEPS}
+        for cfg in (1.0, 3.0):
+            fx[f"out_cfg{cfg}"] = ld.edm_sampler_loop(x.clone(), y.clone(), steps=SAMPLER_STEPS, cfg=cfg).float()
+        torch.save(fx, os.path.join(out_dir, f"sampler_{name}.pt"))
+        print(name, {k: (tuple(v.shape), float(v.abs().mean())) for k, v in fx.items() if torch.is_tensor(v)})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "sampler":
+        main_sampler()
+    else:
+        main()

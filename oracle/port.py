@@ -272,3 +272,37 @@ def latent_diffusion_forward(P, cfg: PortConfig, batch: dict, rnd_normal, eps_no
     if "drop_caption_mask" in batch:
         cond = (cond * batch["drop_caption_mask"].view([-1] + [1] * (cond.dim() - 1))).to(cond.dtype)
     return edm_loss(P, cfg, latents.float(), cond.float(), rnd_normal, eps_noise, mask_ratio, mask_noise)
+
+
+def edm_sampler(P, cfg: PortConfig, x: Tensor, y: Tensor, steps: int, guidance: float = 1.0, sigma_min: float = 0.002,
+                sigma_max: float = 80.0, rho: float = 7.0) -> Tensor:
+    """edm_sampler_loop (model.py:232-297) with the defaults of edm_config (model.py:74-88: S_churn 0, S_noise 1, so
+    gamma = 0 and the churn noise term vanishes -- `randn_like` is still drawn by the reference but multiplied by 0);
+    guidance > 1 goes through DiT.forward_with_cfg (dit.py:521-550).  fp64 state, fp32 denoiser."""
+    P = {k: v.detach() for k, v in P.items()}
+    i = torch.arange(steps, dtype=torch.float64)
+    t_steps = (sigma_max ** (1 / rho) + i / (steps - 1) * (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
+    t_steps = torch.cat([t_steps, torch.zeros(1, dtype=torch.float64)])
+
+    def den(xf: Tensor, sigma: Tensor) -> Tensor:
+        sg = sigma.to(torch.float32).reshape(1).expand(xf.shape[0])
+        if guidance > 1.0:
+            c_skip, c_out, c_in, c_noise = edm_precondition(cfg, sg.view(-1, 1, 1, 1))
+            xin = (c_in * xf)
+            out = dit_forward(P, cfg, torch.cat([xin, xin], 0), torch.cat([c_noise.flatten()] * 2),
+                              torch.cat([y, torch.zeros_like(y)], 0))["sample"]
+            cond, unc = torch.split(out, xf.shape[0], dim=0)
+            return c_skip * xf + c_out * (unc + guidance * (cond - unc))
+        return denoise(P, cfg, xf, sg.view(-1, 1, 1, 1), y)["sample"]
+
+    with torch.no_grad():
+        x_next = x.to(torch.float64) * t_steps[0]
+        for k in range(steps):
+            t_hat, t_next = t_steps[k], t_steps[k + 1]
+            x_hat = x_next
+            d_cur = (x_hat - den(x_hat.float(), t_hat).double()) / t_hat
+            x_next = x_hat + (t_next - t_hat) * d_cur
+            if k < steps - 1:
+                d_prime = (x_next - den(x_next.float(), t_next).double()) / t_next
+                x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
+    return x_next.float()

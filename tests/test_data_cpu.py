@@ -1,0 +1,101 @@
+"""Row f-3 on CPU: MDS shard layout round trip, the reference's sample dict, rank partitioning, device loader."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+def _make(tmp, n=11, C=4, res=32, shard_samples=4, with512=True):
+    from micro_diffusion_b200.data import write_mds
+    rng = np.random.default_rng(0)
+    samples = []
+    for i in range(n):
+        s = {"caption": f"prompt number {i} é", "caption_latents": rng.standard_normal(77 * 1024).astype(np.float16).tobytes(),
+             "latents_256": rng.standard_normal(C * res * res).astype(np.float16).tobytes()}
+        if with512:
+            s["latents_512"] = rng.standard_normal(C * 64 * 64).astype(np.float16).tobytes()
+        samples.append(s)
+    cols = {"caption": "str", "caption_latents": "bytes", "latents_256": "bytes"}
+    if with512:
+        cols["latents_512"] = "bytes"
+    write_mds(str(tmp), samples, cols, shard_samples=shard_samples)
+    return samples
+
+
+def test_shard_layout_and_sample_dict(tmp_path):
+    from micro_diffusion_b200.data import LatentsDataset
+    samples = _make(tmp_path)
+    index = json.load(open(os.path.join(tmp_path, "index.json")))
+    assert [s["samples"] for s in index["shards"]] == [4, 4, 3]
+    # independent check of the byte layout of the first shard
+    raw = open(os.path.join(tmp_path, "shard.00000.mds"), "rb").read()
+    n = int(np.frombuffer(raw, np.uint32, 1)[0])
+    off = np.frombuffer(raw, np.uint32, n + 1, 4)
+    assert n == 4 and off[-1] == len(raw) and off[0] > 4 + 4 * (n + 1)  # a JSON column header sits in between
+    hdr = json.loads(raw[4 + 4 * (n + 1):off[0]])
+    assert hdr["column_names"] == sorted(hdr["column_names"])
+    ds = LatentsDataset(str(tmp_path), image_size=256, cap_drop_prob=0.0)
+    assert len(ds) == 11
+    for i in (0, 3, 4, 10, -1):
+        it = ds[i]
+        ref = samples[i]
+        assert it["drop_caption_mask"] == 1.0
+        assert it["caption_latents"].shape == (1, 77, 1024) and it["caption_latents"].dtype == torch.float16
+        assert it["image_latents"].shape == (4, 32, 32)
+        assert it["caption_latents"].numpy().tobytes() == ref["caption_latents"]
+        assert it["image_latents"].numpy().tobytes() == ref["latents_256"]
+    ds512 = LatentsDataset(str(tmp_path), image_size=512)
+    assert ds512[5]["image_latents"].shape == (4, 64, 64)
+    assert ds512[5]["image_latents"].numpy().tobytes() == samples[5]["latents_512"]
+    with pytest.raises(IndexError):
+        ds.shards[0].raw(4)
+    assert str(bytes(ds.shards[0].raw(1)["caption"]), "utf-8") == samples[1]["caption"]
+
+
+def test_caption_drop_and_torch_dataloader(tmp_path):
+    from micro_diffusion_b200.data import build_streaming_latents_dataloader
+    _make(tmp_path, n=8, with512=False)
+    torch.manual_seed(0)
+    dl = build_streaming_latents_dataloader(str(tmp_path), batch_size=4, image_size=256, cap_drop_prob=0.5,
+                                            shuffle=False, drop_last=True)
+    batches = list(dl)
+    assert len(batches) == 2
+    b = batches[0]
+    assert b["image_latents"].shape == (4, 4, 32, 32) and b["caption_latents"].shape == (4, 1, 77, 1024)
+    assert b["drop_caption_mask"].dtype == torch.float64  # collated Python floats (latents_loader.py:49-51)
+    allm = torch.cat([x["drop_caption_mask"] for x in batches])
+    assert set(allm.tolist()) <= {0.0, 1.0} and 0 < allm.sum() < 8
+
+
+def test_device_loader_partitions_ranks_and_feeds_the_model(tmp_path):
+    from micro_diffusion_b200.data import DeviceBatchLoader, LatentsDataset
+    samples = _make(tmp_path, n=13, with512=False)
+    ds = LatentsDataset(str(tmp_path), image_size=256, cap_drop_prob=0.1)
+    seen = []
+    for r in range(2):
+        dl = DeviceBatchLoader(ds, batch_size=3, device="cpu", rank=r, world=2, shuffle=True, seed=5)
+        assert len(dl) == 2
+        ids = dl._indices(0)
+        seen.append(set(ids.tolist()))
+        got = list(dl)
+        assert len(got) == 2
+        for b, batch in enumerate(got):
+            for j in range(3):
+                i = int(ids[b * 3 + j])
+                assert batch["image_latents"][j].numpy().tobytes() == samples[i]["latents_256"]
+                assert batch["caption_latents"][j].numpy().tobytes() == samples[i]["caption_latents"]
+            assert batch["drop_caption_mask"].dtype == torch.float64
+        # next epoch reshuffles
+        assert not np.array_equal(dl._indices(1), ids)
+    assert not (seen[0] & seen[1]) and len(seen[0]) == len(seen[1]) == 6
+    # the batches drive the model unchanged
+    from oracle.emu_ops import EmuOps
+    from tests import parity_common as pc
+    ld = pc.build_product("P", ops_factory=lambda d: EmuOps(d, exact=True))
+    dl = DeviceBatchLoader(ds, batch_size=4, device="cpu", shuffle=False)
+    batch = next(iter(dl))
+    loss = ld(batch)[0]
+    loss.backward()
+    assert torch.isfinite(loss)

@@ -80,3 +80,46 @@ def test_eval_forward_and_seeded_rng_order():
     with torch.no_grad():
         out = ld.eval_forward({k: v.clone() for k, v in batch.items()})
     assert out[0].dim() == 0 and out[1] is None
+
+
+@pytest.mark.parametrize("name", ["P", "S"])
+def test_sampler_matches_reference_fixture_with_and_without_prompt_cache(name):
+    """Row f-4: edm_sampler_loop through the engine (exact CPU kernels) reproduces the reference's sampler output, and
+    the once-per-prompt caption/K-V cache changes nothing."""
+    from oracle.make_golden import SAMPLER_STEPS, sampler_inputs
+    fx = torch.load(os.path.join(pc.GOLDEN, f"sampler_{name}.pt"), weights_only=False)
+    ld = pc.build_product(name, ops_factory=lambda d: EmuOps(d, exact=True))
+    ld.eval()
+    x, y = sampler_inputs(name)
+    for g in (1.0, 3.0):
+        calls = []
+        orig = ld.dit.engine.prompt_cache
+        ld.dit.engine.prompt_cache = lambda cap: (calls.append(1), orig(cap))[1]
+        ld.cache_prompt = True
+        a = ld.edm_sampler_loop(x.clone(), y.half(), steps=SAMPLER_STEPS, cfg=g)
+        assert len(calls) == 1  # 2*steps-1 denoiser calls, one caption pass
+        ld.cache_prompt = False
+        b = ld.edm_sampler_loop(x.clone(), y.half(), steps=SAMPLER_STEPS, cfg=g)
+        assert len(calls) == 1
+        ld.dit.engine.prompt_cache = orig
+        assert pc.rel_l2(a, fx[f"out_cfg{g}"]) < 2e-5, g
+        assert pc.rel_l2(b, fx[f"out_cfg{g}"]) < 2e-5, g
+        assert pc.rel_l2(a, b) < 1e-6
+    assert ld._prompt_memo is None
+
+
+def test_prompt_cache_goes_stale_with_the_weights():
+    ld = pc.build_product("P", ops_factory=lambda d: EmuOps(d, exact=True))
+    ld.eval()
+    eng = ld.dit.engine
+    cap = torch.randn(2, 1, 77, 1024).half()
+    pcache = eng.prompt_cache(cap)
+    x = torch.randn(2, 4, 32, 32)
+    sg = torch.full((2,), 1.5)
+    d0, _, _ = eng.denoise(x, sg, cap, edm=ld._edm_scalars(), prompt=pcache)
+    d1, _, _ = eng.denoise(x, sg, cap, edm=ld._edm_scalars())
+    assert pc.rel_l2(d0, d1) < 1e-6
+    with torch.no_grad():
+        next(ld.dit.parameters()).add_(0.1)
+    with pytest.raises(RuntimeError):
+        ld.dit.engine.denoise(x, sg, cap, edm=ld._edm_scalars(), prompt=pcache)

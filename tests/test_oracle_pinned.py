@@ -68,3 +68,17 @@ def test_mask_and_routing_match_reference():
     noise = torch.rand(3, 64)
     keep, restore, mask = port.random_mask(noise, 0.75)
     assert torch.equal(keep, m["ids_keep"]) and torch.equal(restore, m["ids_restore"]) and torch.equal(mask, m["mask"])
+
+
+@pytest.mark.parametrize("name", ["P", "S"])
+def test_port_sampler_matches_golden(name):
+    """edm_sampler_loop of the unmodified reference (fixture from oracle.make_golden sampler) vs the restatement."""
+    from oracle.make_golden import SAMPLER_STEPS, sampler_inputs
+    fx = torch.load(os.path.join(pc.GOLDEN, f"sampler_{name}.pt"), weights_only=False)
+    c = configs.PARITY_CONFIGS[name]
+    sd = weights.synth_state_dict(_template(name), seed=pc.WEIGHT_SEED)
+    x, y = sampler_inputs(name)
+    cfg = pc.port_config(c, c["ctor"])
+    for g in (1.0, 3.0):
+        out = port.edm_sampler(sd, cfg, x, y, SAMPLER_STEPS, guidance=g)
+        assert pc.rel_l2(out, fx[f"out_cfg{g}"]) < 1e-5, g
