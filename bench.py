@@ -337,7 +337,7 @@ def main():
                 for k, (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                     tf = f"{fl / (ms * 1e-3) / 1e12:.1f}" if fl else ""
                     f.write(f"{k},{n},{ms:.3f},{ms / tot_ms:.4f},{tf}\n")
-                f.write("# GEMM launches by shape\n")
+                f.write("# GEMM / attention launches by shape\n")
                 for k, (n, ms, fl) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
                     if " " not in k:
                         continue

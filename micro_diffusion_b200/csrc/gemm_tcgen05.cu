@@ -42,7 +42,10 @@ struct GemmCfg {
   static constexpr int kStages = (kStageBytes > 40 * 1024) ? 4 : (kStageBytes > 30 * 1024 ? 6 : 7);
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 256 or 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging for the TMA store: 8 warps x 2 buffers x (32 rows x 32 bf16 = 2 KB, 64B-swizzled)
+  static constexpr int kStoreBufBytes = 32 * 32 * 2;
+  static constexpr int kStoreBytes = 8 * 2 * kStoreBufBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // Cheap activations for the epilogue (it shares 4 issue ports with nothing else but is on the critical path of
@@ -86,12 +89,13 @@ __device__ __forceinline__ void decode_tile(int r, int m_blocks, int n_blocks, i
 template <int BLOCK_N, bool kMN, int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmDev p) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
   using Cfg = GemmCfg<BLOCK_N, kCtas>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* store_stage = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_stage + Cfg::kStoreBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + Cfg::kAccStages;
@@ -103,6 +107,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -229,6 +234,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     constexpr int kChunksPerWarp = BLOCK_N / 64;  // 32-column chunks per warp
+    uint8_t* my_stage = store_stage + (warp - 4) * (2 * Cfg::kStoreBufBytes);
+    uint32_t store_it = 0;  // chunks this warp has handed to the TMA (selects the staging buffer)
     uint32_t acc_it = 0;
     for (long long tile = tile0; tile < tiles; tile += tile_step, ++acc_it) {
       long long t = tile;
@@ -293,6 +300,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (p.epi == EPI_RESID_F32) load_res(c + 1);
         }
         const int col0 = colbase + c * 32;
+        if (p.tma_store) {
+          // bf16 store through shared memory: each lane (= output row) drops its 64 bytes into a 64B-swizzled 32 x 32
+          // box and one lane hands the box to the TMA, which writes full lines and clips at the tensor edge.  Direct
+          // st.global from this layout is one half-sector request per lane per store and kept the L1->XBAR port ~70 %
+          // busy (ncu, profiles/r01_ncu_gemm_full.md).
+          const int row0 = (mb * kCtas + cta_rank) * kBlockM + q * 32;
+          if (row0 < p.M && col0 < p.N) {  // warp-uniform
+            if (p.bias != nullptr) {
+              const int ncols = min(32, p.N - col0);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
+            }
+            uint8_t* buf = my_stage + (store_it & 1) * Cfg::kStoreBufBytes;
+            if (lane == 0) tma_store_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
+            __syncwarp();
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 a;
+              a.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+              a.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+              a.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+              a.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ sw) << 4)) = a;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmC, buf, col0, row0, bz);
+              tma_store_commit();
+            }
+            ++store_it;
+          }
+        } else
         // No divergent `continue`: every lane must reach the next (warp-aligned) tcgen05 instruction together.
         if (row_ok && col0 < p.N && has_k) {
           const int ncols = min(32, p.N - col0);
@@ -406,6 +448,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else mbar_arrive(&tempty_bar[as]);
       }
     }
+    if (p.tma_store && lane == 0) tma_store_wait<0>();  // staging memory must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -462,10 +505,26 @@ static int make_map(CUtensorMap* map, const void* ptr, long long cols, long long
   return 0;
 }
 
+// bf16 output viewed as [batch][M][N]; box = [1][32 rows][32 cols], 64B swizzle (what the epilogue warps stage).
+static int make_store_map(CUtensorMap* map, void* ptr, long long cols, long long rows, long long batch, long long ld,
+                          long long batch_stride) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2,
+                           static_cast<cuuint64_t>(batch > 1 ? batch_stride : rows * ld) * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the output map");
+  return 0;
+}
+
 template <int BLOCK_N, bool kMN, int kCtas>
-static int launch(const md_gemm_args* a, const GemmDev& dev, int sm_count, cudaStream_t stream) {
+static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, kCtas>;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   int rc;
   if (!kMN) {
     rc = make_map(&tmA, a->A, a->K, a->M, a->batch, a->lda, a->strideA, kBlockM);
@@ -477,6 +536,21 @@ static int launch(const md_gemm_args* a, const GemmDev& dev, int sm_count, cudaS
     if (rc) return rc;
     rc = make_map(&tmB, a->B, a->N, a->K, a->batch, a->ldb, a->strideB, kBlockK);
     if (rc) return rc;
+  }
+  // TMA store for the plain bf16 epilogue when the output view is TMA-addressable (16-byte aligned base and pitches)
+  static int tma_store_env = -1;
+  if (tma_store_env == -1) {
+    const char* e = getenv("MD_GEMM_TMA_STORE");
+    tma_store_env = e ? atoi(e) : 1;
+  }
+  dev.tma_store = 0;
+  if (tma_store_env && a->epilogue == EPI_STORE_BF16 && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 &&
+      (a->ldc % 8) == 0 && (a->batch == 1 || (a->strideC % 8) == 0)) {
+    rc = make_store_map(&tmC, a->C, a->N, a->M, a->batch, a->ldc, a->strideC);
+    if (rc) return rc;
+    dev.tma_store = 1;
+  } else {
+    tmC = tmA;  // unused
   }
   auto kern = gemm_tcgen05_kernel<BLOCK_N, kMN, kCtas>;
   static bool attr_set = false;
@@ -502,7 +576,7 @@ static int launch(const md_gemm_args* a, const GemmDev& dev, int sm_count, cudaS
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, dev);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, dev);
   if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
   return 0;
 }

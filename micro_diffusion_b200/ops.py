@@ -103,7 +103,7 @@ class CudaOps:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _call(self, name, *args):
+    def _call(self, name, *args, label=None, flops=0):
         prof = self.profile
         if prof is not None:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -111,7 +111,7 @@ class CudaOps:
         rc = getattr(self.lib, name)(*args, self._stream())
         if prof is not None:
             e1.record()
-            prof.append((name, e0, e1, 0))
+            prof.append((name + (" " + label if label else ""), e0, e1, flops))
         self.launches += 1
         if rc != 0:
             raise MicroditLibraryError(f"{name} failed ({rc}): {self.lib.md_last_error().decode()}")
@@ -218,13 +218,15 @@ class CudaOps:
     # ------------------------------------------------------------------ attention
     def attn_fwd(self, q, k, v, o, lse, B, H, Tq, Tk, hd):
         self._call("md_attn_fwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-                   o.data_ptr(), o.stride(0), lse.data_ptr(), B, H, Tq, Tk, hd)
+                   o.data_ptr(), o.stride(0), lse.data_ptr(), B, H, Tq, Tk, hd,
+                   label=f"B={B} H={H} Tq={Tq} Tk={Tk}", flops=4 * B * H * Tq * Tk * hd)
 
     def attn_bwd(self, dout, q, k, v, o, lse, delta, dq, dk, dv, B, H, Tq, Tk, hd):
         self._call("md_attn_bwd", dout.data_ptr(), dout.stride(0), q.data_ptr(), q.stride(0), k.data_ptr(),
                    k.stride(0), v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(),
                    delta.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
-                   dv.stride(0), B, H, Tq, Tk, hd)
+                   dv.stride(0), B, H, Tq, Tk, hd,
+                   label=f"B={B} H={H} Tq={Tq} Tk={Tk}", flops=10 * B * H * Tq * Tk * hd)
 
     # ------------------------------------------------------------------ feed-forward tails
     def swiglu_fwd(self, u, h):

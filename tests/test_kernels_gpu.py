@@ -325,3 +325,34 @@ def test_gemm_via_ops(layout, M, N, K, epi):
             Cm = torch.zeros(M, N, dtype=BF16); C2 = torch.zeros(M, N, dtype=BF16)
             cpu, cu = both(lambda o, A, B, Cm, C2, bias: o.gemm(A, B, Cm, layout=layout, epi=4, C2=C2, bias=bias, act=act, alpha=0.05), [A, B, Cm, C2, bias])
             close(cu[2], cpu[2], "gemm act pre"); close(cu[3], cpu[3], "gemm act out")
+
+
+@pytest.mark.parametrize("layout,M,N,K,batch,ld_extra,col_off", [
+    (0, 1000, 200, 320, 1, 0, 0),      # ragged M and N (N % 32 != 0): the TMA store box is clipped at both edges
+    (0, 96, 128, 192, 1, 0, 0),        # single 128-row block -> 1-CTA kernel, 128-wide tile
+    (0, 257, 1096, 128, 1, 0, 0),      # odd tail block of a CTA pair + partial last 256-wide tile
+    (0, 640, 256, 256, 3, 0, 0),       # batched (expert banks)
+    (0, 384, 192, 128, 1, 320, 64),    # output is a column slice of a wider buffer (packed qkv / kv layouts)
+    (1, 512, 384, 700, 1, 0, 0),       # MN-major operands with the bf16 store
+    (0, 300, 72, 64, 1, 0, 0),         # N = 72: pitch 144 B, 16-byte aligned rows
+    (0, 130, 100, 64, 1, 2, 0),        # pitch 102 elements (204 B rows) is not TMA-addressable: direct-store fallback
+])
+def test_gemm_bf16_store_paths(layout, M, N, K, batch, ld_extra, col_off):
+    """Plain bf16 epilogue: staged through shared memory + cp.async.bulk.tensor store when the output view is
+    16-byte addressable, direct st.global otherwise; both against the CPU contract, including untouched neighbours."""
+    sa = (batch, M, K) if layout == 0 else (batch, K, M)
+    sb = (batch, N, K) if layout == 0 else (batch, K, N)
+    A = rnd(sa, 1, BF16); B = rnd(sb, 2, BF16)
+    if batch == 1:
+        A, B = A[0], B[0]
+    wide = torch.full((batch, M, N + ld_extra), 7.0, dtype=BF16) if batch > 1 else torch.full((M, N + ld_extra), 7.0, dtype=BF16)
+
+    def run(o, A, B, wide):
+        Cv = wide[..., col_off:col_off + N]
+        o.gemm(A, B, Cv, layout=layout, epi=0)
+
+    cpu, cu = both(run, [A, B, wide])
+    close(cu[2][..., col_off:col_off + N], cpu[2][..., col_off:col_off + N], "gemm bf16 store")
+    if ld_extra:
+        keep = torch.ones(N + ld_extra, dtype=torch.bool); keep[col_off:col_off + N] = False
+        assert torch.equal(cu[2].cpu()[..., keep], cpu[2][..., keep]), "store leaked outside its column slice"
