@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libmicrodit_b200.so"
+import os
+
+# MD_LIB_PATH: developer knob to load an experimental build of the same ABI (tools/build_variant.py)
+_LIB_PATH = Path(os.environ.get("MD_LIB_PATH") or Path(__file__).resolve().parent / "libmicrodit_b200.so")
 _lib = None
 
 

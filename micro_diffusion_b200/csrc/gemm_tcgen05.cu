@@ -32,7 +32,13 @@ namespace md {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 384;  // 4 control warps + 8 epilogue warps
+#ifndef MD_EPI_WARPS
+#define MD_EPI_WARPS 4
+#endif
+constexpr int kEpiWarps = MD_EPI_WARPS;  // 4 (one per TMEM lane quarter) or 8 (two per quarter, half of the columns each)
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps: 4 or 8");
+constexpr int kColSplit = kEpiWarps / 4;
+constexpr int kThreads = 128 + 32 * kEpiWarps;  // 4 control warps + the epilogue warps
 
 template <int BLOCK_N, int kCtas = 1>
 struct GemmCfg {
@@ -44,7 +50,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 256 or 512 (power of two)
   // epilogue staging for the TMA store: 8 warps x 2 buffers x (32 rows x 32 bf16 = 2 KB, 64B-swizzled)
   static constexpr int kStoreBufBytes = 32 * 32 * 2;
-  static constexpr int kStoreBytes = 8 * 2 * kStoreBufBytes;
+  static constexpr int kStoreBytes = kEpiWarps * 2 * kStoreBufBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -67,9 +73,17 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   return 0.5f * x * (1.0f + th);
 }
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b);
+__device__ __forceinline__ uint4 pack_bf16x8(float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                             float a7);
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint4 pack_bf16x8(float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                             float a7) {
+  return make_uint4(pack_bf16(a0, a1), pack_bf16(a2, a3), pack_bf16(a4, a5), pack_bf16(a6, a7));
 }
 
 // Tile order inside one (batch, split) slice: bands of kBand n-blocks, n fastest inside a band, then m, then the
@@ -116,7 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8 * kCtas);  // one arrive per epilogue warp (of both CTAs in pair mode)
+      mbar_init(&tempty_bar[i], kEpiWarps * kCtas);  // one arrive per epilogue warp (of both CTAs in pair mode)
     }
     mbar_fence_init();
   }
@@ -233,7 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // 8 warps: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 4) / 4.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    constexpr int kChunksPerWarp = BLOCK_N / 64;  // 32-column chunks per warp
+    constexpr int kChunksPerWarp = BLOCK_N / kColSplit / 32;  // 32-column chunks per warp
     uint8_t* my_stage = store_stage + (warp - 4) * (2 * Cfg::kStoreBufBytes);
     uint32_t store_it = 0;  // chunks this warp has handed to the TMA (selects the staging buffer)
     uint32_t acc_it = 0;
@@ -256,8 +270,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long rrow = 1LL * bz * p.strideC + 1LL * (p.res_mod > 0 ? row % p.res_mod : row) * p.ldc;
       const float* gate_row = nullptr;
       if (p.gate != nullptr && row_ok) gate_row = p.gate + 1LL * (row / p.rows_per_gate) * p.ldgate;
-      const int colbase = nb * BLOCK_N + half * (BLOCK_N / 2);
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
+      const int colbase = nb * BLOCK_N + half * (BLOCK_N / kColSplit);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / kColSplit);
       const bool want_res = (p.epi == EPI_RESID_F32) && row_ok && has_k;
 
       // residual prefetch for chunk 0 is independent of the accumulator: issue it before waiting on the MMAs
@@ -284,10 +298,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       uint32_t rnext[32];
-      tmem_ld_32x32(tbase, rnext);
+      if (p.debug != 2) tmem_ld_32x32(tbase, rnext);
 
 #pragma unroll 1
-      for (int c = 0; c < kChunksPerWarp; ++c) {
+      for (int c = 0; c < (p.debug == 2 ? 0 : kChunksPerWarp); ++c) {
         tmem_ld_wait();
         float v[32];
         float4 resv[8];
@@ -300,7 +314,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (p.epi == EPI_RESID_F32) load_res(c + 1);
         }
         const int col0 = colbase + c * 32;
-        if (p.tma_store) {
+        if (p.debug == 1) {
+          if (v[0] == 123.456f && v[31] == -654.321f) reinterpret_cast<float*>(p.C)[0] = v[5];  // keep the loads alive
+        } else if (p.tma_store) {
           // bf16 store through shared memory: each lane (= output row) drops its 64 bytes into a 64B-swizzled 32 x 32
           // box and one lane hands the box to the TMA, which writes full lines and clips at the tensor edge.  Direct
           // st.global from this layout is one half-sector request per lane per store and kept the L1->XBAR port ~70 %
@@ -352,7 +368,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                              "f"(v[j + 2]), "f"(v[j + 3])
                              : "memory");
             } else {
-              for (int j = 0; j < ncols; ++j) atomicAdd(dst + j, v[j]);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)  // static indices only: a runtime index would push v[] into local memory
+                if (j < ncols) atomicAdd(dst + j, v[j]);
             }
           } else if (p.epi == EPI_ACT_DUAL) {
             // C = pre-activation (bf16), C2 = act(pre) (bf16); the activation is taken on the bf16-rounded
@@ -363,26 +381,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                              ((reinterpret_cast<uintptr_t>(d2) & 15) == 0);
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              uint4 a, g;
-              uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
-              uint32_t* gp = reinterpret_cast<uint32_t*>(&g);
+              float x[8], y[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float x0 = bf16_round(v[j + 2 * e]), x1 = bf16_round(v[j + 2 * e + 1]);
-                ap[e] = pack_bf16(x0, x1);
-                gp[e] = p.act ? pack_bf16(gelu_tanh_fast(x0), gelu_tanh_fast(x1))
-                              : pack_bf16(gelu_erf_fast(x0), gelu_erf_fast(x1));
+              for (int e = 0; e < 8; ++e) {
+                x[e] = bf16_round(v[j + e]);
+                y[e] = p.act ? gelu_tanh_fast(x[e]) : gelu_erf_fast(x[e]);
               }
+              const uint4 a = pack_bf16x8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+              const uint4 g = pack_bf16x8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
               if (vec) {
                 *reinterpret_cast<uint4*>(d1 + j) = a;
                 *reinterpret_cast<uint4*>(d2 + j) = g;
               } else {
-                const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&a);
-                const __nv_bfloat16* gh = reinterpret_cast<const __nv_bfloat16*>(&g);
+#pragma unroll
                 for (int e = 0; e < 8; ++e)
                   if (j + e < ncols) {
-                    d1[j + e] = ah[e];
-                    d2[j + e] = gh[e];
+                    const uint32_t aw = (e >> 1) == 0 ? a.x : (e >> 1) == 1 ? a.y : (e >> 1) == 2 ? a.z : a.w;
+                    const uint32_t gw = (e >> 1) == 0 ? g.x : (e >> 1) == 1 ? g.y : (e >> 1) == 2 ? g.z : g.w;
+                    const unsigned short ab = static_cast<unsigned short>((e & 1) ? (aw >> 16) : (aw & 0xffffu));
+                    const unsigned short gb = static_cast<unsigned short>((e & 1) ? (gw >> 16) : (gw & 0xffffu));
+                    d1[j + e] = __ushort_as_bfloat16(ab);
+                    d2[j + e] = __ushort_as_bfloat16(gb);
                   }
               }
             }
@@ -393,14 +412,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (ncols == 32 && ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
 #pragma unroll
                   for (int j = 0; j < 32; j += 8) {
-                    uint4 a;
-                    uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) ap[e] = pack_bf16(v[j + 2 * e], v[j + 2 * e + 1]);
-                    *reinterpret_cast<uint4*>(d2 + j) = a;
+                    *reinterpret_cast<uint4*>(d2 + j) =
+                        pack_bf16x8(v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
                   }
                 } else {
-                  for (int j = 0; j < ncols; ++j) d2[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (j < ncols) d2[j] = __float2bfloat16_rn(v[j]);
                 }
               }
               if (gate_row != nullptr) {
@@ -418,14 +436,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                  uint4 a;
-                  uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) ap[e] = pack_bf16(v[j + 2 * e], v[j + 2 * e + 1]);
-                  *reinterpret_cast<uint4*>(dst + j) = a;
+                  *reinterpret_cast<uint4*>(dst + j) =
+                      pack_bf16x8(v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
                 }
               } else {
-                for (int j = 0; j < ncols; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) dst[j] = __float2bfloat16_rn(v[j]);
               }
             } else {  // EPI_STORE_F32 / EPI_RESID_F32
               float* dst = reinterpret_cast<float*>(p.C) + crow + col0;
@@ -434,7 +451,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int j = 0; j < 32; j += 4)
                   *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               } else {
-                for (int j = 0; j < ncols; ++j) dst[j] = v[j];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) dst[j] = v[j];
               }
             }
           }
@@ -543,6 +562,12 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
     const char* e = getenv("MD_GEMM_TMA_STORE");
     tma_store_env = e ? atoi(e) : 1;
   }
+  static int debug_env = -1;
+  if (debug_env == -1) {
+    const char* e = getenv("MD_GEMM_DEBUG");
+    debug_env = e ? atoi(e) : 0;
+  }
+  dev.debug = debug_env;
   dev.tma_store = 0;
   if (tma_store_env && a->epilogue == EPI_STORE_BF16 && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 &&
       (a->ldc % 8) == 0 && (a->batch == 1 || (a->strideC % 8) == 0)) {

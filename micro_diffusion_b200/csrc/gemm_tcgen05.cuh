@@ -19,6 +19,7 @@ struct GemmDev {
   const float* gate;
   long long ldc, strideC, strideBias, ldgate;
   int M, N, K, batch, splits, rows_per_gate, epi, res_mod, act;
+  int debug;      // diagnostics only (MD_GEMM_DEBUG): 1 = epilogue skips its stores, 2 = also skips the TMEM loads
   int tma_store;  // bf16 store epilogue goes through smem staging + cp.async.bulk.tensor (tmC valid)
   float alpha;
 };

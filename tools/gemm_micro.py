@@ -1,19 +1,48 @@
-import ctypes as C, os, sys, torch
+"""GEMM micro-benchmark at the dominant C2 shapes: md_gemm_bf16 vs torch.matmul (cuBLAS) on the same operands.
+MD_GEMM_DEBUG=1|2 (stores skipped | TMEM loads skipped too) shows what the epilogue costs."""
+import os
+import sys
+
+import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from micro_diffusion_b200.ops import CudaOps
-o = CudaOps("cuda:0"); dev = torch.device("cuda:0")
-def bench(M,N,K,epi=0,iters=30):
-    A=torch.randn(M,K,device=dev).bfloat16(); B=torch.randn(N,K,device=dev).bfloat16()
-    Cm=torch.zeros(M,N,device=dev,dtype=torch.bfloat16 if epi==0 else torch.float32)
-    res=torch.zeros(M,N,device=dev) if epi==2 else None
-    for _ in range(3): o.gemm(A,B,Cm,epi=epi,res=res)
-    torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+from micro_diffusion_b200.ops import CudaOps  # noqa: E402
+
+o = CudaOps("cuda:0")
+dev = torch.device("cuda:0")
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters): o.gemm(A,B,Cm,epi=epi,res=res)
-    e1.record(); torch.cuda.synchronize()
-    ms=e0.elapsed_time(e1)/iters
-    print(f"M={M} N={N} K={K} epi={epi}: {ms*1e3:.1f} us {2*M*N*K/ms/1e9:.0f} TF/s", flush=True)
-print("MD_GEMM_DEBUG=", os.environ.get("MD_GEMM_DEBUG"), "MD_GEMM_EPI=", os.environ.get("MD_GEMM_EPI"))
-for K in (256, 1024, 4096):
-    bench(16384, 1024, K); bench(16384, 3072, K)
-bench(16384,1024,1024,epi=2)
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench(M, N, K, batch=1, iters=20, cublas=True):
+    sa = (batch, M, K) if batch > 1 else (M, K)
+    sb = (batch, N, K) if batch > 1 else (N, K)
+    A = torch.randn(sa, device=dev).bfloat16()
+    B = torch.randn(sb, device=dev).bfloat16()
+    Cm = torch.zeros((batch, M, N) if batch > 1 else (M, N), device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: o.gemm(A, B, Cm), iters)
+    fl = 2 * M * N * K * batch
+    line = f"M={M} N={N} K={K} b={batch}: ours {ms * 1e3:8.1f} us {fl / ms / 1e9:7.0f} TF/s"
+    if cublas:
+        Bt = B.transpose(-1, -2)
+        ms2 = timeit(lambda: torch.matmul(A, Bt, out=Cm), iters)
+        line += f" | cuBLAS {ms2 * 1e3:8.1f} us {fl / ms2 / 1e9:7.0f} TF/s | ours/cuBLAS {ms2 / ms:.2f}"
+    print(line, flush=True)
+
+
+print("MD_GEMM_DEBUG=", os.environ.get("MD_GEMM_DEBUG"), "MD_GEMM_TMA_STORE=", os.environ.get("MD_GEMM_TMA_STORE"))
+cub = not os.environ.get("MD_GEMM_DEBUG")
+for shp in [(32768, 1024, 1024), (131072, 768, 768), (131072, 2304, 768), (32768, 3072, 1024), (131072, 768, 2304),
+            (32768, 1024, 3072), (32768, 3072, 768, 8), (32768, 768, 3072, 8), (39424, 57344, 1024)]:
+    bench(*shp[:3], batch=shp[3] if len(shp) > 3 else 1, cublas=cub, iters=10 if shp[1] > 50000 else 20)
