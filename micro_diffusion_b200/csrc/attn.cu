@@ -607,6 +607,209 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, co
   }
 }
 
+// ---------------------------------------------------------------------- backward, few keys, many queries
+// Cross-attention to the caption (Tk <= 80, Tq = 256 / 1024): one CTA per (head, sample) keeps K and V in shared
+// memory, streams the 64-query tiles (cp.async double buffer) and carries dK / dV in registers across the tiles, so
+// Q / dO / K / V are read exactly once and no partial dK / dV ever leaves the SM.  Warp w owns keys 16w..16w+15; with
+// KT = 80 the fifth key block is split by head-dim columns (16 per warp).
+template <int HD, int DP>
+__device__ __forceinline__ void mma_p_m_slice(float (&out)[2][4], const uint32_t (&pa)[4][4], const __nv_bfloat16* m,
+                                              int lane, int dp) {
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t b[4];
+    const int mi = lane >> 3;
+    ldsm_x4_t(b, m + (kt * 16 + (lane & 7) + (mi & 1) * 8) * Smem<HD>::kPitch + dp * 16 + (mi >> 1) * 8);
+    mma16816(out[0], pa[kt], b[0], b[1]);
+    mma16816(out[1], pa[kt], b[2], b[3]);
+  }
+}
+
+template <int HD, int KT>
+__global__ void __launch_bounds__(128)
+attn_bwd_cross_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ q,
+                      long long ldq, const __nv_bfloat16* __restrict__ k, long long ldk,
+                      const __nv_bfloat16* __restrict__ v, long long ldv, const float* __restrict__ lse,
+                      __nv_bfloat16* __restrict__ dq, long long lddq, __nv_bfloat16* __restrict__ dk, long long lddk,
+                      __nv_bfloat16* __restrict__ dv, long long lddv, int H, int Tq, int Tk, float scale,
+                      float scale_log2) {
+  constexpr int P = Smem<HD>::kPitch;
+  constexpr int PP = KT + 8;
+  constexpr bool kExtra = KT > 64;               // fifth 16-key block (keys 64..79)
+  constexpr int kSliceWarps = HD / 16;           // warps that take a 16-column slice of the fifth block
+  extern __shared__ __align__(16) unsigned char smem_cross[];
+  __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(smem_cross);
+  __nv_bfloat16* sv = sk + KT * P;
+  __nv_bfloat16* sqdo = sv + KT * P;             // [2 buffers][Q | dO][64 * P]
+  __nv_bfloat16* sp = sqdo + 4 * kTile * P;      // [64][PP]
+  __nv_bfloat16* sds = sp + kTile * PP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.x;
+  const long long b = blockIdx.y;
+  const __nv_bfloat16* qg = q + b * Tq * ldq;
+  const __nv_bfloat16* dog = dout + b * Tq * lddo;
+  const float* lseg = lse + (b * H + h) * Tq;
+
+  auto prefetch = [&](int q0, int buf) {
+    __nv_bfloat16* dst = sqdo + buf * (2 * kTile * P);
+    load_tile_async<HD>(dst, qg, ldq, q0, Tq, h * HD);
+    load_tile_async<HD>(dst + kTile * P, dog, lddo, q0, Tq, h * HD);
+    cp_async_commit();
+  };
+  load_tile_async<HD, KT>(sk, k + b * Tk * ldk, ldk, 0, Tk, h * HD);
+  load_tile_async<HD, KT>(sv, v + b * Tk * ldv, ldv, 0, Tk, h * HD);
+  prefetch(0, 0);  // one group: K, V and the first Q / dO tile
+
+  float dvacc[HD / 8][4], dkacc[HD / 8][4];
+  float dvx[2][4], dkx[2][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dvacc[i][j] = dkacc[i][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dvx[i][j] = dkx[i][j] = 0.f;
+
+  for (int q0 = 0, it = 0; q0 < Tq; q0 += kTile, ++it) {
+    const __nv_bfloat16* sq = sqdo + (it & 1) * (2 * kTile * P);
+    const __nv_bfloat16* sdo = sq + kTile * P;
+    float lrow[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = q0 + warp * 16 + g + r * 8;
+      lrow[r] = row < Tq ? lseg[row] : INFINITY;  // +inf -> P = 0 for padded queries
+    }
+    if (q0 + kTile < Tq) {
+      prefetch(q0 + kTile, (it + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    uint32_t qa[HD / 16][4], doa[HD / 16][4];
+    load_a_frags<HD>(qa, sq, warp * 16, lane);
+    load_a_frags<HD>(doa, sdo, warp * 16, lane);
+    float s[KT / 8][4], dp[KT / 8][4];
+#pragma unroll
+    for (int i = 0; i < KT / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.f;
+    mma_a_bt<HD, KT>(s, qa, sk, lane);    // S  = Q . K^T
+    mma_a_bt<HD, KT>(dp, doa, sv, lane);  // dP = dO . V^T
+    float dsum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < KT / 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = nt * 8 + 2 * t + (j & 1);
+        const float pr = key < Tk ? exp2f(s[nt][j] * scale_log2 - lrow[j >> 1]) : 0.f;
+        s[nt][j] = pr;
+        dsum[j >> 1] += pr * dp[nt][j];
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 1);
+      dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 2);
+    }
+#pragma unroll
+    for (int nt = 0; nt < KT / 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dp[nt][j] = s[nt][j] * (dp[nt][j] - dsum[j >> 1]);  // dS
+    {
+      uint32_t pa[KT / 16][4];
+      acc_to_afrag<KT / 16>(pa, dp);
+      float dqacc[HD / 8][4];
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dqacc[i][j] = 0.f;
+      mma_p_m<HD, KT>(dqacc, pa, sk, lane);  // dQ = dS . K
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + g + r * 8;
+        if (row < Tq) {
+          __nv_bfloat16* dst = dq + (b * Tq + row) * lddq + h * HD;
+#pragma unroll
+          for (int i = 0; i < HD / 8; ++i)
+            *reinterpret_cast<uint32_t*>(dst + i * 8 + 2 * t) = pack2(dqacc[i][2 * r] * scale, dqacc[i][2 * r + 1] * scale);
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < KT / 8; ++nt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = warp * 16 + g + r * 8;
+        *reinterpret_cast<uint32_t*>(sp + row * PP + nt * 8 + 2 * t) = pack2(s[nt][2 * r], s[nt][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(sds + row * PP + nt * 8 + 2 * t) = pack2(dp[nt][2 * r], dp[nt][2 * r + 1]);
+      }
+    __syncthreads();
+    {  // dV += P^T . dO and dK += dS^T . Q for this warp's 16 keys (reduction over the tile's 64 queries)
+      uint32_t pta[4][4], dsta[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int mi = lane >> 3;
+        const int rowq = ks * 16 + (lane & 7) + (mi >> 1) * 8;
+        const int colk = warp * 16 + (mi & 1) * 8;
+        ldsm_x4_t(pta[ks], sp + rowq * PP + colk);
+        ldsm_x4_t(dsta[ks], sds + rowq * PP + colk);
+      }
+      mma_p_m<HD, 64>(dvacc, pta, sdo, lane);
+      mma_p_m<HD, 64>(dkacc, dsta, sq, lane);
+      if (kExtra && warp < kSliceWarps) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const int mi = lane >> 3;
+          const int rowq = ks * 16 + (lane & 7) + (mi >> 1) * 8;
+          const int colk = 64 + (mi & 1) * 8;
+          ldsm_x4_t(pta[ks], sp + rowq * PP + colk);
+          ldsm_x4_t(dsta[ks], sds + rowq * PP + colk);
+        }
+        mma_p_m_slice<HD, 0>(dvx, pta, sdo, lane, warp);
+        mma_p_m_slice<HD, 0>(dkx, dsta, sq, lane, warp);
+      }
+    }
+    __syncthreads();  // sp / sds / this Q-dO buffer are rewritten by the next iterations
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = warp * 16 + g + r * 8;
+    if (key < Tk) {
+      __nv_bfloat16* pk = dk + (b * Tk + key) * lddk + h * HD;
+      __nv_bfloat16* pv = dv + (b * Tk + key) * lddv + h * HD;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        *reinterpret_cast<uint32_t*>(pk + i * 8 + 2 * t) = pack2(dkacc[i][2 * r] * scale, dkacc[i][2 * r + 1] * scale);
+        *reinterpret_cast<uint32_t*>(pv + i * 8 + 2 * t) = pack2(dvacc[i][2 * r], dvacc[i][2 * r + 1]);
+      }
+    }
+  }
+  if (kExtra && warp < kSliceWarps) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = 64 + g + r * 8;
+      if (key < Tk) {
+        __nv_bfloat16* pk = dk + (b * Tk + key) * lddk + h * HD + warp * 16;
+        __nv_bfloat16* pv = dv + (b * Tk + key) * lddv + h * HD + warp * 16;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          *reinterpret_cast<uint32_t*>(pk + i * 8 + 2 * t) = pack2(dkx[i][2 * r] * scale, dkx[i][2 * r + 1] * scale);
+          *reinterpret_cast<uint32_t*>(pv + i * 8 + 2 * t) = pack2(dvx[i][2 * r], dvx[i][2 * r + 1]);
+        }
+      }
+    }
+  }
+}
+
+template <int HD, int KT>
+static size_t cross_bwd_smem() {
+  return sizeof(__nv_bfloat16) * (2 * KT * Smem<HD>::kPitch + 4 * kTile * Smem<HD>::kPitch + 2 * kTile * (KT + 8));
+}
+
 template <int HD, int KT>
 static size_t small_bwd_smem() {
   const size_t base = 2 * kTile * Smem<HD>::kPitch + 2 * KT * Smem<HD>::kPitch;
@@ -682,6 +885,25 @@ extern "C" int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_
     if (hd == 64) { if (Tk <= 64) BWD_SMALL(64, 64); else BWD_SMALL(64, 80); }
     else { if (Tk <= 64) BWD_SMALL(32, 64); else BWD_SMALL(32, 80); }
 #undef BWD_SMALL
+    return check_launch("md_attn_bwd");
+  }
+  if (Tk <= 80) {  // few keys, many queries (cross-attention at T = 256 / 1024): K / V resident, dK / dV in registers
+    dim3 gs((unsigned)H, (unsigned)B);
+#define BWD_CROSS(HD_, KT_)                                                                                          \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    const size_t sm = cross_bwd_smem<HD_, KT_>();                                                                    \
+    if (!attr) {                                                                                                     \
+      cudaFuncSetAttribute(attn_bwd_cross_kernel<HD_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);  \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    attn_bwd_cross_kernel<HD_, KT_><<<gs, 128, sm, ST(stream)>>>(CBF(dout), lddo, CBF(q), ldq, CBF(k), ldk, CBF(v),  \
+                                                                 ldv, lse, BF(dq), lddq, BF(dk), lddk, BF(dv), lddv, \
+                                                                 (int)H, (int)Tq, (int)Tk, scale, sl2);              \
+  } while (0)
+    if (hd == 64) { if (Tk <= 64) BWD_CROSS(64, 64); else BWD_CROSS(64, 80); }
+    else { if (Tk <= 64) BWD_CROSS(32, 64); else BWD_CROSS(32, 80); }
+#undef BWD_CROSS
     return check_launch("md_attn_bwd");
   }
   if (H * hd > 2048) return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_bwd: H*hd must be <= 2048");

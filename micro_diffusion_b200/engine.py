@@ -135,6 +135,8 @@ class Engine:
             sv.xin = o.empty((E, B * k, D), BF16)
             o.moe_gather(sv.xm3, sv.idx, sv.xin, B, T, E, k)
             sv.hpre = o.empty((E, B * k, f), BF16); sv.hact = o.empty((E, B * k, f), BF16)
+            # GELU stays a separate HBM-bound pass: in the GEMM epilogue (EPI_ACT_DUAL) the erf + second store make the
+            # tile epilogue-bound (456 vs 1240 TFLOP/s measured, profiles/r01_per_op_c2_v15_f1.csv)
             o.gemm(sv.xin, st.WT(n + ".mlp.w1"), sv.hpre)
             o.act_fwd(sv.hpre, sv.hact, ACT_ERF)
             sv.h2 = o.empty((E, B * k, D), BF16)
