@@ -244,7 +244,7 @@ def main():
 
     ld = build_model(wl, device)
     opt = FlatAdamW(ld.dit, lr=2.4e-4, weight_decay=0.1, clip_norm=0.25)
-    reducer = GradReducer(ld.dit.store) if world > 1 else None
+    reducer = GradReducer(ld.dit.store, ops=ld.dit.engine.ops) if world > 1 else None
     ops = ld.dit.engine.ops
 
     host = synth_host_batch(per_rank, wl, seed=18 + rank, pinned=True)
@@ -359,7 +359,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": args.global_batch, "per_gpu_batch": per_rank,
                        "microbatch": micro, "parallelism": f"dp{world}", "optimizer": "clip0.25+AdamW (fused, in step)",
-                       "l2": "per-step working set (activations > 40 GB per microbatch) far exceeds the 126 MB L2"},
+                       "l2": "per-step working set (activations > 40 GB per microbatch) far exceeds the 126 MB L2",
+                       "grad_exchange": (f"NCCL all-reduce (mean) of the flat fp32 gradient, overlap={reducer.overlap}, "
+                                         f"{reducer.reserve} SMs left to NCCL while it overlaps") if reducer else None},
             "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "loss": last_loss},
             "gpu_launches": launches,

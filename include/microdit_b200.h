@@ -67,6 +67,7 @@ typedef struct md_gemm_args {
   int32_t splits;   /* split of the reduction dimension (>=1) */
   int32_t act;      /* activation of MD_EPI_ACT_DUAL */
   float alpha;      /* 0 is treated as 1 */
+  int32_t sm_limit; /* > 0: use at most this many SMs (persistent grid) -- leaves room for a concurrent collective */
 } md_gemm_args;
 
 /* Dense / batched bf16 GEMM, fp32 accumulation, tcgen05 tensor cores fed by TMA.

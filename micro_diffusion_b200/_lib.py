@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("strideA", C.c_int64), ("strideB", C.c_int64), ("strideC", C.c_int64), ("strideBias", C.c_int64),
         ("ldgate", C.c_int64), ("rows_per_gate", C.c_int64), ("res_mod", C.c_int64),
         ("layout", C.c_int32), ("epilogue", C.c_int32), ("splits", C.c_int32), ("act", C.c_int32),
-        ("alpha", C.c_float),
+        ("alpha", C.c_float), ("sm_limit", C.c_int32),
     ]
 
 

@@ -638,6 +638,8 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
     if (dev_id < 64) cached_sm[dev_id] = sm_count;
   }
 
+  if (a->sm_limit > 0 && a->sm_limit < sm_count) sm_count = a->sm_limit >= 2 ? a->sm_limit : 2;
+
   GemmDev dev;
   dev.C = a->C; dev.C2 = a->C2;
   dev.bias = reinterpret_cast<const float*>(a->bias);

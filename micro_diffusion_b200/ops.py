@@ -97,6 +97,7 @@ class CudaOps:
             fn.argtypes = argtypes
         self.launches = 0
         self.gemm_flops = 0      # algorithmic FLOPs of every md_gemm_bf16 launched (2*M*N*K*batch)
+        self.sm_limit = 0        # > 0: persistent GEMM grids use at most this many SMs (set while a collective overlaps)
         self.profile = None      # set to a list to record (name, start_event, end_event, flops) per launch
 
     # ------------------------------------------------------------------ helpers
@@ -158,6 +159,7 @@ class CudaOps:
         a.rows_per_gate = rows_per_gate
         a.res_mod = res_mod
         a.layout, a.epilogue, a.splits, a.act, a.alpha = layout, epi, splits, act, alpha
+        a.sm_limit = self.sm_limit
         if C2 is not None:
             assert C2.is_contiguous() or C2.stride(-2) == C3.stride(1)
         if res is not None:

@@ -10,6 +10,7 @@ them, so that it overlaps the rest of that backward (the path shards by batch: n
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable, List, Optional
 
 import torch
@@ -54,8 +55,17 @@ class GradReducer:
     are therefore all-reduced on a side stream while the patch-mixer and stem backward still run; `reduce()` then
     handles the remainder and joins the streams."""
 
-    def __init__(self, store, buckets: int = 4, group=None):
+    def __init__(self, store, buckets: int = 4, group=None, ops=None, reserve_sms: Optional[int] = None,
+                 overlap: Optional[bool] = None):
+        """`ops` (the model's CudaOps) + `reserve_sms`: while the early all-reduce is in flight the persistent GEMM grids
+        leave that many SMs to NCCL's CTAs -- a statically scheduled 148-CTA grid whose last CTAs cannot become resident
+        until the collective's CTAs retire would otherwise run its tail at half speed."""
         self.store = store
+        self.ops = ops
+        self.reserve = int(os.environ.get("MD_DDP_SM_RESERVE", "16")) if reserve_sms is None else int(reserve_sms)
+        self.overlap = (os.environ.get("MD_DDP_OVERLAP", "1") != "0") if overlap is None else bool(overlap)
+        self.sm_count = (torch.cuda.get_device_properties(store.grad.device).multi_processor_count
+                         if store.grad.is_cuda else 0)
         self.grad = store.grad
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -104,10 +114,12 @@ class GradReducer:
 
     def reduce_early(self):
         """Called from inside the LAST microbatch's backward once the backbone gradients are final."""
-        if self.world == 1:
+        if self.world == 1 or not self.overlap:
             return
         self._allreduce(self.early)
         self._early_done = True
+        if self.ops is not None and self.reserve > 0 and self.sm_count > self.reserve:
+            self.ops.sm_limit = self.sm_count - self.reserve
 
     def reduce(self):
         """All-reduce (mean) whatever has not been reduced yet and make the result visible to the compute stream."""
@@ -117,6 +129,8 @@ class GradReducer:
         self._early_done = False
         if self.stream is not None:
             torch.cuda.current_stream(self.grad.device).wait_stream(self.stream)
+        if self.ops is not None:
+            self.ops.sm_limit = 0
 
 
 def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, reducer: Optional[GradReducer] = None,

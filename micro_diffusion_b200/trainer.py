@@ -137,7 +137,7 @@ class Trainer:
         self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.optimizer = FlatAdamW(model.dit, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip_norm=clip_norm)
-        self.reducer = GradReducer(model.dit.store) if self.world > 1 else None
+        self.reducer = GradReducer(model.dit.store, ops=model.dit.engine.ops) if self.world > 1 else None
         self.batch = 0
         if load_path:
             self.batch = load_checkpoint(load_path, model, self.optimizer, load_weights_only,
