@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 
 GLOBAL_BATCH = 2048
 # algorithmic training GFLOP per image (3 x forward; SURVEY.md section 8d / BASELINE.md section 3)
+NCU_GEMM_TRAFFIC_BYTES = 64.2e6 + 61.5e6
+
 WORKLOADS = {
     "c2": dict(arch="MicroDiT_XL_2", res=32, ch=4, mask=0.75, pos=1.0, p_mean=-0.6, p_std=1.2, micro=512, gf=282.30,
                name="MicroDiT_XL_2 res_256_pretrain mask=0.75 (32x32x4 latents)"),
@@ -369,7 +371,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (md_gemm_bf16)",
                          "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (gemm_tflops / peaks["bf16_sustained"]) if gemm_tflops else None, "traffic": None,
+                         "frac": (gemm_tflops / peaks["bf16_sustained"]) if gemm_tflops else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full`
+                         # capture (profiles/r01_ncu_gemm_full.md, launch 0: M=16384 N=3072 K=1024 bf16 out, whose
+                         # algorithmic traffic is 33.6 + 6.3 + 100.7 = 140.6 MB; part of C is still in L2 when it ends)
+                         "traffic": NCU_GEMM_TRAFFIC_BYTES, "traffic_launch": "M=16384 N=3072 K=1024 epi=bf16, 103.1 GFLOP",
                          "peak_source": peaks["source"] + " sustained", "launches_per_step": gemm_n,
                          "share_of_step_kernel_time": gemm_ms / tot_ms if tot_ms else None,
                          "step_algorithmic_tflops_per_gpu": step_tflops,

@@ -2,7 +2,9 @@
 
 CPU oracle of the MicroDiT training hot path.  Nothing in `micro_diffusion_b200/` may import this
 package; only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference`
-legs use it, and there only as the checker or the timed baseline.
+legs use it, and there only as the checker or the timed baseline (plus `tools/stock_torch_gpu.py`, a developer
+yardstick that times this same restatement through stock PyTorch on the GPU -- SURVEY.md section 8d's "honest GPU
+comparator"; it is not part of the product, the tests or bench.py).
 
 * `oracle.ref_import`  -- loads the UNMODIFIED reference from /root/reference (dev container only).
 * `oracle.port`        -- a functional fp32 restatement of the reference algorithm that travels with
