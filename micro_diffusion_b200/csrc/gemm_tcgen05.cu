@@ -10,8 +10,9 @@
 //   kMN=false  "NT":  C[M,N] = sum_k A[M,k] * B[N,k]     A,B row-major with k contiguous (K-major)
 //   kMN=true   "TN":  C[P,Q] = sum_r A[r,P] * B[r,Q]     A,B row-major with the reduction index r
 //                     strided (MN-major UMMA operands) -- the weight-gradient contraction.
-// Roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-// warps4-11 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31, column half (w-4)/4 of the tile).
+// Roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator, warps4-7 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..+31; MD_EPI_WARPS=8 adds a second warp per lane quarter, half of the columns each
+// -- measured equal or slightly slower once the epilogue stopped spilling its accumulator chunk to local memory).
 //
 // kCtas = 2 is the Blackwell CTA-pair mode: two CTAs of a cluster (adjacent SMs) run ONE tcgen05.mma.cta_group::2
 // with M = 256 (128 rows of D in each CTA's TMEM); every CTA stages its own 128 rows of A and only HALF of the B
@@ -244,7 +245,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    // 8 warps: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 4) / 4.
+    // TMEM lane quarter q = warp % 4 (hardware rule); with 8 epilogue warps, column half = (warp - 4) / 4.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     constexpr int kChunksPerWarp = BLOCK_N / kColSplit / 32;  // 32-column chunks per warp

@@ -133,3 +133,27 @@ def test_pos_embed_matches_golden_probe():
     fx = torch.load(os.path.join(pc.GOLDEN, "parity_S.pt"), weights_only=False)
     pe = torch.from_numpy(get_2d_sincos_pos_embed(256, 8, pos_interp_scale=2.0, base_size=8)).float()
     assert torch.allclose(pe[::7, ::13], fx["pos_embed_probe"], atol=1e-6)
+
+
+def test_gemm_args_struct_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of md_gemm_args (micro_diffusion_b200/_lib.py) must have the field order, offsets and size
+    the C header declares: compile a probe against include/microdit_b200.h with gcc and compare."""
+    import ctypes
+    import shutil
+    import subprocess
+    from micro_diffusion_b200._lib import GemmArgs
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = [f[0] for f in GemmArgs._fields_]
+    src = tmp_path / "probe.c"
+    body = "\n".join(f'  printf("{n} %zu\\n", offsetof(md_gemm_args, {n}));' for n in names)
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "microdit_b200.h"\nint main(void) {\n' + body +
+                   '\n  printf("sizeof %zu\\n", sizeof(md_gemm_args));\n  return 0;\n}\n')
+    exe = tmp_path / "probe"
+    subprocess.run([gcc, "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for n in names:
+        assert int(out[n]) == getattr(GemmArgs, n).offset, n
+    assert int(out["sizeof"]) == ctypes.sizeof(GemmArgs)
