@@ -46,6 +46,22 @@ def cosine_with_warmup(step: int, t_warmup: int, t_max: int, alpha_f: float = 0.
     return alpha_f + (1.0 - alpha_f) * 0.5 * (1.0 + math.cos(math.pi * frac))
 
 
+def lr_multiplier(kind: str, step: int, t_warmup: int, t_max: int, alpha: float = 1.0, alpha_f: float = 0.0) -> float:
+    """The three Composer schedulers the reference's configs name (configs/res_256_pretrain.yaml:58-61,
+    res_256_finetune.yaml:58-60, res_512_pretrain.yaml:63-66), as LR multipliers at optimizer step `step`."""
+    if kind == "cosine_with_warmup":
+        return cosine_with_warmup(step, t_warmup, t_max, alpha_f)
+    if kind == "constant":
+        return alpha
+    if kind == "constant_with_warmup":
+        return alpha * (step / t_warmup) if (t_warmup > 0 and step < t_warmup) else alpha
+    raise ValueError(f"unknown LR schedule {kind!r}")
+
+
+SCHEDULERS = {"CosineAnnealingWithWarmupScheduler": "cosine_with_warmup", "ConstantScheduler": "constant",
+              "ConstantWithWarmupScheduler": "constant_with_warmup"}
+
+
 # ------------------------------------------------------------------------------------------ checkpoints
 def _flatten(tree, prefix=""):
     for k, v in tree.items():
@@ -121,6 +137,7 @@ class Trainer:
     def __init__(self, model, train_dataloader: Iterable[Dict[str, torch.Tensor]], max_duration="50000ba",
                  lr: float = 2.4e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.1,
                  clip_norm: Optional[float] = 0.25, t_warmup="2500ba", alpha_f: float = 0.33,
+                 scheduler: str = "cosine_with_warmup", alpha: float = 1.0,
                  device_train_microbatch_size: int = 256, save_folder: Optional[str] = None, save_interval="2500ba",
                  load_path: Optional[str] = None, load_weights_only: bool = False,
                  load_strict_model_weights: bool = True, load_ignore_keys: Sequence[str] = (),
@@ -131,6 +148,8 @@ class Trainer:
         self.t_max = parse_batches(max_duration)
         self.t_warmup = parse_batches(t_warmup)
         self.alpha_f = alpha_f
+        self.scheduler, self.alpha = scheduler, alpha
+        lr_multiplier(scheduler, 0, 1, 2)  # validate the name early
         self.microbatch = device_train_microbatch_size
         self.save_folder, self.save_interval = save_folder, parse_batches(save_interval)
         self.log_every, self.log = log_every, log_fn
@@ -144,7 +163,7 @@ class Trainer:
                                          load_strict_model_weights, load_ignore_keys)
 
     def lr_at(self, batch: int) -> float:
-        return self.optimizer.lr * cosine_with_warmup(batch, self.t_warmup, self.t_max, self.alpha_f)
+        return self.optimizer.lr * lr_multiplier(self.scheduler, batch, self.t_warmup, self.t_max, self.alpha, self.alpha_f)
 
     def fit(self, until: Optional[int] = None) -> float:
         """Train to `max_duration` (or stop early after batch `until`, schedule unchanged); returns the last logged loss."""

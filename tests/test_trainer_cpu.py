@@ -37,6 +37,17 @@ def test_cosine_with_warmup_matches_composer_formula():
     assert cosine_with_warmup(3, 0, 10, 0.0) == pytest.approx(0.5 * (1 + math.cos(math.pi * 0.3)))
 
 
+def test_constant_schedules():
+    from micro_diffusion_b200.trainer import lr_multiplier
+    assert lr_multiplier("constant", 10, 0, 100, alpha=1.0) == 1.0
+    assert lr_multiplier("constant_with_warmup", 0, 500, 1000, alpha=1.0) == 0.0
+    assert lr_multiplier("constant_with_warmup", 250, 500, 1000, alpha=1.0) == 0.5
+    assert lr_multiplier("constant_with_warmup", 500, 500, 1000, alpha=1.0) == 1.0
+    assert lr_multiplier("constant_with_warmup", 900, 500, 1000, alpha=0.5) == 0.5
+    with pytest.raises(ValueError):
+        lr_multiplier("linear", 0, 1, 2)
+
+
 def test_fit_checkpoint_resume_is_bit_identical(tmp_path):
     from micro_diffusion_b200.trainer import Trainer
     kw = dict(lr=1e-3, eps=1e-2, t_warmup="2ba", alpha_f=0.33, device_train_microbatch_size=2, log_every=1,
