@@ -9,6 +9,7 @@ implements the same interface on CPU tensors so the host-side orchestration can 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -31,6 +32,7 @@ _PROTOS = {
     "md_rownorm_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _P],
     "md_gate_bwd": [_P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _P],
     "md_attn_fwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_attn_fwd_tc": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
     "md_attn_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I64,
                     _I64, _I64, _I64, _I64, _I64, _P],
     "md_swiglu_fwd": [_P, _P, _I64, _I64, _P],
@@ -97,6 +99,7 @@ class CudaOps:
             fn.argtypes = argtypes
         self.launches = 0
         self.gemm_flops = 0      # algorithmic FLOPs of every md_gemm_bf16 launched (2*M*N*K*batch)
+        self.attn_tc = os.environ.get("MD_ATTN_TC", "0") == "1"
         self.sm_limit = 0        # > 0: persistent GEMM grids use at most this many SMs (set while a collective overlaps)
         self.profile = None      # set to a list to record (name, start_event, end_event, flops) per launch
 
@@ -219,7 +222,9 @@ class CudaOps:
 
     # ------------------------------------------------------------------ attention
     def attn_fwd(self, q, k, v, o, lse, B, H, Tq, Tk, hd):
-        self._call("md_attn_fwd", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+        # MD_ATTN_TC=1: experimental tcgen05 forward (round-2 work; never taken by default)
+        name = "md_attn_fwd_tc" if (self.attn_tc and hd == 64 and Tk <= 256) else "md_attn_fwd"
+        self._call(name, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                    o.data_ptr(), o.stride(0), lse.data_ptr(), B, H, Tq, Tk, hd,
                    label=f"B={B} H={H} Tq={Tq} Tk={Tk}", flops=4 * B * H * Tq * Tk * hd)
 
