@@ -118,11 +118,16 @@ MD_API int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_t ld
                        const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
                        void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                        int64_t Tq, int64_t Tk, int64_t hd, void* stream);
-/* EXPERIMENTAL, not dispatched by md_attn_fwd: the same forward on tcgen05 / TMEM for head_dim 64 and Tk <= 256
+/* EXPERIMENTAL, not dispatched by md_attn_fwd / md_attn_bwd: the same forward and backward (no delta scratch: it is
+ * derived from o and dout) on tcgen05 / TMEM for head_dim 64 and Tk <= 256
  * (csrc/attn_tcgen05.cu; written in round 1, first hardware run scheduled for round 2 -- DESIGN.md section 8). */
 MD_API int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                           int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
                           void* stream);
+MD_API int md_attn_bwd_tc(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                          const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, void* dq,
+                          int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
+                          int64_t Tq, int64_t Tk, int64_t hd, void* stream);
 
 /* ------------------------------------------------------------------------------ feed-forward tails */
 /* SwiGLU (dit.py:88-89): u bf16 [rows, 2f] = [w1 x | w2 x];  h = silu(u[:, :f]) * u[:, f:]. */

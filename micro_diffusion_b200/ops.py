@@ -33,6 +33,8 @@ _PROTOS = {
     "md_gate_bwd": [_P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _P],
     "md_attn_fwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
     "md_attn_fwd_tc": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_attn_bwd_tc": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64,
+                       _I64, _I64, _I64, _I64, _I64, _P],
     "md_attn_bwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I64,
                     _I64, _I64, _I64, _I64, _I64, _P],
     "md_swiglu_fwd": [_P, _P, _I64, _I64, _P],
@@ -229,6 +231,12 @@ class CudaOps:
                    label=f"B={B} H={H} Tq={Tq} Tk={Tk}", flops=4 * B * H * Tq * Tk * hd)
 
     def attn_bwd(self, dout, q, k, v, o, lse, delta, dq, dk, dv, B, H, Tq, Tk, hd):
+        if self.attn_tc and hd == 64 and Tk <= 256:  # experimental tcgen05 backward (round-2 work)
+            self._call("md_attn_bwd_tc", dout.data_ptr(), dout.stride(0), q.data_ptr(), q.stride(0), k.data_ptr(),
+                       k.stride(0), v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(),
+                       dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0),
+                       B, H, Tq, Tk, hd, label=f"B={B} H={H} Tq={Tq} Tk={Tk}", flops=10 * B * H * Tq * Tk * hd)
+            return
         self._call("md_attn_bwd", dout.data_ptr(), dout.stride(0), q.data_ptr(), q.stride(0), k.data_ptr(),
                    k.stride(0), v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(),
                    delta.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
