@@ -462,7 +462,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int j = 0; j < 32; ++j) {
             const int key = hf * 128 + c * 32 + j;
             p[j] = key < Tk ? exp2f(fmaf(__uint_as_float(rs[j]), scale_log2, -lrow)) : 0.f;
-            ds[j] = p[j] * (__uint_as_float(rp[j]) - delta);
+            ds[j] = key < Tk ? p[j] * (__uint_as_float(rp[j]) - delta) : 0.f;  // stale TMEM beyond the MMA's N may be NaN
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
