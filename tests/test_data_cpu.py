@@ -99,3 +99,37 @@ def test_device_loader_partitions_ranks_and_feeds_the_model(tmp_path):
     loss = ld(batch)[0]
     loss.backward()
     assert torch.isfinite(loss)
+
+
+def test_device_loader_partial_batch_multi_dir_and_error_surfacing(tmp_path):
+    from micro_diffusion_b200.data import DeviceBatchLoader, LatentsDataset, write_mds
+    a = _make(tmp_path / "a", n=5, with512=False)
+    b = _make(tmp_path / "b", n=6, with512=False, shard_samples=2)
+    ds = LatentsDataset([str(tmp_path / "a"), str(tmp_path / "b")], image_size=256)
+    assert len(ds) == 11 and ds.latent_channels() == 4
+    assert ds[7]["image_latents"].numpy().tobytes() == b[2]["latents_256"]  # second directory follows the first
+    dl = DeviceBatchLoader(ds, batch_size=4, device="cpu", shuffle=False, drop_last=False)
+    got = list(dl)
+    assert [x["image_latents"].shape[0] for x in got] == [4, 4, 3]  # ragged tail kept
+    assert got[2]["caption_latents"][2].numpy().tobytes() == b[5]["caption_latents"]
+    assert len(list(DeviceBatchLoader(ds, batch_size=4, device="cpu", shuffle=False, drop_last=True))) == 2
+    # abandoning the iterator mid-epoch must not leave the producer thread blocked
+    it = iter(DeviceBatchLoader(ds, batch_size=2, device="cpu", shuffle=False))
+    next(it)
+    it.close()
+    # a sample of the wrong size is reported in the consuming thread, not swallowed by the producer
+    rng = np.random.default_rng(3)
+    bad = [{"caption": "x", "caption_latents": rng.standard_normal(77 * 1024).astype(np.float16).tobytes(),
+            "latents_256": rng.standard_normal(4 * 32 * 32).astype(np.float16).tobytes()} for _ in range(3)]
+    bad[2]["caption_latents"] = bad[2]["caption_latents"][:-2]
+    write_mds(str(tmp_path / "bad"), bad, {"caption": "str", "caption_latents": "bytes", "latents_256": "bytes"})
+    dsb = LatentsDataset(str(tmp_path / "bad"), image_size=256)
+    with pytest.raises(ValueError):
+        list(DeviceBatchLoader(dsb, batch_size=3, device="cpu", shuffle=False))
+    # unsupported shard kinds are refused up front
+    idx = json.load(open(os.path.join(tmp_path / "a", "index.json")))
+    idx["shards"][0]["compression"] = "zstd"
+    os.makedirs(tmp_path / "z", exist_ok=True)
+    json.dump(idx, open(os.path.join(tmp_path / "z", "index.json"), "w"))
+    with pytest.raises(ValueError):
+        LatentsDataset(str(tmp_path / "z"), image_size=256)
