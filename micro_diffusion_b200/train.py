@@ -8,7 +8,7 @@ The file format and the keys are the reference's (configs/res_*.yaml; consumed b
 (torch.optim.AdamW kwargs), `scheduler` (Composer's CosineAnnealingWithWarmup / Constant / ConstantWithWarmup), `algorithms.gradient_clipping`,
 `trainer` (max_duration, save/load options, device_train_microbatch_size), `seed`.  `${key}` / `${a.b}` interpolation
 and `a.b=value` command-line overrides follow OmegaConf's surface for the subset the configs use.  What the hot path
-does not cover is accepted and ignored with a note: loggers, the image-monitor callback, the evaluation loop,
+does not cover is accepted and ignored with a note: loggers, the image-monitor callback,
 `misc.compile`, `fsdp_config` (weights are replicated, gradients all-reduced -- train_step.GradReducer), and
 `algorithms.low_precision_layernorm` (LayerNorm statistics are fp32 inside md_ln_fwd already).
 """
@@ -80,8 +80,6 @@ def ignored_sections(cfg: dict) -> List[str]:
     tr = cfg.get("trainer") or {}
     if tr.get("fsdp_config"):
         notes.append("trainer.fsdp_config (replicated weights + all-reduce of the flat gradient)")
-    if tr.get("eval_interval") not in (None, 0, "0ba"):
-        notes.append("trainer.eval_interval / dataset.eval (no evaluation loop)")
     return notes
 
 
@@ -136,7 +134,18 @@ def build(cfg: dict, device, rank: int = 0, world: int = 1, model=None):
     per_rank = int(ds_cfg["train_batch_size"]) // world  # train.py:50
     loader = DeviceBatchLoader(ds, per_rank, device, rank=rank, world=world, shuffle=bool(tr_cfg.get("shuffle", True)),
                                drop_last=bool(tr_cfg.get("drop_last", True)), seed=int(cfg.get("seed", 0)))
-    trainer = Trainer(model, loader, **trainer_kwargs(cfg))
+    kw = trainer_kwargs(cfg)
+    ev_cfg = ds_cfg.get("eval")
+    interval = (cfg.get("trainer") or {}).get("eval_interval", 0)
+    if (cfg.get("misc") or {}).get("compile"):
+        interval = 0  # train.py:99-101 disables online evals when misc.compile is set
+    if ev_cfg and interval not in (None, 0, "0ba"):
+        eds = LatentsDataset(ev_cfg["datadir"], image_size=ds_cfg["image_size"], cap_seq_size=seq, cap_emb_dim=dim)
+        kw["eval_dataloader"] = DeviceBatchLoader(eds, int(ds_cfg.get("eval_batch_size", per_rank * world)) // world, device,
+                                                  rank=rank, world=world, shuffle=False, drop_last=False,
+                                                  seed=int(cfg.get("seed", 0)))
+        kw["eval_interval"] = interval
+    trainer = Trainer(model, loader, **kw)
     return model, loader, trainer
 
 

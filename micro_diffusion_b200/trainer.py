@@ -141,7 +141,8 @@ class Trainer:
                  device_train_microbatch_size: int = 256, save_folder: Optional[str] = None, save_interval="2500ba",
                  load_path: Optional[str] = None, load_weights_only: bool = False,
                  load_strict_model_weights: bool = True, load_ignore_keys: Sequence[str] = (),
-                 log_every: int = 50, log_fn: Callable[[str], None] = print):
+                 log_every: int = 50, log_fn: Callable[[str], None] = print,
+                 eval_dataloader: Optional[Iterable[Dict[str, torch.Tensor]]] = None, eval_interval="0ba"):
         import torch.distributed as dist
         self.model = model
         self.loader = train_dataloader
@@ -153,6 +154,8 @@ class Trainer:
         self.microbatch = device_train_microbatch_size
         self.save_folder, self.save_interval = save_folder, parse_batches(save_interval)
         self.log_every, self.log = log_every, log_fn
+        self.eval_loader, self.eval_interval = eval_dataloader, parse_batches(eval_interval)
+        self.last_eval_loss: Optional[float] = None
         self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.optimizer = FlatAdamW(model.dit, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip_norm=clip_norm)
@@ -164,6 +167,29 @@ class Trainer:
 
     def lr_at(self, batch: int) -> float:
         return self.optimizer.lr * lr_multiplier(self.scheduler, batch, self.t_warmup, self.t_max, self.alpha, self.alpha_f)
+
+    @torch.no_grad()
+    def evaluate(self) -> float:
+        """Composer's eval pass over `eval_dataloader` (trainer.eval_interval, dataset.eval in the configs): mean over
+        batches and ranks of `model.eval_forward(batch)`'s loss -- DistLoss (utils.py:598-613: sum of batch losses and a
+        batch count, both sum-reduced across ranks).  The model runs in eval mode (no patch masking, model.py:115-118)."""
+        import torch.distributed as dist
+        dev = self.model.dit.store.device
+        was_training = self.model.training
+        self.model.eval()
+        total = torch.zeros(2, dtype=torch.float64, device=dev)  # [sum of batch losses, batches]
+        for batch in self.eval_loader:
+            batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            loss = self.model.eval_forward(batch)[0]
+            total[0] += loss.detach().double()
+            total[1] += 1
+        if self.world > 1:
+            dist.all_reduce(total)
+        self.model.train(was_training)
+        if float(total[1]) == 0:
+            raise RuntimeError("eval_dataloader yielded no batches")
+        self.last_eval_loss = float(total[0] / total[1])
+        return self.last_eval_loss
 
     def fit(self, until: Optional[int] = None) -> float:
         """Train to `max_duration` (or stop early after batch `until`, schedule unchanged); returns the last logged loss."""
@@ -191,6 +217,10 @@ class Trainer:
                         self.log(f"batch {self.batch}/{self.t_max} loss {last:.4f} lr {self.optimizer.lr_now:.3e} "
                                  f"{n0 / dt:.0f} img/s")
                     t0, n0 = time.perf_counter(), 0
+                if self.eval_loader is not None and self.eval_interval > 0 and self.batch % self.eval_interval == 0:
+                    ev = self.evaluate()
+                    if self.rank == 0:
+                        self.log(f"batch {self.batch}/{self.t_max} eval loss {ev:.4f}")
                 if self.save_folder and self.batch % self.save_interval == 0:
                     save_checkpoint(os.path.join(self.save_folder, f"ba{self.batch}.pt"), self.model, self.optimizer,
                                     self.batch, self.rank)

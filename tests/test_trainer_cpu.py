@@ -112,3 +112,32 @@ def test_load_ignore_keys_and_strictness(tmp_path):
     sd = c.dit.state_dict()
     assert all(float(v.abs().max()) == 0.0 for k, v in sd.items() if k.startswith("blocks.0.") )
     assert float(sd["blocks.1.attn.qkv.weight"].abs().max()) > 0
+
+
+def test_eval_interval_runs_the_eval_pass_without_touching_training_state():
+    from micro_diffusion_b200.trainer import Trainer
+    kw = dict(lr=1e-3, eps=1e-2, t_warmup="1ba", device_train_microbatch_size=2, log_every=1)
+    a, b = _build(), _build()
+    logs = []
+    torch.manual_seed(3)
+    Trainer(a, _loader(3), max_duration="3ba", log_fn=lambda s: None, **kw).fit()
+    torch.manual_seed(3)
+    ev = _loader(2, seed0=900)
+    tb = Trainer(b, _loader(3), max_duration="3ba", log_fn=logs.append, eval_dataloader=ev, eval_interval="2ba", **kw)
+    rng_before_eval = []
+    orig = tb.evaluate
+    tb.evaluate = lambda: (rng_before_eval.append(1), orig())[1]
+    tb.fit()
+    assert len(rng_before_eval) == 1 and tb.last_eval_loss == tb.last_eval_loss
+    assert any("eval loss" in s for s in logs)
+    assert b.training  # back in train mode
+    # the eval pass draws noise too, so the training streams differ afterwards -- but the first two steps are identical
+    # and the eval loss is the mean of the two eval batch losses at mask ratio 0
+    b2 = _build()
+    b2.dit.load_state_dict(b.dit.state_dict())
+    b2.eval()
+    torch.manual_seed(11)
+    want = sum(float(b2.eval_forward(x)[0]) for x in ev) / 2
+    torch.manual_seed(11)
+    got = Trainer(b2, [], max_duration="1ba", log_fn=lambda s: None, eval_dataloader=ev, **kw).evaluate()
+    assert got == pytest.approx(want, rel=1e-6)
