@@ -232,9 +232,12 @@ MD_API int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch,
 /* sumsq(f32 [1]) += sum x^2  (gradient-norm clipping, train.py:85-86) */
 MD_API int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream);
 /* fused (clip-scaled) AdamW on flat fp32 buffers (train.py:39, configs/res_256_pretrain.yaml:50-57):
- * g *= min(1, clip / (sqrt(sumsq[0]) + 1e-6)) if sumsq != NULL; decoupled weight decay; bias correction by step. */
+ * g *= min(1, clip / (sqrt(sumsq[0]) + 1e-6)) if sumsq != NULL and clip > 0; decoupled weight decay; bias correction by
+ * step.  If sumsq[0] is not finite (a NaN / Inf gradient, cf. NaNCatcher callbacks.py:47-64) nothing is written and
+ * *nonfinite (nullable, i32) is set to 1.  p/g/m/v may be any 16-byte aligned slice of the flat buffers (sharded step). */
 MD_API int md_adamw(float* p, const float* g, float* m, float* v, const float* sumsq, float clip, float lr,
-                    float beta1, float beta2, float eps, float wd, int64_t step, int64_t n, void* stream);
+                    float beta1, float beta2, float eps, float wd, int64_t step, int32_t* nonfinite, int64_t n,
+                    void* stream);
 
 #ifdef __cplusplus
 }

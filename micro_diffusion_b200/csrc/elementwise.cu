@@ -285,11 +285,16 @@ __global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ ou
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, const float* __restrict__ sumsq, float clip, float lr, float b1,
-                             float b2, float eps, float wd, float bc1, float bc2, long long n) {
+                             float b2, float eps, float wd, float bc1, float bc2, int* __restrict__ nonfinite,
+                             long long n) {
   float gs = 1.f;
-  if (sumsq != nullptr && clip > 0.f) {
-    const float norm = sqrtf(sumsq[0]);
-    gs = fminf(1.f, clip / (norm + 1e-6f));
+  if (sumsq != nullptr) {
+    const float ss = sumsq[0];
+    if (!isfinite(ss)) {  // a NaN / Inf gradient anywhere: leave weights and moments untouched (NaNCatcher, callbacks.py:47-64)
+      if (nonfinite != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *nonfinite = 1;
+      return;
+    }
+    if (clip > 0.f) gs = fminf(1.f, clip / (sqrtf(ss) + 1e-6f));
   }
   const long long nv = n >> 2;
   for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += 1LL * gridDim.x * blockDim.x) {
@@ -427,11 +432,12 @@ extern "C" int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream) {
   return check_launch("md_sumsq");
 }
 extern "C" int md_adamw(float* p, const float* g, float* m, float* v, const float* sumsq, float clip, float lr,
-                        float beta1, float beta2, float eps, float wd, int64_t step, int64_t n, void* stream) {
+                        float beta1, float beta2, float eps, float wd, int64_t step, int32_t* nonfinite, int64_t n,
+                        void* stream) {
   if (n == 0) return 0;
   if (!p || !g || !m || !v || step < 1) return md_set_error(MD_ERR_INVALID, "md_adamw: null pointer or step < 1");
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(p, g, m, v, sumsq, clip, lr, beta1, beta2, eps, wd,
-                                                                 bc1, bc2, n);
+                                                                 bc1, bc2, nonfinite, n);
   return check_launch("md_adamw");
 }

@@ -43,7 +43,9 @@ class DeviceBatchLoader:
         self.rank, self.world, self.shuffle, self.drop_last, self.seed = rank, world, shuffle, drop_last, seed
         self.p_drop = dataset.cap_drop_prob if cap_drop_prob is None else cap_drop_prob
         self.depth = max(2, depth)
-        self.epoch = 0
+        self.epoch = 0            # epoch the NEXT iteration will run
+        self.batch_in_epoch = 0   # batches of the running epoch already handed to the consumer
+        self._resume_batch = 0    # batches to skip at the start of the next iteration (set by load_state_dict)
         if in_channels is None:  # read it off the first sample
             in_channels = dataset.latent_channels()
         self.C, self.res = in_channels, dataset.res
@@ -66,17 +68,32 @@ class DeviceBatchLoader:
         per_rank = n // self.world  # every rank sees the same number of samples (no ragged last step across ranks)
         return perm[self.rank * per_rank:(self.rank + 1) * per_rank]
 
-    def _produce(self, idx: np.ndarray, epoch: int, out: "queue.Queue", stop: threading.Event):
+    def state_dict(self) -> dict:
+        """Position of the sample stream: what Composer restores from the dataset state + timestamp on resume."""
+        running = self.batch_in_epoch > 0
+        return {"epoch": self.epoch - 1 if running else self.epoch, "batch_in_epoch": self.batch_in_epoch if running else 0}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.epoch = int(sd.get("epoch", 0))
+        self._resume_batch = int(sd.get("batch_in_epoch", 0))
+        if self._resume_batch >= len(self):  # the checkpoint was written on an epoch boundary
+            self.epoch += 1
+            self._resume_batch = 0
+
+    def _produce(self, idx: np.ndarray, epoch: int, out: "queue.Queue", stop: threading.Event, first: int = 0):
         try:
             rng = np.random.default_rng([self.seed, epoch, self.rank])
             nb = len(self)
             for b in range(nb):
                 if stop.is_set():
                     return
-                sl = self.slots[b % len(self.slots)]
                 ids = idx[b * self.B:(b + 1) * self.B]
                 n = len(ids)
-                if sl.copied is not None and b >= len(self.slots):
+                if b < first:  # resumed run: replay the caption-drop stream of the batches already consumed
+                    rng.random(n)
+                    continue
+                sl = self.slots[b % len(self.slots)]
+                if sl.copied is not None and b - first >= len(self.slots):
                     sl.copied.synchronize()  # the previous H2D out of this staging buffer has finished
                 for j, i in enumerate(ids):
                     self.ds.fill(int(i), sl.lat_np[j], sl.cap_np[j])
@@ -102,9 +119,11 @@ class DeviceBatchLoader:
         idx = self._indices(self.epoch)
         q: "queue.Queue" = queue.Queue(maxsize=self.depth - 1)
         stop = threading.Event()
-        th = threading.Thread(target=self._produce, args=(idx, self.epoch, q, stop), daemon=True)
+        first, self._resume_batch = self._resume_batch, 0
+        th = threading.Thread(target=self._produce, args=(idx, self.epoch, q, stop, first), daemon=True)
         th.start()
         self.epoch += 1
+        self.batch_in_epoch = first
         prev = None
         try:
             while True:
@@ -116,6 +135,7 @@ class DeviceBatchLoader:
                     prev.released = ev
                 item = q.get()
                 if item is None:
+                    self.batch_in_epoch = 0
                     return
                 if isinstance(item, BaseException):
                     raise item
@@ -123,6 +143,7 @@ class DeviceBatchLoader:
                 if sl.copied is not None:
                     torch.cuda.current_stream(self.device).wait_event(sl.copied)
                 prev = sl
+                self.batch_in_epoch += 1
                 yield batch
         finally:
             stop.set()

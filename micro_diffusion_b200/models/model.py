@@ -34,12 +34,15 @@ class _EDMLossFn(torch.autograd.Function):
     """loss = edm_loss(...) with the whole forward and backward executed by the engine."""
 
     @staticmethod
-    def forward(ctx, anchor, ld, lat, cap, drop, rnd, eps_noise, mask_ratio, mask_noise, cap_out):
+    def forward(ctx, anchor, ld, lat, cap, drop, rnd, eps_noise, mask_ratio, mask_noise, cap_out, keep):
         eng = ld.dit.engine
-        keep = torch.is_grad_enabled() or ctx.needs_input_grad[0]
-        c = eng.forward_loss(lat, cap, drop, rnd, eps_noise, mask_ratio, mask_noise, ld._edm_scalars(), keep=True,
+        # `keep` = grad mode at the call site (inside Function.forward torch.is_grad_enabled() is always False and
+        # ctx.needs_input_grad ignores no_grad).  Under no_grad (eval_forward / Trainer.evaluate) nothing is saved,
+        # like the reference's no_grad evaluation.
+        keep = bool(keep and ctx.needs_input_grad[0])
+        c = eng.forward_loss(lat, cap, drop, rnd, eps_noise, mask_ratio, mask_noise, ld._edm_scalars(), keep=keep,
                              cap_out=cap_out)
-        ctx.ld, ctx.c = ld, c
+        ctx.ld, ctx.c = ld, (c if keep else None)
         ld.last_per_sample_loss = c.per_sample
         return c.loss.reshape(())
 
@@ -47,12 +50,13 @@ class _EDMLossFn(torch.autograd.Function):
     def backward(ctx, gout):
         ld, c = ctx.ld, ctx.c
         if c is None:
-            raise RuntimeError("backward through the same MicroDiT loss twice is not supported")
+            raise RuntimeError("MicroDiT loss: no saved activations (backward called twice, or the forward ran without "
+                               "a gradient-requiring anchor)")
         ld.dit.prepare_grads()
         gscale = gout.detach().reshape(1).to(torch.float32).contiguous()
         ld.dit.engine.backward(c, gscale)
         ctx.c = None  # free the saved activations
-        return (None,) * 10
+        return (None,) * 11
 
 
 class LatentDiffusion(_Base):
@@ -140,7 +144,7 @@ class LatentDiffusion(_Base):
         dit.engine  # bind storage / anchor before the autograd node is built
         return _EDMLossFn.apply(dit._anchor, self, x, y, drop, rnd_normal.reshape(B).contiguous(),
                                 eps_noise.contiguous(), float(mask_ratio), mask_noise,
-                                y if (inplace_caption_mask and drop is not None) else None)
+                                y if (inplace_caption_mask and drop is not None) else None, torch.is_grad_enabled())
 
     def edm_loss_with_draws(self, x, y, drop, rnd_normal, eps_noise, mask_noise, mask_ratio: float) -> torch.Tensor:
         """edm_loss with the three random draws supplied by the caller (seeded replay / parity tests):
@@ -153,7 +157,8 @@ class LatentDiffusion(_Base):
         self.dit.engine
         return _EDMLossFn.apply(self.dit._anchor, self, x, y, drop, rnd_normal.to(dev).float().reshape(-1).contiguous(),
                                 eps_noise.to(dev).float().contiguous(), float(mask_ratio),
-                                mask_noise.to(dev).float().contiguous() if mask_noise is not None else None, None)
+                                mask_noise.to(dev).float().contiguous() if mask_noise is not None else None, None,
+                                torch.is_grad_enabled())
 
     def edm_loss(self, x: torch.Tensor, y: torch.Tensor, mask_ratio: float = 0, **kwargs) -> torch.Tensor:
         """model.py:181-210 (x: latents, y: caption embeddings (B,1,L,Dc))."""

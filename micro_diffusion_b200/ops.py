@@ -66,7 +66,7 @@ _PROTOS = {
     "md_colsum": [_P, _I, _I64, _P, _I64, _I64, _P],
     "md_cast_transpose": [_P, _P, _P, _I64, _I64, _I64, _P],
     "md_sumsq": [_P, _P, _I64, _P],
-    "md_adamw": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I64, _I64, _P],
+    "md_adamw": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I64, _P, _I64, _P],
 }
 
 EXPORTED_SYMBOLS = ["md_last_error", "md_abi_version", "md_gemm_bf16", *_PROTOS.keys()]
@@ -366,6 +366,6 @@ class CudaOps:
     def sumsq(self, x, out):
         self._call("md_sumsq", x.data_ptr(), out.data_ptr(), x.numel())
 
-    def adamw(self, p, g, m, v, sumsq, clip, lr, beta1, beta2, eps, wd, step):
+    def adamw(self, p, g, m, v, sumsq, clip, lr, beta1, beta2, eps, wd, step, nonfinite=None):
         self._call("md_adamw", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(sumsq), clip, lr, beta1,
-                   beta2, eps, wd, step, p.numel())
+                   beta2, eps, wd, step, _ptr(nonfinite), p.numel())

@@ -126,6 +126,9 @@ def build(cfg: dict, device, rank: int = 0, world: int = 1, model=None):
         "For microbudget training, we assume that latents are already precomputed for all datasets"  # train.py:25
     if model is None:
         model = create_latent_diffusion(**mcfg).to(device)
+    # Composer seeds every process with seed + global rank AFTER the identically-seeded model construction, so the ranks
+    # draw different sigma / noise / patch masks (the replicas have no parameter broadcast and rely on the shared init)
+    torch.manual_seed(int(cfg.get("seed", 0)) + int(rank))
     ds_cfg = cfg["dataset"]
     tr_cfg = dict(ds_cfg["train"])
     seq, dim = text_encoder_embedding_format(mcfg.get("text_encoder_name", "openclip:hf-hub:apple/DFN5B-CLIP-ViT-H-14-378"))

@@ -27,6 +27,7 @@ class FlatAdamW:
         self.m = torch.zeros_like(st.flat)
         self.v = torch.zeros_like(st.flat)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=st.device)
+        self.nonfinite = torch.zeros(1, dtype=torch.int32, device=st.device)  # set by md_adamw when it skipped a step
         self.t = 0
 
     @torch.no_grad()
@@ -34,13 +35,13 @@ class FlatAdamW:
         eng = self.dit.engine
         st, o = eng.store, eng.ops
         self.t += 1
-        ss = None
-        if self.clip is not None and self.clip > 0:
-            self.sumsq.zero_()
-            o.sumsq(st.grad, self.sumsq)
-            ss = self.sumsq
-        o.adamw(st.flat, st.grad, self.m, self.v, ss, float(self.clip or 0.0), float(lr if lr is not None else self.lr),
-                self.betas[0], self.betas[1], self.eps, self.wd, self.t)
+        # the squared gradient norm is always taken: it scales the clip AND guards the update -- a non-finite norm
+        # (NaN / Inf loss, callbacks.py:47-64) makes md_adamw leave weights and moments untouched and raise `nonfinite`
+        self.sumsq.zero_()
+        o.sumsq(st.grad, self.sumsq)
+        o.adamw(st.flat, st.grad, self.m, self.v, self.sumsq, float(self.clip or 0.0),
+                float(lr if lr is not None else self.lr), self.betas[0], self.betas[1], self.eps, self.wd, self.t,
+                nonfinite=self.nonfinite)
         self.dit.mark_weights_dirty()
 
     def zero_grad(self):

@@ -493,9 +493,13 @@ class EmuOps:
         self.launches += 1
         out.add_((x.double() ** 2).sum().float())
 
-    def adamw(self, p, g, m, v, sumsq, clip, lr, beta1, beta2, eps, wd, step):
+    def adamw(self, p, g, m, v, sumsq, clip, lr, beta1, beta2, eps, wd, step, nonfinite=None):
         self.launches += 1
         gs = 1.0
+        if sumsq is not None and not math.isfinite(float(sumsq[0])):
+            if nonfinite is not None:
+                nonfinite.fill_(1)
+            return
         if sumsq is not None and clip > 0:
             gs = min(1.0, clip / (float(sumsq[0]) ** 0.5 + 1e-6))
         gg = g * gs

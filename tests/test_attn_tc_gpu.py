@@ -32,6 +32,7 @@ def test_attn_fwd_tc_matches_contract(B, H, Tq, Tk):
     ops.attn_fwd(qd[:, :hsz], kd[:, :hsz], kd[:, hsz:], o, lse, B, H, Tq, Tk, hd)
     torch.cuda.synchronize()
     err = (o.float().cpu() - o_ref.float()).norm() / o_ref.float().norm()
+    print(f'\n[attn_fwd_tc B={B} H={H} Tq={Tq} Tk={Tk}] o rel {float(err):.3e} lse maxabs {float((lse.cpu()-lse_ref).abs().max()):.3e}')
     assert err < 2e-2, err
     assert torch.allclose(lse.cpu(), lse_ref, atol=2e-3, rtol=1e-3)
 
@@ -64,4 +65,5 @@ def test_attn_bwd_tc_matches_contract(B, H, Tq, Tk):
 
     def rel(a, b):
         return float((a.float().cpu() - b.float()).norm() / b.float().norm())
+    print(f'\n[attn_bwd_tc B={B} H={H} Tq={Tq} Tk={Tk}] dq {rel(dq, dq_ref):.3e} dk {rel(dkv[:, :hsz], dkv_ref[:, :hsz]):.3e} dv {rel(dkv[:, hsz:], dkv_ref[:, hsz:]):.3e}')
     assert rel(dq, dq_ref) < 2e-2 and rel(dkv, dkv_ref) < 2e-2, (rel(dq, dq_ref), rel(dkv, dkv_ref))

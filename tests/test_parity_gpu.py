@@ -41,35 +41,74 @@ def test_cuda_path_matches_oracle_and_golden(name):
         assert pc.rel_l2(grads[k], g) < 2 * fx["ref_amp_bf16_grad_rel_max"] + 2e-2, k
 
 
-def test_tiny_zoo_model_matches_oracle():
-    """MicroDiT_Tiny_2 (16 layers, d=512, head_dim 32) at res 256 / mask 0.75 / batch 4 -- BASELINE.json configs[0]."""
-    from micro_diffusion_b200.models.dit import MicroDiT_Tiny_2
+def _zoo_case(factory, head_dim, input_size, in_channels, mask_ratio, B=2, pos_interp_scale=1.0, p_mean=-0.6, p_std=1.2):
+    """A zoo model (dit.py:630-709) on the B200 against the fp32 port on the same seeded weights, batch and draws:
+    loss, unmasked D_x and every parameter gradient."""
     from micro_diffusion_b200.models.model import LatentDiffusion, PrecomputedLatentStubs
     from oracle import port, weights
-    net = MicroDiT_Tiny_2(input_size=32, in_channels=4)
+    net = factory(input_size=input_size, in_channels=in_channels, pos_interp_scale=pos_interp_scale)
     net.load_state_dict(weights.synth_state_dict(net.state_dict(), seed=7))
     sd_cpu = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.to(DEV)
     vae, te, tok = PrecomputedLatentStubs.make()
-    ld = LatentDiffusion(net, vae, te, tok, train_mask_ratio=0.75)
+    ld = LatentDiffusion(net, vae, te, tok, p_mean=p_mean, p_std=p_std, train_mask_ratio=mask_ratio, latent_res=input_size)
     ld.train()
-    B = 4
-    batch = weights.synth_batch(B, 4, 32, seed=11)
-    rnd, eps, noise = weights.replay_draws(123, (B, 4, 32, 32), 256, 0.75)
+    T = (input_size // 2) ** 2
+    batch = weights.synth_batch(B, in_channels, input_size, seed=11)
+    rnd, eps, noise = weights.replay_draws(123, (B, in_channels, input_size, input_size), T, mask_ratio)
     loss = ld.edm_loss_with_draws(batch["image_latents"], batch["caption_latents"], batch["drop_caption_mask"],
-                                  rnd.reshape(-1), eps, noise, 0.75)
+                                  rnd.reshape(-1), eps, noise, mask_ratio)
     loss.backward()
-    P = {k: v.clone().requires_grad_(k not in ("pos_embed", "mask_token")) for k, v in sd_cpu.items()}
-    cfg = port.PortConfig(patch_size=2, head_dim=32, num_experts=8, expert_capacity=2.0)
-    oloss, _ = port.latent_diffusion_forward(P, cfg, batch, rnd, eps, 0.75, noise)
-    oloss.backward()
     grads = {k: p.grad.detach().float().cpu() for k, p in net.named_parameters()}
+    sigma = (rnd * p_std + p_mean).exp()
+    x = batch["image_latents"].float()
+    y = (batch["caption_latents"] * batch["drop_caption_mask"].view(-1, 1, 1, 1)).to(torch.float16)
+    with torch.no_grad():
+        net.eval()
+        den = ld.model_forward_wrapper((x + eps * sigma).to(DEV), sigma.to(DEV), y.to(DEV), net, mask_ratio=0.0)["sample"]
+        net.train()
+    den = den.float().cpu()
+    del ld, net
+    torch.cuda.empty_cache()
+    P = {k: v.clone().requires_grad_(k not in ("pos_embed", "mask_token")) for k, v in sd_cpu.items()}
+    cfg = port.PortConfig(patch_size=2, head_dim=head_dim, num_experts=8, expert_capacity=2.0, p_mean=p_mean, p_std=p_std)
+    oloss, _ = port.latent_diffusion_forward(P, cfg, batch, rnd, eps, mask_ratio, noise)
+    oloss.backward()
     ograds = {k: v.grad for k, v in P.items() if v.grad is not None}
+    with torch.no_grad():
+        oden = port.denoise({k: v.detach() for k, v in P.items()}, cfg, x + eps * sigma, sigma, y.float())["sample"]
     errs, med, worst = pc.grad_report(grads, ograds)
-    print(f"\n[Tiny_2] loss cuda {float(loss):.6f} oracle {float(oloss):.6f} rel {abs(float(loss) - float(oloss)) / float(oloss):.2e} "
+    lrel = abs(float(loss) - float(oloss)) / float(oloss)
+    drel = pc.rel_l2(den, oden)
+    return float(loss), float(oloss), lrel, drel, med, worst, errs
+
+
+def test_tiny_zoo_model_matches_oracle():
+    """MicroDiT_Tiny_2 (16 layers, d=512, head_dim 32) at res 256 / mask 0.75 / batch 4 -- BASELINE.json configs[0]."""
+    from micro_diffusion_b200.models.dit import MicroDiT_Tiny_2
+    loss, oloss, lrel, drel, med, worst, errs = _zoo_case(MicroDiT_Tiny_2, 32, 32, 4, 0.75, B=4)
+    print(f"\n[Tiny_2] loss cuda {loss:.6f} oracle {oloss:.6f} rel {lrel:.2e} D_x relL2 {drel:.2e} "
           f"grads median {med:.2e} worst {worst:.2e} ({errs[0][1]})")
-    assert abs(float(loss) - float(oloss)) / float(oloss) < 5e-3
+    assert lrel < 5e-3 and drel < 1.5e-2
     assert med < 4e-2 and worst < 0.25, errs[:5]
+
+
+@pytest.mark.parametrize("label,input_size,in_channels,mask_ratio,scale,p_mean,p_std", [
+    ("C2 res256 mask0.75", 32, 4, 0.75, 1.0, -0.6, 1.2),
+    ("C3 res256 mask0", 32, 4, 0.0, 1.0, -0.6, 1.2),
+    ("C5 res512 16ch mask0", 64, 16, 0.0, 2.0, 0.0, 0.6),
+    ("C4 res512 mask0.75", 64, 4, 0.75, 2.0, 0.0, 0.6),
+])
+def test_xl2_matches_oracle(label, input_size, in_channels, mask_ratio, scale, p_mean, p_std):
+    """MicroDiT_XL_2 (dit.py:671-709: d=1024, head_dim 64, 28 + 6 blocks, mixer 768) -- the model bench.py times -- at the
+    shapes of BASELINE.json configs 2-5, batch 2, CUDA path vs the fp32 port of the reference."""
+    from micro_diffusion_b200.models.dit import MicroDiT_XL_2
+    loss, oloss, lrel, drel, med, worst, errs = _zoo_case(MicroDiT_XL_2, 64, input_size, in_channels, mask_ratio, B=2,
+                                                          pos_interp_scale=scale, p_mean=p_mean, p_std=p_std)
+    print(f"\n[XL_2 {label}] loss cuda {loss:.6f} oracle {oloss:.6f} rel {lrel:.2e} D_x relL2 {drel:.2e} "
+          f"grads median {med:.2e} worst {worst:.2e} ({errs[0][1]})")
+    assert lrel < 5e-3 and drel < 2e-2
+    assert med < 4e-2 and worst < 0.3, errs[:5]
 
 
 def test_sampler_surface_runs():
