@@ -14,6 +14,12 @@
  * per-sample modulation vectors (shift / scale / gate) are passed as a pointer to sample 0 plus a row
  * pitch `ldmod` in elements (they are column slices of one [samples, sum(6*D)] adaLN buffer);
  * `T` = rows per sample.
+ *
+ * `prec` selects the storage type of the GEMM-operand / saved-activation tensors an entry point reads or writes (the
+ * arguments documented as bf16): 0 = bf16, the product path (the reference's amp_bf16 regime, train.py:113);
+ * 1 = fp32, the high-precision mode (MD_PRECISION=high) in which the same kernels and the same host sequencing are
+ * gated against the fp32 oracle at 1e-3 on loss and denoiser output.  Statistics, the residual stream, router
+ * probabilities, the loss and every parameter gradient are fp32 in both modes.
  */
 #ifndef MICRODIT_B200_H_
 #define MICRODIT_B200_H_
@@ -88,23 +94,24 @@ MD_API int md_gemm_bf16(const md_gemm_args* args, void* stream);
  * the branch GEMM then stores plain bf16 instead of doing the fp32 read-modify-write in its epilogue. */
 MD_API int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const void* y_add, const float* gate_add,
                      float* x_new, const float* gamma, const float* shift, const float* scale, int64_t ldmod,
-                     int64_t T, void* y, float* mean, float* rstd, int64_t rows, int64_t D, float eps, void* stream);
+                     int64_t T, void* y, float* mean, float* rstd, int64_t rows, int64_t D, float eps,
+                     int prec, void* stream);
 /* Backward of the above.  dy bf16 [rows, D].  dx_mode: 0 = dx(f32)[r] += , 1 = dx(bf16)[r] = ,
  * 2 = dx(f32)[src_rows[r]] += (scatter).  dgamma f32 [D] += (atomic); dshift / dscale f32 [samples, D]
  * pitched by ldmod, += (atomic; caller zeroes them once per step).  NULL outputs are skipped. */
 MD_API int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_t* src_rows, const float* gamma,
                      const float* scale, int64_t ldmod, int64_t T, const float* mean, const float* rstd,
                      void* dx, int dx_mode, float* dgamma, float* dshift, float* dscale, int64_t rows,
-                     int64_t D, void* stream);
+                     int64_t D, int prec, void* stream);
 /* Non-affine LayerNorm over a W-wide column slice, in place on bf16 (QK-norm: ln_q / ln_k utils.py:183-186,
  * 122-125).  fwd: x <- (x-mean)*rstd, rstd out.  bwd: dy <- rstd*(dy - mean(dy) - xhat*mean(dy*xhat)). */
-MD_API int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, float eps, void* stream);
+MD_API int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, float eps, int prec, void* stream);
 MD_API int md_rownorm_bwd(void* dy, int64_t ld_dy, const void* xhat, int64_t ld_x, const float* rstd, int64_t rows,
-                          int64_t W, void* stream);
+                          int64_t W, int prec, void* stream);
 /* Backward of x_new = x + gate[sample] * y (dit.py:236,238): dy(bf16) = gate * dres;
  * dgate[sample] += sum_t dres * y (atomic).  y / gate / dgate may be NULL (plain f32->bf16 cast). */
 MD_API int md_gate_bwd(const float* dres, const void* y, const float* gate, int64_t ldmod, int64_t T, void* dy,
-                       float* dgate, int64_t rows, int64_t D, void* stream);
+                       float* dgate, int64_t rows, int64_t D, int prec, void* stream);
 
 /* ------------------------------------------------------------------------------------- attention */
 /* softmax(Q K^T / sqrt(hd)) V, non-causal (F.scaled_dot_product_attention at utils.py:188-193 self,
@@ -118,9 +125,10 @@ MD_API int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_t ld
                        const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
                        void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                        int64_t Tq, int64_t Tk, int64_t hd, void* stream);
-/* EXPERIMENTAL, not dispatched by md_attn_fwd / md_attn_bwd: the same forward and backward (no delta scratch: it is
- * derived from o and dout) on tcgen05 / TMEM for head_dim 64 and Tk <= 256
- * (csrc/attn_tcgen05.cu; written in round 1, first hardware run scheduled for round 2 -- DESIGN.md section 8). */
+/* The same forward and backward on the 5th-generation tensor cores (tcgen05.mma, accumulators and S / dP tiles in
+ * TMEM, operands by TMA; csrc/attn_tc.cu) for head_dim 64 and Tk <= 256 -- every sequence of the res-256 configs.
+ * Persistent, warp-specialised kernels; no delta scratch (derived from o and dout).  md_attn_fwd / md_attn_bwd
+ * dispatch here whenever the shape is inside this envelope. */
 MD_API int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                           int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
                           void* stream);
@@ -128,48 +136,64 @@ MD_API int md_attn_bwd_tc(const void* dout, int64_t lddo, const void* q, int64_t
                           const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, void* dq,
                           int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                           int64_t Tq, int64_t Tk, int64_t hd, void* stream);
+/* High-precision mode (prec = 1): the same contract with fp32 q / k / v / o / gradients, plain fp32 FMAs. */
+MD_API int md_attn_fwd_f32(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                           int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
+                           void* stream);
+MD_API int md_attn_bwd_f32(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                           const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
+                           void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
+                           int64_t Tq, int64_t Tk, int64_t hd, void* stream);
+/* High-precision GEMM operands: fp32 x [batch][rows][cols] (row pitch ldx, batch pitch batch_stride, elements) ->
+ * bf16 triples hi = bf16(x), lo = bf16(x - hi) stacked along the contraction, so that md_gemm_bf16 at 3x the depth
+ * accumulates a_hi b_hi + a_lo b_hi + a_hi b_lo in fp32 (the high-precision mode runs on the same tcgen05 kernel).
+ * role 0 (A operand): [hi | lo | hi]; role 1 (B operand): [hi | hi | lo].
+ * along 0: out [batch][rows][3*cols] (K-major operands); along 1: out [batch][3*rows][cols] (MN-major operands). */
+MD_API int md_split3_bf16(const float* x, int64_t ldx, int64_t batch_stride, void* out, int64_t batch, int64_t rows,
+                          int64_t cols, int role, int along, void* stream);
 
 /* ------------------------------------------------------------------------------ feed-forward tails */
 /* SwiGLU (dit.py:88-89): u bf16 [rows, 2f] = [w1 x | w2 x];  h = silu(u[:, :f]) * u[:, f:]. */
-MD_API int md_swiglu_fwd(const void* u, void* h, int64_t rows, int64_t f, void* stream);
-MD_API int md_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int64_t f, void* stream);
+MD_API int md_swiglu_fwd(const void* u, void* h, int64_t rows, int64_t f, int prec, void* stream);
+MD_API int md_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int64_t f, int prec, void* stream);
 /* act = act(pre), bf16 -> bf16 (the expert GELU, dit.py:136, as its own HBM-bound pass: in the GEMM epilogue it
  * made the expert GEMM epilogue-bound) */
-MD_API int md_act_fwd(const void* pre, void* out, int64_t n, int act, void* stream);
+MD_API int md_act_fwd(const void* pre, void* out, int64_t n, int act, int prec, void* stream);
 /* dpre = dact * act'(pre), bf16 (act: 0 gelu-erf dit.py:136, 1 gelu-tanh utils.py:65). */
-MD_API int md_act_bwd(const void* dact, const void* pre, void* dpre, int64_t n, int act, void* stream);
+MD_API int md_act_bwd(const void* dact, const void* pre, void* dpre, int64_t n, int act, int prec, void* stream);
 /* c_act(bf16) = gelu_tanh(c f32)  (the nn.GELU in every adaLN_modulation, dit.py:227-230);
  * bwd: dc(f32) (+)= dc_act(f32) * gelu_tanh'(c). */
-MD_API int md_gelu_tanh_f32_fwd(const float* c, void* out_bf16, int64_t n, void* stream);
+MD_API int md_gelu_tanh_f32_fwd(const float* c, void* out_bf16, int64_t n, int prec, void* stream);
 MD_API int md_gelu_tanh_f32_bwd(const float* dact, const float* c, float* dc, int accumulate, int64_t n, void* stream);
 
 /* -------------------------------------------------------------------------- expert-choice MoE */
 /* FeedForwardECMoe (dit.py:126-143).  E <= 16, D % 8 == 0. */
 /* probs(f32 [rows,E]) = softmax(x(bf16 [rows,D]) . Wg(f32 [E,D])^T)   (dit.py:130-131) */
 MD_API int md_moe_gate_fwd(const void* x, const float* wg, float* probs, int64_t rows, int64_t D, int64_t E,
-                           void* stream);
+                           int prec, void* stream);
 /* per (sample, expert) top-k over the T tokens (dit.py:132): idx int32 [B,E,k], gval f32 [B,E,k],
  * inv int32 [B,T,E] = slot of token t in expert e's list or -1.  T <= 4096. */
 MD_API int md_moe_topk(const float* probs, int32_t* idx, float* gval, int32_t* inv, int64_t B, int64_t T, int64_t E,
                        int64_t k, void* stream);
 /* dispatch (the one-hot einsum dit.py:134 as a gather): xin bf16 [E, B*k, D] */
 MD_API int md_moe_gather(const void* x, const int32_t* idx, void* xin, int64_t B, int64_t T, int64_t E, int64_t k,
-                         int64_t D, void* stream);
+                         int64_t D, int prec, void* stream);
 /* combine (dit.py:139-140) fused with the gated residual (dit.py:238):
  * ymoe(bf16 [rows,D]) = sum_e g*h2 ; xout(f32) = xres + gate[sample]*ymoe */
 MD_API int md_moe_combine_fwd(const void* h2, const float* gval, const int32_t* inv, const float* xres,
                               const float* gate, int64_t ldmod, float* xout, void* ymoe, int64_t B, int64_t T,
-                              int64_t E, int64_t k, int64_t D, void* stream);
+                              int64_t E, int64_t k, int64_t D, int prec, void* stream);
 /* dh2(bf16 [E,B*k,D]) = g * dy[token] ; dgval(f32 [B,E,k]) = <h2, dy[token]> */
 MD_API int md_moe_combine_bwd(const void* dy, const void* h2, const float* gval, const int32_t* idx, void* dh2,
-                              float* dgval, int64_t B, int64_t T, int64_t E, int64_t k, int64_t D, void* stream);
+                              float* dgval, int64_t B, int64_t T, int64_t E, int64_t k, int64_t D,
+                              int prec, void* stream);
 /* softmax/top-k backward + un-dispatch: dscores f32 [rows,E]; dx(bf16 [rows,D]) = sum_e dxin[slot] + dscores.Wg */
 MD_API int md_moe_dx_bwd(const void* dxin, const int32_t* inv, const float* dgval, const float* probs,
                          const float* wg, float* dscores, void* dx, int64_t B, int64_t T, int64_t E, int64_t k,
-                         int64_t D, void* stream);
+                         int64_t D, int prec, void* stream);
 /* dWg(f32 [E,D]) += dscores^T . x  (atomic) */
 MD_API int md_moe_gate_wgrad(const float* dscores, const void* x, float* dwg, int64_t rows, int64_t D, int64_t E,
-                             void* stream);
+                             int prec, void* stream);
 
 /* ------------------------------------------------------------------------- masking (utils.py:382-426) */
 /* get_mask with the uniform noise given: ascending argsort per sample (ties by index).
@@ -186,20 +210,20 @@ MD_API int md_scatter_rows_f32(const float* dy, const int32_t* src_rows, float* 
 /* conditioning *= drop_caption_mask; .float() (model.py:132-139): cap fp16 [B, L*Dc] -> bf16.  keep f64 or NULL;
  * cap_out_f16 (optional, may alias cap_f16) receives the masked fp16 captions (the reference's in-place `*=`). */
 MD_API int md_cond_prepare(const void* cap_f16, const double* keep, void* out_bf16, void* cap_out_f16, int64_t B,
-                           int64_t per_sample, void* stream);
+                           int64_t per_sample, int prec, void* stream);
 /* model.py:182-188,153-166 + the im2col of the patch-embed conv (dit.py:479):
  * sigma = exp(rnd*P_std+P_mean); xn = x + sigma*eps; patches(bf16 [B*T, Kp]) = c_in * xn, column
  * (c*p+i)*p+j, Kp = C*p*p; coef f32 [6,B] = sigma, c_skip, c_out, c_in, c_noise, weight.
  * lat: fp16 (lat_f16=1) or f32.  sigma_in (optional) overrides the draw (sampler path). */
 MD_API int md_edm_prepare(const void* lat, int lat_f16, const float* eps, const float* rnd, const float* sigma_in,
                           float p_mean, float p_std, float sigma_data, float* xn, void* patches, float* coef,
-                          int64_t B, int64_t C, int64_t H, int64_t W, int64_t p, void* stream);
+                          int64_t B, int64_t C, int64_t H, int64_t W, int64_t p, int prec, void* stream);
 /* im2col of the patch-embed conv for the plain DiT.forward entry (dit.py:479,552): patches(bf16 [B*T, C*p*p]) =
  * scale[b] * x, scale f32 [B] or NULL. */
 MD_API int md_patchify(const float* x, const float* scale, void* patches, int64_t B, int64_t C, int64_t H, int64_t W,
-                       int64_t p, void* stream);
+                       int64_t p, int prec, void* stream);
 /* TimestepEmbedder.timestep_embedding (utils.py:265-281): out bf16 [B, dim] = [cos | sin](t * freqs) */
-MD_API int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, void* stream);
+MD_API int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, int prec, void* stream);
 /* weighted masked MSE (model.py:199-210) straight from the final-layer tokens ftok f32 [B*Tk, p*p*C]
  * (column (i*p+j)*C+c, unpatchify dit.py:566-575); keep_tok int32 [B,Tk] = global rows (b*T + token) of the kept
  * tokens (md_mask_sort's keep_rows) or NULL (all tokens).
@@ -210,7 +234,7 @@ MD_API int md_edm_loss_fwd(const float* ftok, const int32_t* keep_tok, const voi
 /* d loss / d ftok * gscale[0] (f32 device scalar: the incoming grad_output) -> bf16 [B*Tk, p*p*C] */
 MD_API int md_edm_loss_bwd(const float* ftok, const int32_t* keep_tok, const void* lat, int lat_f16, const float* xn,
                            const float* coef, const float* gscale, void* dftok, int64_t B, int64_t C, int64_t H,
-                           int64_t W, int64_t p, int64_t Tk, void* stream);
+                           int64_t W, int64_t p, int64_t Tk, int prec, void* stream);
 /* unmask_tokens + unpatchify (utils.py:417-426, dit.py:566-575) + D = c_skip*xn + c_out*F (model.py:173-178).
  * ids_restore int32 [B,T] or NULL; mask_token f32 [p*p*C]; fx (raw network output) and dx (denoised), f32
  * [B,C,H,W]; either may be NULL. */
@@ -220,15 +244,15 @@ MD_API int md_edm_output(const float* ftok, const int32_t* ids_restore, const fl
 
 /* ------------------------------------------------------------------------------------ utilities */
 /* mean over the L tokens of each sample (dit.py:484): x f32 [B,L,D] -> bf16 [B,D]; bwd: dx[b,l,:] += d[b,:]/L */
-MD_API int md_mean_tokens_fwd(const float* x, void* out, int64_t B, int64_t L, int64_t D, void* stream);
+MD_API int md_mean_tokens_fwd(const float* x, void* out, int64_t B, int64_t L, int64_t D, int prec, void* stream);
 MD_API int md_mean_tokens_bwd(const float* d, float* dx, int64_t B, int64_t L, int64_t D, void* stream);
-MD_API int md_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+MD_API int md_cast_f32_bf16(const float* x, void* y, int64_t n, int prec, void* stream);
 /* out(f32 [N]) += column sums of x [rows, N] (bf16 if x_bf16 else f32), pitch ld (bias gradients) */
 MD_API int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int64_t rows, int64_t N, void* stream);
 /* W f32 [batch, rows, cols] -> wb bf16 same layout (optional) and wbt bf16 [batch, cols, rows] (optional):
  * the per-step bf16 operand copies of the fp32 master weights (what autocast does per call in the reference). */
 MD_API int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch, int64_t rows, int64_t cols,
-                             void* stream);
+                             int prec, void* stream);
 /* sumsq(f32 [1]) += sum x^2  (gradient-norm clipping, train.py:85-86) */
 MD_API int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream);
 /* fused (clip-scaled) AdamW on flat fp32 buffers (train.py:39, configs/res_256_pretrain.yaml:50-57):

@@ -1,0 +1,861 @@
+// Attention on the 5th-generation tensor cores (tcgen05 / TMEM / TMA) for head_dim 64 -- forward.
+//
+// Contract = md_attn_fwd: softmax(Q K^T / sqrt(hd)) V, non-causal (F.scaled_dot_product_attention at reference
+// utils.py:188-193 self, 127-132 cross); q / k / v are column slices of the packed projection buffers; lse in the
+// log2 domain.  Envelope: all keys of one (sample, head) fit one S tile, i.e. Tk <= 256 (every sequence of the res-256
+// configs: 64, 77, 256) -- longer sequences stay on the mma.sync kernels (attn.cu).
+//
+// Persistent, warp-specialised, double-buffered.  One CTA per SM loops over tiles = (sample, head or head pair,
+// 128-query block); 12 warps:
+//   warp 0      TMA producer: Q / K (one barrier) and V (another) of tile i+2 as soon as tile i's PV has retired
+//   warp 1      one thread issues S = Q K^T (M 128, N = keys, K 64) and O = P V (M 128, N 64, K = keys)
+//   warp 2      TMEM allocator (512 columns: two 256-column buffers; O of a tile overwrites the first 64 columns of
+//               its own S once the softmax has consumed it)
+//   warps 4-7   softmax group 0 (even tiles), warps 8-11 softmax group 1 (odd tiles): one query row per thread,
+//               whole-row softmax straight from TMEM in two passes (max, then exp2 / sum -- no online rescale because
+//               all of S is resident), P written as bf16 into 128B-swizzled K-major atoms that overwrite the dead Q / K
+//               tiles in shared memory, then O read back, scaled by 1 / rowsum and stored.
+// While group 0 does the softmax of tile i the tensor core runs S of tile i+1 and PV of tile i-1.
+//
+// Tq <= 64 ("packed" mode, the 64-token backbone of mask 0.75): two heads share one 128-row tile -- rows 0-63 are head
+// h, rows 64-127 head h+1, the keys of both heads are stacked along N (S is 128 x 2*keys, each row uses its own head's
+// column range) and P is written block-diagonal so that one PV chain over the stacked V tiles serves both heads.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace md {
+namespace attn_tc {
+
+constexpr int kQ = 128;               // query rows per tile (UMMA M)
+constexpr int kHd = 64;               // head_dim == one 128-byte swizzle row of bf16
+constexpr int kMaxCols = 256;         // S columns per tile (keys, or 2 x keys in packed mode)
+constexpr int kThreads = 384;
+constexpr int kTmemCols = 512;
+constexpr int kBytesQ = kQ * kHd * 2;            // 16 KB
+constexpr int kStageQKP = 64 * 1024;             // Q (16 KB) + K (<= 32 KB); later P (<= 64 KB = 4 atoms of 64 keys)
+constexpr int kStageV = 32 * 1024;
+constexpr int kStage = kStageQKP + kStageV;      // 96 KB
+constexpr int kBytesPAtom = kQ * 64 * 2;         // 16 KB: 128 rows x 64 keys
+constexpr int kOffBar = 2 * kStage;
+constexpr int kSmemBytes = kOffBar + 256 + 1024;
+
+struct FwdParams {
+  __nv_bfloat16* o;
+  long long ldo;
+  float* lse;
+  int H, Tq, Tk, n_pad, packed, q_blocks, head_tiles;
+  long long tiles;
+  float scale_log2;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void decode_tile(long long t, const FwdParams& p, int& b, int& h0, int& qb) {
+  qb = static_cast<int>(t % p.q_blocks);
+  t /= p.q_blocks;
+  const int ht = static_cast<int>(t % p.head_tiles);
+  b = static_cast<int>(t / p.head_tiles);
+  h0 = p.packed ? 2 * ht : ht;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* qk_full = bars;        // [2] TMA bytes of Q + K
+  uint64_t* v_full = bars + 2;     // [2] TMA bytes of V
+  uint64_t* s_full = bars + 4;     // [2] S in TMEM (tcgen05.commit)
+  uint64_t* p_full = bars + 6;     // [2] P in shared memory, S consumed (4 warps)
+  uint64_t* o_full = bars + 8;     // [2] O in TMEM, stage's shared memory free again (tcgen05.commit)
+  uint64_t* o_free = bars + 10;    // [2] O read back: the TMEM buffer is free (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pad = p.n_pad;                          // keys of one head, padded to 16
+  const int n_s = p.packed ? 2 * n_pad : n_pad;       // S columns / PV reduction length of a tile
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t n = it >> 1;
+        if (it >= 2) mbar_wait_sleep(&o_full[s], (n - 1) & 1);  // PV of the tile two back has read P and V of this stage
+        int b, h0, qb;
+        decode_tile(t, p, b, h0, qb);
+        uint8_t* sQ = smem + s * kStage;
+        uint8_t* sK = sQ + kBytesQ;
+        uint8_t* sV = sQ + kStageQKP;
+        mbar_expect_tx(&qk_full[s], kBytesQ + n_s * 128);
+        if (!p.packed) {
+          tma_load_3d(&tmQ, &qk_full[s], sQ, h0 * kHd, qb * kQ, b);
+          tma_load_3d(&tmK, &qk_full[s], sK, h0 * kHd, 0, b);
+        } else {
+          tma_load_3d(&tmQ, &qk_full[s], sQ, h0 * kHd, 0, b);
+          tma_load_3d(&tmQ, &qk_full[s], sQ + kBytesQ / 2, (h0 + 1) * kHd, 0, b);
+          tma_load_3d(&tmK, &qk_full[s], sK, h0 * kHd, 0, b);
+          tma_load_3d(&tmK, &qk_full[s], sK + n_pad * 128, (h0 + 1) * kHd, 0, b);
+        }
+        mbar_expect_tx(&v_full[s], n_s * 128);
+        tma_load_3d(&tmV, &v_full[s], sV, h0 * kHd, 0, b);
+        if (p.packed) tma_load_3d(&tmV, &v_full[s], sV + n_pad * 128, (h0 + 1) * kHd, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(kQ, n_s, false, false);   // Q, K both K-major (head_dim contiguous)
+      const uint32_t idesc_o = umma_idesc_bf16(kQ, kHd, false, true);    // P K-major, V MN-major (head_dim contiguous)
+      const int ksteps = n_s / 16;
+      auto issue_pv = [&](uint32_t j) {
+        const int s = j & 1;
+        const uint32_t n = j >> 1;
+        mbar_wait_sleep(&p_full[s], n & 1);
+        mbar_wait_sleep(&v_full[s], n & 1);
+        tc_fence_after();
+        const uint32_t ap = smem_u32(smem + s * kStage);
+        const uint32_t av = ap + kStageQKP;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t da = umma_smem_desc(ap + (kk >> 2) * kBytesPAtom + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_smem_desc(av + kk * (16 * 128), 64 * 128, 1024);
+          umma_bf16(tmem_base + s * kMaxCols, da, db, idesc_o, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[s]);
+      };
+      uint32_t it = 0;
+      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t n = it >> 1;
+        mbar_wait_sleep(&qk_full[s], n & 1);
+        if (it >= 2) mbar_wait_sleep(&o_free[s], (n - 1) & 1);  // O of the tile two back has left this TMEM buffer
+        tc_fence_after();
+        const uint32_t aq = smem_u32(smem + s * kStage);
+        const uint32_t ak = aq + kBytesQ;
+#pragma unroll
+        for (int ks = 0; ks < kHd / 16; ++ks)
+          umma_bf16(tmem_base + s * kMaxCols, umma_smem_desc(aq + ks * 32, 16, 1024),
+                    umma_smem_desc(ak + ks * 32, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        umma_commit(&s_full[s]);
+        if (it >= 1) issue_pv(it - 1);
+      }
+      if (it >= 1) issue_pv(it - 1);
+    }
+  } else if (warp >= 4) {
+    // ================================ softmax / epilogue groups ================================
+    const int grp = (warp - 4) >> 2;              // group g handles tiles with (iteration & 1) == g -> stage g
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch (hardware rule)
+    const int row = quarter * 32 + lane;          // row inside the tile == TMEM lane
+    const int hi = (p.packed && row >= 64) ? 1 : 0;
+    const int col0 = hi ? n_pad : 0;              // first S column of this row's head
+    const int chunks = (n_pad + 31) / 32;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + grp * kMaxCols;
+    uint8_t* sP = smem + grp * kStage;
+    const int s = grp;
+    uint32_t n = 0;
+    for (long long t = blockIdx.x + 1LL * grp * gridDim.x; t < p.tiles; t += 2LL * gridDim.x, ++n) {
+      int b, h0, qb;
+      decode_tile(t, p, b, h0, qb);
+      const int h = h0 + hi;
+      const int qrow = p.packed ? (row & 63) : qb * kQ + row;
+      const bool q_ok = qrow < p.Tq;
+
+      mbar_wait_sleep(&s_full[s], n & 1);
+      tc_fence_after();
+      // ---- pass 1: row maximum.  Two register arrays alternate so that the next 32 columns are in flight while the
+      // current ones are reduced (tcgen05.wait::ld waits for ALL outstanding loads: issue order = wait, issue, use).
+      float m;
+      {
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
+        auto red = [&](const uint32_t (&r)[32], int c) {
+          if ((c + 1) * 32 <= p.Tk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < p.Tk) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
+          }
+        };
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(trow + col0, ra);
+        for (int c = 0; c < chunks; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < chunks) tmem_ld_32x32(trow + col0 + (c + 1) * 32, rb);
+          red(ra, c);
+          if (c + 1 < chunks) {
+            tmem_ld_wait();
+            if (c + 2 < chunks) tmem_ld_32x32(trow + col0 + (c + 2) * 32, ra);
+            red(rb, c + 1);
+          }
+        }
+        m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      }
+      const float m2 = m * p.scale_log2;
+      // ---- pass 2: P = exp2(s * scale - max), row sum, bf16 P into the swizzled K-major atoms
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        uint8_t* prow = sP + row * 128;
+        const int sw = row & 7;
+        auto emit = [&](uint32_t (&r)[32], int c) {
+          float pv[32];
+          if ((c + 1) * 32 <= p.Tk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -m2));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              pv[j] = (c * 32 + j < p.Tk) ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -m2)) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ls[j & 3] += pv[j];
+          const int k8 = (col0 >> 3) + c * 4;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c * 32 + g * 8 < n_pad) {   // n_pad is a multiple of 16: whole 8-key groups
+              const int key8 = k8 + g;
+              uint4 w;
+              w.x = pack2(pv[8 * g + 0], pv[8 * g + 1]);
+              w.y = pack2(pv[8 * g + 2], pv[8 * g + 3]);
+              w.z = pack2(pv[8 * g + 4], pv[8 * g + 5]);
+              w.w = pack2(pv[8 * g + 6], pv[8 * g + 7]);
+              *reinterpret_cast<uint4*>(prow + (key8 >> 3) * kBytesPAtom + (((key8 & 7) ^ sw) << 4)) = w;
+            }
+          }
+        };
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(trow + col0, ra);
+        for (int c = 0; c < chunks; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < chunks) tmem_ld_32x32(trow + col0 + (c + 1) * 32, rb);
+          emit(ra, c);
+          if (c + 1 < chunks) {
+            tmem_ld_wait();
+            if (c + 2 < chunks) tmem_ld_32x32(trow + col0 + (c + 2) * 32, ra);
+            emit(rb, c + 1);
+          }
+        }
+      }
+      const float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      if (p.packed) {  // block-diagonal P: zero this row's columns of the other head
+        const int z0 = (hi ? 0 : n_pad) >> 3;
+        for (int g = 0; g < (n_pad >> 3); ++g) {
+          const int key8 = z0 + g;
+          *reinterpret_cast<uint4*>(sP + (key8 >> 3) * kBytesPAtom + row * 128 + (((key8 & 7) ^ (row & 7)) << 4)) =
+              make_uint4(0, 0, 0, 0);
+        }
+      }
+      fence_proxy_async_smem();  // the UMMA reads P through the async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[s]);
+
+      // ---- epilogue: O / rowsum
+      mbar_wait_sleep(&o_full[s], n & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(trow, r0);
+      tmem_ld_32x32(trow + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[s]);
+      if (q_ok) {
+        const float inv = 1.f / l;
+        __nv_bfloat16* dst = p.o + (static_cast<long long>(b) * p.Tq + qrow) * p.ldo + h * kHd;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t* rr = g < 4 ? r0 : r1;
+          const int e = (g & 3) * 8;
+          __nv_bfloat162 v0 = __floats2bfloat162_rn(__uint_as_float(rr[e + 0]) * inv, __uint_as_float(rr[e + 1]) * inv);
+          __nv_bfloat162 v1 = __floats2bfloat162_rn(__uint_as_float(rr[e + 2]) * inv, __uint_as_float(rr[e + 3]) * inv);
+          __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(rr[e + 4]) * inv, __uint_as_float(rr[e + 5]) * inv);
+          __nv_bfloat162 v3 = __floats2bfloat162_rn(__uint_as_float(rr[e + 6]) * inv, __uint_as_float(rr[e + 7]) * inv);
+          uint4 w;
+          w.x = *reinterpret_cast<uint32_t*>(&v0);
+          w.y = *reinterpret_cast<uint32_t*>(&v1);
+          w.z = *reinterpret_cast<uint32_t*>(&v2);
+          w.w = *reinterpret_cast<uint32_t*>(&v3);
+          *reinterpret_cast<uint4*>(dst + g * 8) = w;
+        }
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + qrow] = m2 + log2f(l);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// bf16 [batch][rows][cols] view, box = [1][box_rows][64 columns], 128B swizzle (the encoding of the GEMM operand maps).
+int make_map(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long batch, long long ld,
+             int box_rows) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(rows * ld) * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return md_set_error(MD_ERR_CUDA, "attention (tcgen05): cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+int sm_count_cached() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+}  // namespace attn_tc
+}  // namespace md
+
+extern "C" int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                              int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
+                              void* stream) {
+  using namespace md;
+  using namespace md::attn_tc;
+  if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0) return B == 0 ? 0 : md_set_error(MD_ERR_INVALID, "md_attn_fwd_tc: bad sizes");
+  if (hd != kHd || Tk > kMaxCols)
+    return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_fwd_tc: needs head_dim 64 and Tk <= 256");
+  if (!q || !k || !v || !o || !lse) return md_set_error(MD_ERR_INVALID, "md_attn_fwd_tc: null pointer");
+  const uintptr_t align = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                          reinterpret_cast<uintptr_t>(o);
+  if ((align & 15) != 0 || ((ldq | ldk | ldv | ldo) % 8) != 0)
+    return md_set_error(MD_ERR_INVALID, "md_attn_fwd_tc: operands must be 16-byte aligned with pitches % 8 == 0");
+  FwdParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.ldo = ldo;
+  p.lse = lse;
+  p.H = static_cast<int>(H); p.Tq = static_cast<int>(Tq); p.Tk = static_cast<int>(Tk);
+  p.n_pad = (p.Tk + 15) & ~15;
+  p.packed = (Tq <= 64 && (H % 2) == 0 && 2 * p.n_pad <= kMaxCols) ? 1 : 0;
+  p.q_blocks = p.packed ? 1 : static_cast<int>((Tq + kQ - 1) / kQ);
+  p.head_tiles = p.packed ? p.H / 2 : p.H;
+  p.tiles = static_cast<long long>(B) * p.head_tiles * p.q_blocks;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
+  CUtensorMap tmQ, tmK, tmV;
+  if (int rc = make_map(&tmQ, q, H * hd, Tq, B, ldq, p.packed ? 64 : kQ)) return rc;
+  if (int rc = make_map(&tmK, k, H * hd, Tk, B, ldk, p.n_pad)) return rc;
+  if (int rc = make_map(&tmV, v, H * hd, Tk, B, ldv, p.n_pad)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
+    attr = true;
+  }
+  const long long sms = sm_count_cached();
+  const unsigned grid = static_cast<unsigned>(p.tiles < sms ? p.tiles : sms);
+  attn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  return check_launch("md_attn_fwd_tc");
+}
+
+// ================================================================================================ backward
+// dQ, dK, dV of the same attention (the reference gets them from autograd through F.scaled_dot_product_attention).
+// delta = rowsum(dO * O) is derived here from o and dout (no scratch buffer).  Same envelope (head_dim 64, Tk <= 256).
+//
+// Persistent, warp-specialised.  A CTA loops over "iterations" = (sample, head [pair], 128-key block kb, 128-query block
+// qb), kb outer / qb inner, so that dK / dV of the resident key block accumulate in TMEM over the query blocks and are
+// read out once; dQ of a query block is produced per key block and summed across key blocks through global memory by
+// the one thread that owns that row segment (deterministic).  Per iteration the five GEMMs are
+//     S = Q K^T, dP = dO V^T            (M 128 queries, N = keys of the block, K 64)      -> TMEM
+//     dV += P^T dO, dK += dS^T Q        (M 128 keys,    N 64, K 128 queries)              -> TMEM accumulators
+//     dQ  = dS K                        (M 128 queries, N 64, K = keys of the block)      -> TMEM
+// and the element-wise part  P = exp2(S * scale - lse),  dS = P * (dP - delta)  runs on two groups of four warps, each
+// owning HALF of the block's key columns (chunk 0 / chunk 1: separate TMEM buffers and barriers), one query row per
+// thread.  P and dS go to shared memory once, as bf16 [query][key] in 128B-swizzled atoms of 64 keys: that buffer is the
+// K-major A operand of dQ and -- read through the MN-major descriptor -- the A operand of dV and dK.
+// The issuer runs one iteration ahead with S / dP (double-buffered Q / dO and K / V stages), so the tensor core computes
+// S / dP of iteration g+1 and the three gradient GEMMs of iteration g while the groups work on iteration g+1.
+// Tq <= 64 and Tk <= 64 ("packed"): two heads share the 128-row tile; chunk c holds the keys of head c and rows of the
+// other head write zeros there (block-diagonal P / dS).
+namespace md {
+namespace attn_tc {
+
+constexpr int kBwdOffK = 0;                       // [2] x 16 KB : 128 keys x 64
+constexpr int kBwdOffV = 32 * 1024;               // [2] x 16 KB
+constexpr int kBwdOffQ = 64 * 1024;               // [2] x 16 KB : 128 queries x 64
+constexpr int kBwdOffdO = 96 * 1024;              // [2] x 16 KB
+constexpr int kBwdOffP = 128 * 1024;              // 32 KB : 2 atoms (128 queries x 64 keys)
+constexpr int kBwdOffdS = 160 * 1024;             // 32 KB
+constexpr int kBwdOffBar = 192 * 1024;
+constexpr int kBwdSmemBytes = kBwdOffBar + 256 + 1024;
+constexpr int kTile = 16 * 1024;
+// TMEM columns
+constexpr uint32_t kColS = 0, kColdP = 64, kColBuf = 128, kColdQ = 256, kColdK = 320, kColdV = 384;
+
+struct BwdParams {
+  const __nv_bfloat16* dout; long long lddo;
+  const __nv_bfloat16* o; long long ldo;
+  const float* lse;
+  __nv_bfloat16* dq; long long lddq;
+  __nv_bfloat16* dk; long long lddk;
+  __nv_bfloat16* dv; long long lddv;
+  int H, Tq, Tk, n_pad, packed, QB, KB, head_tiles, kv_box;
+  long long items;
+  float scale, scale_log2;
+};
+
+struct BwdIter {  // position of iteration g inside this CTA's sequence
+  int b, h0, kb, qb, n_kb, n0, n1;
+  uint32_t u;       // key-block phase counter (one per (item, kb))
+  bool first, last; // first / last query block of the phase
+};
+
+__device__ __forceinline__ BwdIter bwd_iter(uint32_t g, const BwdParams& p) {
+  BwdIter it;
+  const uint32_t ipi = p.KB * p.QB;
+  const long long item = blockIdx.x + static_cast<long long>(g / ipi) * gridDim.x;
+  const uint32_t j = g % ipi;
+  it.kb = j / p.QB;
+  it.qb = j % p.QB;
+  it.u = g / p.QB;
+  it.first = it.qb == 0;
+  it.last = it.qb == p.QB - 1;
+  const int ht = static_cast<int>(item % p.head_tiles);
+  it.b = static_cast<int>(item / p.head_tiles);
+  it.h0 = p.packed ? 2 * ht : ht;
+  if (p.packed) {
+    it.n_kb = 2 * p.n_pad; it.n0 = p.n_pad; it.n1 = p.n_pad;
+  } else {
+    it.n_kb = min(128, p.n_pad - it.kb * 128);
+    it.n0 = ((it.n_kb >> 1) + 15) & ~15;
+    it.n1 = it.n_kb - it.n0;
+  }
+  return it;
+}
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float (&f)[8]) {
+  __nv_bfloat162 v0 = __floats2bfloat162_rn(f[0], f[1]);
+  __nv_bfloat162 v1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 v2 = __floats2bfloat162_rn(f[4], f[5]);
+  __nv_bfloat162 v3 = __floats2bfloat162_rn(f[6], f[7]);
+  uint4 w;
+  w.x = *reinterpret_cast<uint32_t*>(&v0);
+  w.y = *reinterpret_cast<uint32_t*>(&v1);
+  w.z = *reinterpret_cast<uint32_t*>(&v2);
+  w.w = *reinterpret_cast<uint32_t*>(&v3);
+  *reinterpret_cast<uint4*>(dst) = w;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdOffBar);
+  uint64_t* kv_full = bars;          // [2] TMA bytes of a K / V block
+  uint64_t* kv_free = bars + 2;      // [2] every MMA of the phase that used this K / V stage has retired (commit)
+  uint64_t* qdo_full = bars + 4;     // [2] TMA bytes of a Q / dO block
+  uint64_t* mma_done = bars + 6;     // [2] gradient GEMMs of an iteration retired (commit): Q/dO stage, P/dS, dQ ready
+  uint64_t* sdp_full = bars + 8;     // [2] S / dP chunk in TMEM (commit)
+  uint64_t* sdp_free = bars + 10;    // [2] chunk consumed by its group (4 warps)
+  uint64_t* pds_full = bars + 12;    // P / dS of the iteration in shared memory (8 warps)
+  uint64_t* dq_free = bars + 13;     // dQ of the previous iteration read back (8 warps)
+  uint64_t* acc_free = bars + 14;    // dK / dV of the previous phase read back (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t my_items = blockIdx.x < p.items ? static_cast<uint32_t>((p.items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const uint32_t total = my_items * p.KB * p.QB;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_free[i], 1);
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&mma_done[i], 1);
+      mbar_init(&sdp_full[i], 1);
+      mbar_init(&sdp_free[i], 4);
+    }
+    mbar_init(pds_full, 8);
+    mbar_init(dq_free, 8);
+    mbar_init(acc_free, 8);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      for (uint32_t g = 0; g < total; ++g) {
+        const BwdIter it = bwd_iter(g, p);
+        if (it.first) {
+          const int ks = it.u & 1;
+          if (it.u >= 2) mbar_wait_sleep(&kv_free[ks], ((it.u >> 1) - 1) & 1);
+          uint8_t* sK = smem + kBwdOffK + ks * kTile;
+          uint8_t* sV = smem + kBwdOffV + ks * kTile;
+          if (!p.packed) {
+            mbar_expect_tx(&kv_full[ks], 2 * p.kv_box * 128);
+            tma_load_3d(&tmK, &kv_full[ks], sK, it.h0 * kHd, it.kb * 128, it.b);
+            tma_load_3d(&tmV, &kv_full[ks], sV, it.h0 * kHd, it.kb * 128, it.b);
+          } else {
+            mbar_expect_tx(&kv_full[ks], 4 * p.kv_box * 128);
+            tma_load_3d(&tmK, &kv_full[ks], sK, it.h0 * kHd, 0, it.b);
+            tma_load_3d(&tmK, &kv_full[ks], sK + p.n_pad * 128, (it.h0 + 1) * kHd, 0, it.b);
+            tma_load_3d(&tmV, &kv_full[ks], sV, it.h0 * kHd, 0, it.b);
+            tma_load_3d(&tmV, &kv_full[ks], sV + p.n_pad * 128, (it.h0 + 1) * kHd, 0, it.b);
+          }
+        }
+        const int st = g & 1;
+        if (g >= 2) mbar_wait_sleep(&mma_done[st], ((g >> 1) - 1) & 1);
+        uint8_t* sQ = smem + kBwdOffQ + st * kTile;
+        uint8_t* sdO = smem + kBwdOffdO + st * kTile;
+        mbar_expect_tx(&qdo_full[st], 2 * kTile);
+        if (!p.packed) {
+          tma_load_3d(&tmQ, &qdo_full[st], sQ, it.h0 * kHd, it.qb * kQ, it.b);
+          tma_load_3d(&tmdO, &qdo_full[st], sdO, it.h0 * kHd, it.qb * kQ, it.b);
+        } else {
+          tma_load_3d(&tmQ, &qdo_full[st], sQ, it.h0 * kHd, 0, it.b);
+          tma_load_3d(&tmQ, &qdo_full[st], sQ + kTile / 2, (it.h0 + 1) * kHd, 0, it.b);
+          tma_load_3d(&tmdO, &qdo_full[st], sdO, it.h0 * kHd, 0, it.b);
+          tma_load_3d(&tmdO, &qdo_full[st], sdO + kTile / 2, (it.h0 + 1) * kHd, 0, it.b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0 && total > 0) {
+      const uint32_t idesc_mn = umma_idesc_bf16(kQ, kHd, true, true);    // dV, dK: A and B MN-major
+      const uint32_t idesc_dq = umma_idesc_bf16(kQ, kHd, false, true);   // dQ: A K-major, B MN-major
+      auto issue_sdp = [&](uint32_t g) {
+        const BwdIter it = bwd_iter(g, p);
+        const int st = g & 1, ks = it.u & 1;
+        mbar_wait_sleep(&qdo_full[st], (g >> 1) & 1);
+        if (it.first) mbar_wait_sleep(&kv_full[ks], (it.u >> 1) & 1);
+        const uint32_t aQ = smem_u32(smem + kBwdOffQ + st * kTile), adO = smem_u32(smem + kBwdOffdO + st * kTile);
+        const uint32_t aK = smem_u32(smem + kBwdOffK + ks * kTile), aV = smem_u32(smem + kBwdOffV + ks * kTile);
+        for (int c = 0; c < 2; ++c) {
+          const int n_c = c ? it.n1 : it.n0;
+          const int colbase = c ? it.n0 : 0;
+          if (g > 0) mbar_wait_sleep(&sdp_free[c], (g - 1) & 1);
+          tc_fence_after();
+          if (n_c > 0) {
+            const uint32_t idesc_s = umma_idesc_bf16(kQ, n_c, false, false);
+            const uint32_t d = tmem_base + c * kColBuf;
+#pragma unroll
+            for (int ks4 = 0; ks4 < kHd / 16; ++ks4)
+              umma_bf16(d + kColS, umma_smem_desc(aQ + ks4 * 32, 16, 1024),
+                        umma_smem_desc(aK + colbase * 128 + ks4 * 32, 16, 1024), idesc_s, ks4 > 0 ? 1u : 0u);
+#pragma unroll
+            for (int ks4 = 0; ks4 < kHd / 16; ++ks4)
+              umma_bf16(d + kColdP, umma_smem_desc(adO + ks4 * 32, 16, 1024),
+                        umma_smem_desc(aV + colbase * 128 + ks4 * 32, 16, 1024), idesc_s, ks4 > 0 ? 1u : 0u);
+          }
+          umma_commit(&sdp_full[c]);
+        }
+      };
+      auto issue_grad = [&](uint32_t g) {
+        const BwdIter it = bwd_iter(g, p);
+        const int st = g & 1, ks = it.u & 1;
+        mbar_wait_sleep(pds_full, g & 1);
+        if (g > 0) mbar_wait_sleep(dq_free, (g - 1) & 1);
+        if (it.first && it.u > 0) mbar_wait_sleep(acc_free, (it.u - 1) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(smem + kBwdOffQ + st * kTile), adO = smem_u32(smem + kBwdOffdO + st * kTile);
+        const uint32_t aK = smem_u32(smem + kBwdOffK + ks * kTile);
+        const uint32_t aP = smem_u32(smem + kBwdOffP), adS = smem_u32(smem + kBwdOffdS);
+        // dV += P^T dO, dK += dS^T Q  (reduction over the 128 queries of the block)
+        for (int kk = 0; kk < kQ / 16; ++kk) {
+          const uint64_t db_do = umma_smem_desc(adO + kk * (16 * 128), 64 * 128, 1024);
+          const uint64_t db_q = umma_smem_desc(aQ + kk * (16 * 128), 64 * 128, 1024);
+          const uint64_t da_p = umma_smem_desc(aP + kk * (16 * 128), kTile, 1024);
+          const uint64_t da_ds = umma_smem_desc(adS + kk * (16 * 128), kTile, 1024);
+          const uint32_t acc = (!it.first || kk > 0) ? 1u : 0u;
+          umma_bf16(tmem_base + kColdV, da_p, db_do, idesc_mn, acc);
+          umma_bf16(tmem_base + kColdK, da_ds, db_q, idesc_mn, acc);
+        }
+        // dQ = dS K over the keys of the block (A K-major atoms, B = K tile read MN-major)
+        for (int kk = 0; kk < it.n_kb / 16; ++kk)
+          umma_bf16(tmem_base + kColdQ, umma_smem_desc(adS + (kk >> 2) * kTile + (kk & 3) * 32, 16, 1024),
+                    umma_smem_desc(aK + kk * (16 * 128), 64 * 128, 1024), idesc_dq, kk > 0 ? 1u : 0u);
+        umma_commit(&mma_done[st]);
+        if (it.last) umma_commit(&kv_free[ks]);
+      };
+      issue_sdp(0);
+      for (uint32_t g = 0; g < total; ++g) {
+        if (g + 1 < total) issue_sdp(g + 1);
+        issue_grad(g);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ element-wise groups ================================
+    const int c = (warp - 4) >> 2;                // chunk (half of the key block) this group owns
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;          // query row inside the tile == TMEM lane (== key row for dK / dV)
+    const int hi = (p.packed && row >= 64) ? 1 : 0;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint8_t* sP = smem + kBwdOffP;
+    uint8_t* sdS = smem + kBwdOffdS;
+
+    // read back dQ of iteration g (this thread: 32 columns of its row) and, after the last query block of a phase,
+    // dK (group 0) or dV (group 1) of the key row this thread owns
+    auto drain = [&](uint32_t g) {
+      const BwdIter it = bwd_iter(g, p);
+      mbar_wait_sleep(&mma_done[g & 1], (g >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32(trow + kColdQ + c * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+      const int qidx = p.packed ? (row & 63) : it.qb * kQ + row;
+      if (qidx < p.Tq) {
+        __nv_bfloat16* dst = p.dq + (static_cast<long long>(it.b) * p.Tq + qidx) * p.lddq + (it.h0 + hi) * kHd + c * 32;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[8 * e + j]) * p.scale;
+          if (it.kb > 0) {  // sum over key blocks: the partial of the previous block was written by this very thread
+            const uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * e);
+            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 of = __bfloat1622float2(oh[j]);
+              f[2 * j] += of.x;
+              f[2 * j + 1] += of.y;
+            }
+          }
+          store_bf16x8(dst + 8 * e, f);
+        }
+      }
+      if (it.last) {
+        uint32_t r2[32];
+        const uint32_t col = c == 0 ? kColdK : kColdV;
+        tmem_ld_32x32(trow + col, r);
+        tmem_ld_32x32(trow + col + 32, r2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);
+        int key, kh;
+        if (p.packed) { kh = row >= p.n_pad ? 1 : 0; key = row - kh * p.n_pad; if (row >= 2 * p.n_pad) key = p.Tk; }
+        else { kh = 0; key = it.kb * 128 + row; }
+        if (key < p.Tk) {
+          const float mul = c == 0 ? p.scale : 1.0f;
+          __nv_bfloat16* base = c == 0 ? p.dk + (static_cast<long long>(it.b) * p.Tk + key) * p.lddk
+                                       : p.dv + (static_cast<long long>(it.b) * p.Tk + key) * p.lddv;
+          __nv_bfloat16* dst = base + (it.h0 + kh) * kHd;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t* rr = e < 4 ? r : r2;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(rr[8 * (e & 3) + j]) * mul;
+            store_bf16x8(dst + 8 * e, f);
+          }
+        }
+      }
+    };
+
+    for (uint32_t g = 0; g < total; ++g) {
+      const BwdIter it = bwd_iter(g, p);
+      const int n_c = c ? it.n1 : it.n0;
+      const int colbase = c ? it.n0 : 0;
+      const bool active = !p.packed || hi == c;   // warp-uniform (rows 0-63 / 64-127 are whole warps)
+      const int h = it.h0 + hi;
+      const int qidx = p.packed ? (row & 63) : it.qb * kQ + row;
+      const bool q_ok = qidx < p.Tq;
+      // lse (log2 domain) and delta = sum_d dO * O of this thread's query row; +inf lse -> P = 0 for padded queries
+      float lrow = INFINITY, delta = 0.f;
+      if (active && q_ok) {
+        lrow = p.lse[(static_cast<long long>(it.b) * p.H + h) * p.Tq + qidx];
+        const uint4* po = reinterpret_cast<const uint4*>(p.o + (static_cast<long long>(it.b) * p.Tq + qidx) * p.ldo + h * kHd);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (static_cast<long long>(it.b) * p.Tq + qidx) * p.lddo + h * kHd);
+        float dl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < kHd / 8; ++j) {
+          const uint4 a = po[j], d = pd[j];
+          const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+          const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fa = __bfloat1622float2(ah[e]), fd = __bfloat1622float2(dh[e]);
+            dl[e] = fmaf(fa.x, fd.x, dl[e]);
+            dl[e] = fmaf(fa.y, fd.y, dl[e]);
+          }
+        }
+        delta = (dl[0] + dl[1]) + (dl[2] + dl[3]);
+      }
+      // key index (inside its head) of column 0 of this chunk
+      const int key0 = p.packed ? 0 : it.kb * 128 + colbase;
+
+      uint32_t Pp[32], dSp[32];  // 64 columns of P and dS, packed bf16x2
+#pragma unroll
+      for (int j = 0; j < 32; ++j) Pp[j] = dSp[j] = 0u;
+      mbar_wait_sleep(&sdp_full[c], g & 1);
+      tc_fence_after();
+      if (active && n_c > 0) {
+        const uint32_t tb = trow + c * kColBuf;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (hf * 32 < n_c) {
+            uint32_t rs[32], rp[32];
+            tmem_ld_32x32(tb + kColS + hf * 32, rs);
+            tmem_ld_32x32(tb + kColdP + hf * 32, rp);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int key = key0 + hf * 32 + j;
+              float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), p.scale_log2, -lrow));
+              float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), p.scale_log2, -lrow));
+              float d0 = p0 * (__uint_as_float(rp[j]) - delta);
+              float d1 = p1 * (__uint_as_float(rp[j + 1]) - delta);
+              if (key >= p.Tk) { p0 = 0.f; d0 = 0.f; }       // zero-filled K / V rows beyond Tk (and stale TMEM beyond N)
+              if (key + 1 >= p.Tk) { p1 = 0.f; d1 = 0.f; }
+              Pp[hf * 16 + (j >> 1)] = pack2(p0, p1);
+              dSp[hf * 16 + (j >> 1)] = pack2(d0, d1);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sdp_free[c]);
+
+      // P / dS of the previous iteration must have been consumed (its gradient GEMMs retired) before they are overwritten
+      if (g > 0) mbar_wait_sleep(&mma_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {
+        if (g8 * 8 < n_c) {
+          const int key8 = (colbase >> 3) + g8;
+          const int off = (key8 >> 3) * kTile + row * 128 + (((key8 & 7) ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(sP + off) = make_uint4(Pp[4 * g8], Pp[4 * g8 + 1], Pp[4 * g8 + 2], Pp[4 * g8 + 3]);
+          *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dSp[4 * g8], dSp[4 * g8 + 1], dSp[4 * g8 + 2], dSp[4 * g8 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      if (g > 0) drain(g - 1);
+    }
+    if (total > 0) drain(total - 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace attn_tc
+}  // namespace md
+
+extern "C" int md_attn_bwd_tc(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                              const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, void* dq,
+                              int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
+                              int64_t Tq, int64_t Tk, int64_t hd, void* stream) {
+  using namespace md;
+  using namespace md::attn_tc;
+  if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0) return B == 0 ? 0 : md_set_error(MD_ERR_INVALID, "md_attn_bwd_tc: bad sizes");
+  if (hd != kHd || Tk > kMaxCols)
+    return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_bwd_tc: needs head_dim 64 and Tk <= 256");
+  if (!dout || !q || !k || !v || !o || !lse || !dq || !dk || !dv)
+    return md_set_error(MD_ERR_INVALID, "md_attn_bwd_tc: null pointer");
+  const uintptr_t align = reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                          reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(dq) |
+                          reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv);
+  if ((align & 15) != 0 || ((lddo | ldq | ldk | ldv | ldo | lddq | lddk | lddv) % 8) != 0)
+    return md_set_error(MD_ERR_INVALID, "md_attn_bwd_tc: operands must be 16-byte aligned with pitches % 8 == 0");
+  BwdParams p;
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(dout); p.lddo = lddo;
+  p.o = reinterpret_cast<const __nv_bfloat16*>(o); p.ldo = ldo;
+  p.lse = lse;
+  p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.lddq = lddq;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.lddk = lddk;
+  p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.lddv = lddv;
+  p.H = static_cast<int>(H); p.Tq = static_cast<int>(Tq); p.Tk = static_cast<int>(Tk);
+  p.n_pad = (p.Tk + 15) & ~15;
+  p.packed = (Tq <= 64 && (H % 2) == 0 && 2 * p.n_pad <= 128) ? 1 : 0;
+  p.QB = p.packed ? 1 : static_cast<int>((Tq + kQ - 1) / kQ);
+  p.KB = p.packed ? 1 : (p.n_pad + 127) / 128;
+  p.head_tiles = p.packed ? p.H / 2 : p.H;
+  p.kv_box = p.packed ? p.n_pad : (p.KB > 1 ? 128 : p.n_pad);
+  p.items = static_cast<long long>(B) * p.head_tiles;
+  p.scale = 1.f / sqrtf(static_cast<float>(hd));
+  p.scale_log2 = 1.4426950408889634f * p.scale;
+  CUtensorMap tmQ, tmdO, tmK, tmV;
+  if (int rc = make_map(&tmQ, q, H * hd, Tq, B, ldq, p.packed ? 64 : kQ)) return rc;
+  if (int rc = make_map(&tmdO, dout, H * hd, Tq, B, lddo, p.packed ? 64 : kQ)) return rc;
+  if (int rc = make_map(&tmK, k, H * hd, Tk, B, ldk, p.kv_box)) return rc;
+  if (int rc = make_map(&tmV, v, H * hd, Tk, B, ldv, p.kv_box)) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+    if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
+    attr = true;
+  }
+  const long long sms = sm_count_cached();
+  const unsigned grid = static_cast<unsigned>(p.items < sms ? p.items : sms);
+  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmdO, tmK, tmV, p);
+  return check_launch("md_attn_bwd_tc");
+}

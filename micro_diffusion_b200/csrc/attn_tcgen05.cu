@@ -17,7 +17,7 @@
 #include "ptx.cuh"
 
 namespace md {
-namespace attn_tc {
+namespace attn_tc0 {
 
 constexpr int kQ = 128;        // queries per CTA (UMMA M)
 constexpr int kHd = 64;        // head_dim == one 128-byte swizzle row of bf16
@@ -233,14 +233,14 @@ static int make_map(CUtensorMap* map, const void* ptr, long long cols, long long
   return 0;
 }
 
-}  // namespace attn_tc
+}  // namespace attn_tc0
 }  // namespace md
 
-extern "C" int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+extern "C" int md_attn_fwd_tc_v0(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                               int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
                               void* stream) {
   using namespace md;
-  using namespace md::attn_tc;
+  using namespace md::attn_tc0;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0) return B == 0 ? 0 : md_set_error(MD_ERR_INVALID, "md_attn_fwd_tc: bad sizes");
   if (hd != kHd || Tk > kMaxKeys || H > 65535 || B > 65535)
     return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_fwd_tc: needs head_dim 64 and Tk <= 256");
@@ -275,7 +275,7 @@ namespace md {
 // 128B-swizzled atoms of 64 keys: that buffer is the K-major A operand of dQ = dS . K and -- the same bytes read with
 // the MN-major descriptor -- the A operand of dV = P^T . dO and dK = dS^T . Q.  delta = rowsum(dO * O) is taken from
 // global memory by the thread that owns the row.  dQ / dK carry the 1/sqrt(hd) factor in their epilogues.
-namespace attn_tc {
+namespace attn_tc0 {
 
 constexpr int kBwdOffdO = kBytesQ;
 constexpr int kBwdOffK = kBwdOffdO + kBytesQ;
@@ -519,15 +519,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-}  // namespace attn_tc
+}  // namespace attn_tc0
 }  // namespace md
 
-extern "C" int md_attn_bwd_tc(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+extern "C" int md_attn_bwd_tc_v0(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
                               const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, void* dq,
                               int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                               int64_t Tq, int64_t Tk, int64_t hd, void* stream) {
   using namespace md;
-  using namespace md::attn_tc;
+  using namespace md::attn_tc0;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0) return B == 0 ? 0 : md_set_error(MD_ERR_INVALID, "md_attn_bwd_tc: bad sizes");
   if (hd != kHd || Tk > kMaxKeys || H > 65535 || B > 65535)
     return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_bwd_tc: needs head_dim 64 and Tk <= 256");

@@ -5,7 +5,7 @@
 // and masked patches carry zero loss weight, model.py:206-209).
 #include <cuda_fp16.h>
 
-#include "common.cuh"
+#include "act.cuh"
 
 namespace md {
 
@@ -29,9 +29,10 @@ __global__ void edm_coef_kernel(const float* __restrict__ rnd, const float* __re
 }
 
 // one thread per (sample, patch, channel, patch-row): p consecutive pixels (coalesced across patches)
+template <typename AT>
 __global__ void edm_prepare_kernel(const void* __restrict__ lat, int lat_f16, const float* __restrict__ eps,
-                                   const float* __restrict__ coef, float* __restrict__ xn,
-                                   __nv_bfloat16* __restrict__ patches, int B, int C, int H, int W, int p) {
+                                   const float* __restrict__ coef, float* __restrict__ xn, AT* __restrict__ patches,
+                                   int B, int C, int H, int W, int p) {
   const int gw = W / p, gh = H / p;
   const long long total = 1LL * B * C * H * gw;  // (b, c, y, patch-col)
   const int Kp = C * p * p;
@@ -48,13 +49,14 @@ __global__ void edm_prepare_kernel(const void* __restrict__ lat, int lat_f16, co
       const long long src = ((1LL * b * C + c) * H + y) * W + pw * p + j;
       const float v = load_lat(lat, lat_f16, src) + sigma * eps[src];
       xn[src] = v;
-      patches[tok * Kp + (c * p + ii) * p + j] = __float2bfloat16_rn(c_in * v);
+      st1a(patches + tok * Kp + (c * p + ii) * p + j, c_in * v);
     }
   }
 }
 
-__global__ void patchify_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                __nv_bfloat16* __restrict__ patches, int B, int C, int H, int W, int p) {
+template <typename AT>
+__global__ void patchify_kernel(const float* __restrict__ x, const float* __restrict__ scale, AT* __restrict__ patches,
+                                int B, int C, int H, int W, int p) {
   const int gw = W / p, gh = H / p;
   const long long total = 1LL * B * C * H * gw;
   const int Kp = C * p * p;
@@ -67,19 +69,18 @@ __global__ void patchify_kernel(const float* __restrict__ x, const float* __rest
     const float sc = scale ? scale[b] : 1.f;
     const long long tok = 1LL * b * gh * gw + 1LL * (y / p) * gw + pw;
     for (int j = 0; j < p; ++j)
-      patches[tok * Kp + (c * p + y % p) * p + j] =
-          __float2bfloat16_rn(sc * x[((1LL * b * C + c) * H + y) * W + pw * p + j]);
+      st1a(patches + tok * Kp + (c * p + y % p) * p + j, sc * x[((1LL * b * C + c) * H + y) * W + pw * p + j]);
   }
 }
 
 // Per-sample masked, weighted MSE.  One block per sample; thread per kept token.
 // ftok column for pixel (c, i, j) of a patch is (i*p + j)*C + c (unpatchify 'nhwpqc->nchpwq').
-template <bool kBackward>
+template <bool kBackward, typename AT>
 __global__ void __launch_bounds__(256)
 edm_loss_kernel(const float* __restrict__ ftok, const int32_t* __restrict__ keep_tok, const void* __restrict__ lat,
                 int lat_f16, const float* __restrict__ xn, const float* __restrict__ coef,
                 float* __restrict__ per_sample, float* __restrict__ loss, const float* __restrict__ gscale,
-                __nv_bfloat16* __restrict__ dftok, int B, int C, int H, int W, int p, int Tk) {
+                AT* __restrict__ dftok, int B, int C, int H, int W, int p, int Tk) {
   const int b = blockIdx.x;
   const int gw = W / p;
   const int T = gw * (H / p);
@@ -100,7 +101,7 @@ edm_loss_kernel(const float* __restrict__ ftok, const int32_t* __restrict__ keep
           const float xv = load_lat(lat, lat_f16, src);
           const float d = c_skip * xn[src] + c_out * f[(ii * p + jj) * C + c] - xv;
           if (kBackward)
-            dftok[(1LL * b * Tk + j) * Nf + (ii * p + jj) * C + c] = __float2bfloat16_rn(gs * d);
+            st1a(dftok + (1LL * b * Tk + j) * Nf + (ii * p + jj) * C + c, gs * d);
           else
             acc += wgt * d * d;
         }
@@ -214,25 +215,25 @@ using namespace md;
 
 extern "C" int md_edm_prepare(const void* lat, int lat_f16, const float* eps, const float* rnd, const float* sigma_in,
                               float p_mean, float p_std, float sigma_data, float* xn, void* patches, float* coef,
-                              int64_t B, int64_t C, int64_t H, int64_t W, int64_t p, void* stream) {
+                              int64_t B, int64_t C, int64_t H, int64_t W, int64_t p, int prec, void* stream) {
   if (B == 0) return 0;
   if (!lat || !eps || (!rnd && !sigma_in) || !xn || !patches || !coef)
     return md_set_error(MD_ERR_INVALID, "md_edm_prepare: null pointer");
   if (p <= 0 || H % p != 0 || W % p != 0) return md_set_error(MD_ERR_INVALID, "md_edm_prepare: H, W must be multiples of p");
   edm_coef_kernel<<<(unsigned)((B + 127) / 128), 128, 0, ST(stream)>>>(rnd, sigma_in, p_mean, p_std, sigma_data, coef,
                                                                       (int)B);
-  edm_prepare_kernel<<<grid_for(B * C * H * (W / p), 256), 256, 0, ST(stream)>>>(
-      lat, lat_f16, eps, coef, xn, reinterpret_cast<__nv_bfloat16*>(patches), (int)B, (int)C, (int)H, (int)W, (int)p);
+  MD_WITH_ACT(prec, edm_prepare_kernel<AT><<<grid_for(B * C * H * (W / p), 256), 256, 0, ST(stream)>>>(
+                        lat, lat_f16, eps, coef, xn, AP(AT, patches), (int)B, (int)C, (int)H, (int)W, (int)p));
   return check_launch("md_edm_prepare");
 }
 
 extern "C" int md_patchify(const float* x, const float* scale, void* patches, int64_t B, int64_t C, int64_t H,
-                           int64_t W, int64_t p, void* stream) {
+                           int64_t W, int64_t p, int prec, void* stream) {
   if (B == 0) return 0;
   if (!x || !patches) return md_set_error(MD_ERR_INVALID, "md_patchify: null pointer");
   if (p <= 0 || H % p != 0 || W % p != 0) return md_set_error(MD_ERR_INVALID, "md_patchify: H, W must be multiples of p");
-  patchify_kernel<<<grid_for(B * C * H * (W / p), 256), 256, 0, ST(stream)>>>(
-      x, scale, reinterpret_cast<__nv_bfloat16*>(patches), (int)B, (int)C, (int)H, (int)W, (int)p);
+  MD_WITH_ACT(prec, patchify_kernel<AT><<<grid_for(B * C * H * (W / p), 256), 256, 0, ST(stream)>>>(
+                        x, scale, AP(AT, patches), (int)B, (int)C, (int)H, (int)W, (int)p));
   return check_launch("md_patchify");
 }
 
@@ -242,21 +243,21 @@ extern "C" int md_edm_loss_fwd(const float* ftok, const int32_t* keep_tok, const
   if (B == 0) return 0;
   if (!ftok || !lat || !xn || !coef || !per_sample || !loss)
     return md_set_error(MD_ERR_INVALID, "md_edm_loss_fwd: null pointer");
-  edm_loss_kernel<false><<<(unsigned)B, 256, 0, ST(stream)>>>(ftok, keep_tok, lat, lat_f16, xn, coef, per_sample, loss,
-                                                              nullptr, nullptr, (int)B, (int)C, (int)H, (int)W, (int)p,
-                                                              (int)Tk);
+  edm_loss_kernel<false, float><<<(unsigned)B, 256, 0, ST(stream)>>>(ftok, keep_tok, lat, lat_f16, xn, coef, per_sample,
+                                                                     loss, nullptr, nullptr, (int)B, (int)C, (int)H,
+                                                                     (int)W, (int)p, (int)Tk);
   return check_launch("md_edm_loss_fwd");
 }
 
 extern "C" int md_edm_loss_bwd(const float* ftok, const int32_t* keep_tok, const void* lat, int lat_f16,
                                const float* xn, const float* coef, const float* gscale, void* dftok, int64_t B,
-                               int64_t C, int64_t H, int64_t W, int64_t p, int64_t Tk, void* stream) {
+                               int64_t C, int64_t H, int64_t W, int64_t p, int64_t Tk, int prec, void* stream) {
   if (B == 0) return 0;
   if (!ftok || !lat || !xn || !coef || !gscale || !dftok)
     return md_set_error(MD_ERR_INVALID, "md_edm_loss_bwd: null pointer");
-  edm_loss_kernel<true><<<(unsigned)B, 256, 0, ST(stream)>>>(ftok, keep_tok, lat, lat_f16, xn, coef, nullptr, nullptr,
-                                                             gscale, reinterpret_cast<__nv_bfloat16*>(dftok), (int)B,
-                                                             (int)C, (int)H, (int)W, (int)p, (int)Tk);
+  MD_WITH_ACT(prec, edm_loss_kernel<true, AT><<<(unsigned)B, 256, 0, ST(stream)>>>(
+                        ftok, keep_tok, lat, lat_f16, xn, coef, nullptr, nullptr, gscale, AP(AT, dftok), (int)B, (int)C,
+                        (int)H, (int)W, (int)p, (int)Tk));
   return check_launch("md_edm_loss_bwd");
 }
 

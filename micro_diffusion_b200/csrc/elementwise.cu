@@ -4,7 +4,7 @@
 // 16-byte vector accesses, grids sized as multiples of the SM count with grid-stride loops.
 #include <cuda_fp16.h>
 
-#include "common.cuh"
+#include "act.cuh"
 
 namespace md {
 
@@ -34,32 +34,33 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------ SwiGLU
-__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h, long long rows,
-                                  int f) {
+template <typename AT>
+__global__ void swiglu_fwd_kernel(const AT* __restrict__ u, AT* __restrict__ h, long long rows, int f) {
   const int fv = f >> 3;
   const long long total = rows * fv;
   for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
     const long long r = i / fv;
     const int c = static_cast<int>(i % fv) * 8;
     float a[8], b[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(u + r * 2 * f + c), a);
-    unpack8(*reinterpret_cast<const uint4*>(u + r * 2 * f + f + c), b);
+    ld8(u + r * 2 * f + c, a);
+    ld8(u + r * 2 * f + f + c, b);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = silu_f(a[e]) * b[e];
-    *reinterpret_cast<uint4*>(h + r * f + c) = pack8(o);
+    st8(h + r * f + c, o);
   }
 }
-__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ u,
-                                  __nv_bfloat16* __restrict__ du, long long rows, int f) {
+template <typename AT>
+__global__ void swiglu_bwd_kernel(const AT* __restrict__ dh, const AT* __restrict__ u, AT* __restrict__ du, long long rows,
+                                  int f) {
   const int fv = f >> 3;
   const long long total = rows * fv;
   for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
     const long long r = i / fv;
     const int c = static_cast<int>(i % fv) * 8;
     float a[8], b[8], d[8], da[8], db[8];
-    unpack8(*reinterpret_cast<const uint4*>(u + r * 2 * f + c), a);
-    unpack8(*reinterpret_cast<const uint4*>(u + r * 2 * f + f + c), b);
-    unpack8(*reinterpret_cast<const uint4*>(dh + r * f + c), d);
+    ld8(u + r * 2 * f + c, a);
+    ld8(u + r * 2 * f + f + c, b);
+    ld8(dh + r * f + c, d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float sg = 1.f / (1.f + __expf(-a[e]));
@@ -67,38 +68,40 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __
       da[e] = d[e] * b[e] * (sg * (1.f + a[e] * (1.f - sg)));
       db[e] = d[e] * sl;
     }
-    *reinterpret_cast<uint4*>(du + r * 2 * f + c) = pack8(da);
-    *reinterpret_cast<uint4*>(du + r * 2 * f + f + c) = pack8(db);
+    st8(du + r * 2 * f + c, da);
+    st8(du + r * 2 * f + f + c, db);
   }
 }
 
 // ---------------------------------------------------------------------------------------- act fwd
-__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ out, long long nvec,
-                               int act) {
+template <typename AT>
+__global__ void act_fwd_kernel(const AT* __restrict__ pre, AT* __restrict__ out, long long nvec, int act) {
   for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 1LL * gridDim.x * blockDim.x) {
     float x[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(pre + 8 * i), x);
+    ld8(pre + 8 * i, x);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = act ? gelu_tanh_f(x[e]) : gelu_erf_f(x[e]);
-    *reinterpret_cast<uint4*>(out + 8 * i) = pack8(o);
+    st8(out + 8 * i, o);
   }
 }
 
 // ---------------------------------------------------------------------------------------- act bwd
-__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const __nv_bfloat16* __restrict__ pre,
-                               __nv_bfloat16* __restrict__ dpre, long long nvec, int act) {
+template <typename AT>
+__global__ void act_bwd_kernel(const AT* __restrict__ dact, const AT* __restrict__ pre, AT* __restrict__ dpre,
+                               long long nvec, int act) {
   for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 1LL * gridDim.x * blockDim.x) {
     float d[8], x[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(dact + 8 * i), d);
-    unpack8(*reinterpret_cast<const uint4*>(pre + 8 * i), x);
+    ld8(dact + 8 * i, d);
+    ld8(pre + 8 * i, x);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = d[e] * (act ? gelu_tanh_grad_f(x[e]) : gelu_erf_grad_f(x[e]));
-    *reinterpret_cast<uint4*>(dpre + 8 * i) = pack8(o);
+    st8(dpre + 8 * i, o);
   }
 }
-__global__ void gelu_tanh_f32_fwd_kernel(const float* __restrict__ c, __nv_bfloat16* __restrict__ out, long long n) {
+template <typename AT>
+__global__ void gelu_tanh_f32_fwd_kernel(const float* __restrict__ c, AT* __restrict__ out, long long n) {
   for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16_rn(gelu_tanh_f(c[i]));
+    st1a(out + i, gelu_tanh_f(c[i]));
 }
 __global__ void gelu_tanh_f32_bwd_kernel(const float* __restrict__ dact, const float* __restrict__ c,
                                          float* __restrict__ dc, int accumulate, long long n) {
@@ -109,13 +112,14 @@ __global__ void gelu_tanh_f32_bwd_kernel(const float* __restrict__ dact, const f
 }
 
 // -------------------------------------------------------------------------------------- token mean
-__global__ void mean_tokens_fwd_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int L, int D) {
+template <typename AT>
+__global__ void mean_tokens_fwd_kernel(const float* __restrict__ x, AT* __restrict__ out, int L, int D) {
   const long long b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   float s = 0.f;
   for (int l = 0; l < L; ++l) s += x[(b * L + l) * D + c];
-  out[b * D + c] = __float2bfloat16_rn(s / L);
+  st1a(out + b * D + c, s / L);
 }
 __global__ void mean_tokens_bwd_kernel(const float* __restrict__ d, float* __restrict__ dx, int L, int D) {
   const long long b = blockIdx.y;
@@ -141,6 +145,10 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
   }
 }
 
+__global__ void copy_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) y[i] = x[i];
+}
+
 // ------------------------------------------------------------------------------------------ colsum
 // grid (ceil(N/256), ceil(rows/256)): each thread owns one column of a 256-row slab.
 __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, float* __restrict__ out,
@@ -162,9 +170,10 @@ __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long 
 // ---------------------------------------------------------------------------------- cast_transpose
 // 64x64 tiles, 256 threads: 16-byte fp32 loads, 8-byte bf16 stores in both orientations (the transposed one through
 // a padded smem tile).  HBM-bound: 4 B read + 2 x 2 B written per element.
+template <typename AT>
 __global__ void __launch_bounds__(256)
-cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wbt,
-                      long long rows, long long cols) {
+cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __restrict__ wbt, long long rows,
+                      long long cols) {
   __shared__ float tile[64][65];
   const long long bz = blockIdx.z;
   const float* wsrc = w + bz * rows * cols;
@@ -179,18 +188,12 @@ cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w
       if (vec && c + 3 < cols) {
         const float4 f = *reinterpret_cast<const float4*>(wsrc + r * cols + c);
         v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-        if (wb) {
-          __nv_bfloat162 a = __floats2bfloat162_rn(f.x, f.y), b2 = __floats2bfloat162_rn(f.z, f.w);
-          uint2 raw;
-          raw.x = *reinterpret_cast<uint32_t*>(&a);
-          raw.y = *reinterpret_cast<uint32_t*>(&b2);
-          *reinterpret_cast<uint2*>(wb + bz * rows * cols + r * cols + c) = raw;
-        }
+        if (wb) st4a(wb + bz * rows * cols + r * cols + c, f);
       } else {
         for (int e = 0; e < 4; ++e)
           if (c + e < cols) {
             v[e] = wsrc[r * cols + c + e];
-            if (wb) wb[bz * rows * cols + r * cols + c + e] = __float2bfloat16_rn(v[e]);
+            if (wb) st1a(wb + bz * rows * cols + r * cols + c + e, v[e]);
           }
       }
     }
@@ -207,36 +210,34 @@ cast_transpose_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[e] = tile[4 * tx + e][ty + 16 * pass];
-    __nv_bfloat16* dst = wbt + bz * rows * cols + c * rows + r;
+    AT* dst = wbt + bz * rows * cols + c * rows + r;
     if (vec && r + 3 < rows) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b2 = __floats2bfloat162_rn(v[2], v[3]);
-      uint2 raw;
-      raw.x = *reinterpret_cast<uint32_t*>(&a);
-      raw.y = *reinterpret_cast<uint32_t*>(&b2);
-      *reinterpret_cast<uint2*>(dst) = raw;
+      st4a(dst, make_float4(v[0], v[1], v[2], v[3]));
     } else {
       for (int e = 0; e < 4; ++e)
-        if (r + e < rows) dst[e] = __float2bfloat16_rn(v[e]);
+        if (r + e < rows) st1a(dst + e, v[e]);
     }
   }
 }
 
 // -------------------------------------------------------------------------------- timestep / cond
-__global__ void timestep_embed_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int dim) {
+template <typename AT>
+__global__ void timestep_embed_kernel(const float* __restrict__ t, AT* __restrict__ out, int dim) {
   const long long b = blockIdx.x;
   const int half = dim / 2;
   const float tv = t[b];
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float freq = expf(-9.210340371976184f * static_cast<float>(i) / static_cast<float>(half));
     const float a = tv * freq;
-    out[b * dim + i] = __float2bfloat16_rn(cosf(a));
-    out[b * dim + half + i] = __float2bfloat16_rn(sinf(a));
+    st1a(out + b * dim + i, cosf(a));
+    st1a(out + b * dim + half + i, sinf(a));
   }
-  if ((dim & 1) && threadIdx.x == 0) out[b * dim + dim - 1] = __float2bfloat16_rn(0.f);
+  if ((dim & 1) && threadIdx.x == 0) st1a(out + b * dim + dim - 1, 0.f);
 }
 
-__global__ void cond_prepare_kernel(const __half* cap, const double* __restrict__ keep,
-                                    __nv_bfloat16* __restrict__ out, __half* cap_out, long long per_sample) {
+template <typename AT>
+__global__ void cond_prepare_kernel(const __half* cap, const double* __restrict__ keep, AT* __restrict__ out,
+                                    __half* cap_out, long long per_sample) {
   const long long b = blockIdx.y;
   const float k = keep ? static_cast<float>(keep[b]) : 1.f;
   const long long nv = per_sample >> 3;
@@ -255,7 +256,7 @@ __global__ void cond_prepare_kernel(const __half* cap, const double* __restrict_
       o[2 * e] = f.x;
       o[2 * e + 1] = f.y;
     }
-    *reinterpret_cast<uint4*>(out + b * per_sample + 8 * i) = pack8(o);
+    st8(out + b * per_sample + 8 * i, o);
     if (cap_out) *reinterpret_cast<uint4*>(cap_out + b * per_sample + 8 * i) = masked;
   }
 }
@@ -337,34 +338,34 @@ using namespace md;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
-extern "C" int md_swiglu_fwd(const void* u, void* h, int64_t rows, int64_t f, void* stream) {
+extern "C" int md_swiglu_fwd(const void* u, void* h, int64_t rows, int64_t f, int prec, void* stream) {
   if (rows == 0) return 0;
   if (!u || !h || f % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_swiglu_fwd: null pointer or f % 8 != 0");
-  swiglu_fwd_kernel<<<grid_for(rows * (f / 8), 256), 256, 0, ST(stream)>>>(CBF(u), BF(h), rows, (int)f);
+  MD_WITH_ACT(prec, swiglu_fwd_kernel<AT><<<grid_for(rows * (f / 8), 256), 256, 0, ST(stream)>>>(CAP(AT, u), AP(AT, h), rows, (int)f));
   return check_launch("md_swiglu_fwd");
 }
-extern "C" int md_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int64_t f, void* stream) {
+extern "C" int md_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int64_t f, int prec, void* stream) {
   if (rows == 0) return 0;
   if (!dh || !u || !du || f % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_swiglu_bwd: null pointer or f % 8 != 0");
-  swiglu_bwd_kernel<<<grid_for(rows * (f / 8), 256), 256, 0, ST(stream)>>>(CBF(dh), CBF(u), BF(du), rows, (int)f);
+  MD_WITH_ACT(prec, swiglu_bwd_kernel<AT><<<grid_for(rows * (f / 8), 256), 256, 0, ST(stream)>>>(CAP(AT, dh), CAP(AT, u), AP(AT, du), rows, (int)f));
   return check_launch("md_swiglu_bwd");
 }
-extern "C" int md_act_fwd(const void* pre, void* out, int64_t n, int act, void* stream) {
+extern "C" int md_act_fwd(const void* pre, void* out, int64_t n, int act, int prec, void* stream) {
   if (n == 0) return 0;
   if (!pre || !out || n % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_act_fwd: null pointer or n % 8 != 0");
-  act_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>(CBF(pre), BF(out), n / 8, act);
+  MD_WITH_ACT(prec, act_fwd_kernel<AT><<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>(CAP(AT, pre), AP(AT, out), n / 8, act));
   return check_launch("md_act_fwd");
 }
-extern "C" int md_act_bwd(const void* dact, const void* pre, void* dpre, int64_t n, int act, void* stream) {
+extern "C" int md_act_bwd(const void* dact, const void* pre, void* dpre, int64_t n, int act, int prec, void* stream) {
   if (n == 0) return 0;
   if (!dact || !pre || !dpre || n % 8 != 0) return md_set_error(MD_ERR_INVALID, "md_act_bwd: null pointer or n % 8 != 0");
-  act_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>(CBF(dact), CBF(pre), BF(dpre), n / 8, act);
+  MD_WITH_ACT(prec, act_bwd_kernel<AT><<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>(CAP(AT, dact), CAP(AT, pre), AP(AT, dpre), n / 8, act));
   return check_launch("md_act_bwd");
 }
-extern "C" int md_gelu_tanh_f32_fwd(const float* c, void* out, int64_t n, void* stream) {
+extern "C" int md_gelu_tanh_f32_fwd(const float* c, void* out, int64_t n, int prec, void* stream) {
   if (n == 0) return 0;
   if (!c || !out) return md_set_error(MD_ERR_INVALID, "md_gelu_tanh_f32_fwd: null pointer");
-  gelu_tanh_f32_fwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(c, BF(out), n);
+  MD_WITH_ACT(prec, gelu_tanh_f32_fwd_kernel<AT><<<grid_for(n, 256), 256, 0, ST(stream)>>>(c, AP(AT, out), n));
   return check_launch("md_gelu_tanh_f32_fwd");
 }
 extern "C" int md_gelu_tanh_f32_bwd(const float* dact, const float* c, float* dc, int accumulate, int64_t n,
@@ -374,11 +375,11 @@ extern "C" int md_gelu_tanh_f32_bwd(const float* dact, const float* c, float* dc
   gelu_tanh_f32_bwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(dact, c, dc, accumulate, n);
   return check_launch("md_gelu_tanh_f32_bwd");
 }
-extern "C" int md_mean_tokens_fwd(const float* x, void* out, int64_t B, int64_t L, int64_t D, void* stream) {
+extern "C" int md_mean_tokens_fwd(const float* x, void* out, int64_t B, int64_t L, int64_t D, int prec, void* stream) {
   if (B == 0) return 0;
   if (!x || !out) return md_set_error(MD_ERR_INVALID, "md_mean_tokens_fwd: null pointer");
   dim3 grid((unsigned)((D + 127) / 128), (unsigned)B);
-  mean_tokens_fwd_kernel<<<grid, 128, 0, ST(stream)>>>(x, BF(out), (int)L, (int)D);
+  MD_WITH_ACT(prec, mean_tokens_fwd_kernel<AT><<<grid, 128, 0, ST(stream)>>>(x, AP(AT, out), (int)L, (int)D));
   return check_launch("md_mean_tokens_fwd");
 }
 extern "C" int md_mean_tokens_bwd(const float* d, float* dx, int64_t B, int64_t L, int64_t D, void* stream) {
@@ -388,10 +389,11 @@ extern "C" int md_mean_tokens_bwd(const float* d, float* dx, int64_t B, int64_t 
   mean_tokens_bwd_kernel<<<grid, 128, 0, ST(stream)>>>(d, dx, (int)L, (int)D);
   return check_launch("md_mean_tokens_bwd");
 }
-extern "C" int md_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+extern "C" int md_cast_f32_bf16(const float* x, void* y, int64_t n, int prec, void* stream) {
   if (n == 0) return 0;
   if (!x || !y) return md_set_error(MD_ERR_INVALID, "md_cast_f32_bf16: null pointer");
-  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(x, BF(y), n);
+  if (prec) copy_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, reinterpret_cast<float*>(y), n);
+  else cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(x, BF(y), n);
   return check_launch("md_cast_f32_bf16");
 }
 extern "C" int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int64_t rows, int64_t N, void* stream) {
@@ -402,27 +404,28 @@ extern "C" int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int6
   return check_launch("md_colsum");
 }
 extern "C" int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch, int64_t rows, int64_t cols,
-                                 void* stream) {
+                                 int prec, void* stream) {
   if (batch * rows * cols == 0) return 0;
   if (!w) return md_set_error(MD_ERR_INVALID, "md_cast_transpose: null pointer");
   dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64), (unsigned)batch);
-  cast_transpose_kernel<<<grid, 256, 0, ST(stream)>>>(w, BF(wb), BF(wbt), rows, cols);
+  MD_WITH_ACT(prec, cast_transpose_kernel<AT><<<grid, 256, 0, ST(stream)>>>(w, AP(AT, wb), AP(AT, wbt), rows, cols));
   return check_launch("md_cast_transpose");
 }
-extern "C" int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, void* stream) {
+extern "C" int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, int prec, void* stream) {
   if (B == 0) return 0;
   if (!t || !out) return md_set_error(MD_ERR_INVALID, "md_timestep_embed: null pointer");
-  timestep_embed_kernel<<<(unsigned)B, 128, 0, ST(stream)>>>(t, BF(out), (int)dim);
+  MD_WITH_ACT(prec, timestep_embed_kernel<AT><<<(unsigned)B, 128, 0, ST(stream)>>>(t, AP(AT, out), (int)dim));
   return check_launch("md_timestep_embed");
 }
 extern "C" int md_cond_prepare(const void* cap_f16, const double* keep, void* out_bf16, void* cap_out_f16, int64_t B,
-                               int64_t per_sample, void* stream) {
+                               int64_t per_sample, int prec, void* stream) {
   if (B == 0) return 0;
   if (!cap_f16 || !out_bf16 || per_sample % 8 != 0)
     return md_set_error(MD_ERR_INVALID, "md_cond_prepare: null pointer or per_sample % 8 != 0");
   dim3 grid((unsigned)min((long long)((per_sample / 8 + 255) / 256), 64LL), (unsigned)B);
-  cond_prepare_kernel<<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(cap_f16), keep, BF(out_bf16),
-                                                    reinterpret_cast<__half*>(cap_out_f16), per_sample);
+  MD_WITH_ACT(prec, cond_prepare_kernel<AT><<<grid, 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(cap_f16), keep,
+                                                                          AP(AT, out_bf16),
+                                                                          reinterpret_cast<__half*>(cap_out_f16), per_sample));
   return check_launch("md_cond_prepare");
 }
 extern "C" int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream) {

@@ -3,7 +3,7 @@
 // fused with the gated residual, and the matching backward pieces.  The reference materialises a
 // one-hot (n,e,k,t) tensor and contracts with it (dit.py:133-134,140); here dispatch and combine are
 // index gathers (deterministic: an inverse slot table replaces scatter-add atomics).
-#include "common.cuh"
+#include "act.cuh"
 
 namespace md {
 
@@ -28,9 +28,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // ---------------------------------------------------------------------------------------- gate fwd
 // warp per row; gate weights staged in shared memory (E*D fp32 <= 64 KB).
+template <typename AT>
 __global__ void __launch_bounds__(256)
-moe_gate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wg, float* __restrict__ probs,
-                    long long rows, int D, int E) {
+moe_gate_fwd_kernel(const AT* __restrict__ x, const float* __restrict__ wg, float* __restrict__ probs, long long rows,
+                    int D, int E) {
   extern __shared__ float swg[];  // [E][D]
   for (int i = threadIdx.x; i < E * D; i += blockDim.x) swg[i] = wg[i];
   __syncthreads();
@@ -41,18 +42,18 @@ moe_gate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 #pragma unroll
     for (int e = 0; e < kMaxE; ++e) acc[e] = 0.f;
     for (int base = 0; base < nvec; base += 32 * kChunk) {
-      uint4 raw[kChunk];
+      V8<AT> raw[kChunk];
 #pragma unroll
       for (int j = 0; j < kChunk; ++j) {  // all loads of this slab first
         const int i = base + lane + 32 * j;
-        raw[j] = i < nvec ? *reinterpret_cast<const uint4*>(x + row * D + 8 * i) : make_uint4(0, 0, 0, 0);
+        raw[j] = i < nvec ? ldv8(x + row * D + 8 * i) : zerov8<AT>();
       }
 #pragma unroll
       for (int j = 0; j < kChunk; ++j) {
         const int i = base + lane + 32 * j;
         if (i < nvec) {
           float xv[8];
-          unpack8(raw[j], xv);
+          unpackv8(raw[j], xv);
 #pragma unroll
           for (int e = 0; e < kMaxE; ++e) {
             if (e < E) {
@@ -134,9 +135,10 @@ moe_topk_kernel(const float* __restrict__ probs, int32_t* __restrict__ idx, floa
 
 // ------------------------------------------------------------------------------------------ gather
 // warp per slot: xin[e][b*k + j][:] = x[b*T + idx[b,e,j]][:]
+template <typename AT>
 __global__ void __launch_bounds__(256)
-moe_gather_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ xin,
-                  int B, int T, int E, int k, int D) {
+moe_gather_kernel(const AT* __restrict__ x, const int32_t* __restrict__ idx, AT* __restrict__ xin, int B, int T, int E,
+                  int k, int D) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long slots = 1LL * B * E * k;
   const int nvec = D >> 3;
@@ -145,21 +147,23 @@ moe_gather_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict
     const int e = static_cast<int>((s / k) % E);
     const long long b = s / (1LL * k * E);
     const int tok = idx[s];  // idx is [B,E,k] == s ordering
-    const __nv_bfloat16* src = x + (b * T + tok) * D;
-    __nv_bfloat16* dst = xin + ((1LL * e * B + b) * k + j) * D;
-    for (int i = lane; i < nvec; i += 32)
-      *reinterpret_cast<uint4*>(dst + 8 * i) = *reinterpret_cast<const uint4*>(src + 8 * i);
+    const AT* src = x + (b * T + tok) * D;
+    AT* dst = xin + ((1LL * e * B + b) * k + j) * D;
+    for (int i = lane; i < nvec; i += 32) {
+      float v[8];
+      ld8(src + 8 * i, v);
+      st8(dst + 8 * i, v);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------- combine fwd
 // warp per token: ymoe = sum_e g*h2[slot]; xout = xres + gate*ymoe
-template <int ME>
+template <int ME, typename AT>
 __global__ void __launch_bounds__(256)
-moe_combine_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __restrict__ gval,
-                       const int32_t* __restrict__ inv, const float* __restrict__ xres, const float* __restrict__ gate,
-                       long long ldmod, float* __restrict__ xout, __nv_bfloat16* __restrict__ ymoe, int B, int T, int E,
-                       int k, int D) {
+moe_combine_fwd_kernel(const AT* __restrict__ h2, const float* __restrict__ gval, const int32_t* __restrict__ inv,
+                       const float* __restrict__ xres, const float* __restrict__ gate, long long ldmod,
+                       float* __restrict__ xout, AT* __restrict__ ymoe, int B, int T, int E, int k, int D) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long rows = 1LL * B * T;
   const int nvec = D >> 3;
@@ -181,21 +185,20 @@ moe_combine_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __rest
       float acc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-      uint4 raw[ME];
+      V8<AT> raw[ME];
 #pragma unroll
       for (int e = 0; e < ME; ++e)  // every selected expert's row chunk in flight before the first use
-        if (e < E && slot[e] >= 0)
-          raw[e] = *reinterpret_cast<const uint4*>(h2 + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i);
+        if (e < E && slot[e] >= 0) raw[e] = ldv8(h2 + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i);
 #pragma unroll
       for (int e = 0; e < ME; ++e) {
         if (e < E && slot[e] >= 0) {
           float hv[8];
-          unpack8(raw[e], hv);
+          unpackv8(raw[e], hv);
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc[q] += g[e] * hv[q];
         }
       }
-      if (ymoe) *reinterpret_cast<uint4*>(ymoe + row * D + 8 * i) = pack8(acc);
+      if (ymoe) st8(ymoe + row * D + 8 * i, acc);
       if (xout) {
 #pragma unroll
         for (int q = 0; q < 8; q += 4) {
@@ -212,10 +215,11 @@ moe_combine_fwd_kernel(const __nv_bfloat16* __restrict__ h2, const float* __rest
 
 // ------------------------------------------------------------------------------------- combine bwd
 // warp per slot: dh2 = g * dy[token]; dgval = <h2, dy[token]>
+template <typename AT>
 __global__ void __launch_bounds__(256)
-moe_combine_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h2,
-                       const float* __restrict__ gval, const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ dh2,
-                       float* __restrict__ dgval, int B, int T, int E, int k, int D) {
+moe_combine_bwd_kernel(const AT* __restrict__ dy, const AT* __restrict__ h2, const float* __restrict__ gval,
+                       const int32_t* __restrict__ idx, AT* __restrict__ dh2, float* __restrict__ dgval, int B, int T,
+                       int E, int k, int D) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long slots = 1LL * B * E * k;
   const int nvec = D >> 3;
@@ -225,19 +229,19 @@ moe_combine_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
     const long long b = s / (1LL * k * E);
     const int tok = idx[s];
     const float g = gval[s];
-    const __nv_bfloat16* dyr = dy + (b * T + tok) * D;
+    const AT* dyr = dy + (b * T + tok) * D;
     const long long hrow = ((1LL * e * B + b) * k + j) * D;
     float dot = 0.f;
     for (int i = lane; i < nvec; i += 32) {
       float dv[8], hv[8], o[8];
-      unpack8(*reinterpret_cast<const uint4*>(dyr + 8 * i), dv);
-      unpack8(*reinterpret_cast<const uint4*>(h2 + hrow + 8 * i), hv);
+      ld8(dyr + 8 * i, dv);
+      ld8(h2 + hrow + 8 * i, hv);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         dot += dv[q] * hv[q];
         o[q] = g * dv[q];
       }
-      *reinterpret_cast<uint4*>(dh2 + hrow + 8 * i) = pack8(o);
+      st8(dh2 + hrow + 8 * i, o);
     }
     dot = warp_sum(dot);
     if (lane == 0) dgval[s] = dot;
@@ -247,11 +251,11 @@ moe_combine_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
 // ------------------------------------------------------------------------------------------ dx bwd
 // warp per token: dscores (softmax backward of the selected gate values) and
 // dx = sum_e dxin[slot] + dscores . Wg
-template <int ME>
+template <int ME, typename AT>
 __global__ void __launch_bounds__(256)
-moe_dx_bwd_kernel(const __nv_bfloat16* __restrict__ dxin, const int32_t* __restrict__ inv,
-                  const float* __restrict__ dgval, const float* __restrict__ probs, const float* __restrict__ wg,
-                  float* __restrict__ dscores, __nv_bfloat16* __restrict__ dx, int B, int T, int E, int k, int D) {
+moe_dx_bwd_kernel(const AT* __restrict__ dxin, const int32_t* __restrict__ inv, const float* __restrict__ dgval,
+                  const float* __restrict__ probs, const float* __restrict__ wg, float* __restrict__ dscores,
+                  AT* __restrict__ dx, int B, int T, int E, int k, int D) {
   extern __shared__ float swg[];  // [E][D]
   for (int i = threadIdx.x; i < E * D; i += blockDim.x) swg[i] = wg[i];
   __syncthreads();
@@ -287,11 +291,10 @@ moe_dx_bwd_kernel(const __nv_bfloat16* __restrict__ dxin, const int32_t* __restr
       float acc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-      uint4 raw[ME];
+      V8<AT> raw[ME];
 #pragma unroll
       for (int e = 0; e < ME; ++e)
-        if (e < E && slot[e] >= 0)
-          raw[e] = *reinterpret_cast<const uint4*>(dxin + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i);
+        if (e < E && slot[e] >= 0) raw[e] = ldv8(dxin + ((1LL * e * B + b) * k + slot[e]) * D + 8 * i);
 #pragma unroll
       for (int e = 0; e < ME; ++e) {
         if (e < E) {
@@ -301,21 +304,22 @@ moe_dx_bwd_kernel(const __nv_bfloat16* __restrict__ dxin, const int32_t* __restr
           acc[4] += ds[e] * w1.x; acc[5] += ds[e] * w1.y; acc[6] += ds[e] * w1.z; acc[7] += ds[e] * w1.w;
           if (slot[e] >= 0) {
             float dv[8];
-            unpack8(raw[e], dv);
+            unpackv8(raw[e], dv);
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[q] += dv[q];
           }
         }
       }
-      *reinterpret_cast<uint4*>(dx + row * D + 8 * i) = pack8(acc);
+      st8(dx + row * D + 8 * i, acc);
     }
   }
 }
 
 // -------------------------------------------------------------------------------------- gate wgrad
 // block = 256 threads, slab of 128 rows; thread owns columns c, c+256, ... ; dwg[e][c] += sum_r ds[r][e]*x[r][c]
+template <typename AT>
 __global__ void __launch_bounds__(256)
-moe_gate_wgrad_kernel(const float* __restrict__ dscores, const __nv_bfloat16* __restrict__ x, float* __restrict__ dwg,
+moe_gate_wgrad_kernel(const float* __restrict__ dscores, const AT* __restrict__ x, float* __restrict__ dwg,
                       long long rows, int D, int E) {
   __shared__ float sds[128 * kMaxE];
   const long long r0 = 1LL * blockIdx.x * 128;
@@ -329,7 +333,7 @@ moe_gate_wgrad_kernel(const float* __restrict__ dscores, const __nv_bfloat16* __
     for (int r = 0; r < nr; r += 8) {
       float xv[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) xv[u] = (r + u < nr) ? __bfloat162float(x[(r0 + r + u) * D + c]) : 0.f;
+      for (int u = 0; u < 8; ++u) xv[u] = (r + u < nr) ? ld1a(x + (r0 + r + u) * D + c) : 0.f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         if (r + u < nr) {
@@ -368,7 +372,7 @@ using namespace md;
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
 extern "C" int md_moe_gate_fwd(const void* x, const float* wg, float* probs, int64_t rows, int64_t D, int64_t E,
-                               void* stream) {
+                               int prec, void* stream) {
   if (int rc = check_moe("md_moe_gate_fwd", D, E)) return rc;
   if (rows == 0) return 0;
   if (!x || !wg || !probs) return md_set_error(MD_ERR_INVALID, "md_moe_gate_fwd: null pointer");
@@ -376,10 +380,11 @@ extern "C" int md_moe_gate_fwd(const void* x, const float* wg, float* probs, int
   if (smem > 200 * 1024) return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_gate_fwd: E*D too large for shared memory");
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(moe_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_gate_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_gate_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  moe_gate_fwd_kernel<<<warp_grid(rows), 256, smem, ST(stream)>>>(CBF(x), wg, probs, rows, (int)D, (int)E);
+  MD_WITH_ACT(prec, moe_gate_fwd_kernel<AT><<<warp_grid(rows), 256, smem, ST(stream)>>>(CAP(AT, x), wg, probs, rows, (int)D, (int)E));
   return check_launch("md_moe_gate_fwd");
 }
 
@@ -398,44 +403,45 @@ extern "C" int md_moe_topk(const float* probs, int32_t* idx, float* gval, int32_
 }
 
 extern "C" int md_moe_gather(const void* x, const int32_t* idx, void* xin, int64_t B, int64_t T, int64_t E, int64_t k,
-                             int64_t D, void* stream) {
+                             int64_t D, int prec, void* stream) {
   if (int rc = check_moe("md_moe_gather", D, E)) return rc;
   if (B * k == 0) return 0;
   if (!x || !idx || !xin) return md_set_error(MD_ERR_INVALID, "md_moe_gather: null pointer");
-  moe_gather_kernel<<<warp_grid(B * E * k), 256, 0, ST(stream)>>>(CBF(x), idx, BF(xin), (int)B, (int)T, (int)E, (int)k,
-                                                                  (int)D);
+  MD_WITH_ACT(prec, moe_gather_kernel<AT><<<warp_grid(B * E * k), 256, 0, ST(stream)>>>(CAP(AT, x), idx, AP(AT, xin), (int)B,
+                                                                                        (int)T, (int)E, (int)k, (int)D));
   return check_launch("md_moe_gather");
 }
 
 extern "C" int md_moe_combine_fwd(const void* h2, const float* gval, const int32_t* inv, const float* xres,
                                   const float* gate, int64_t ldmod, float* xout, void* ymoe, int64_t B, int64_t T,
-                                  int64_t E, int64_t k, int64_t D, void* stream) {
+                                  int64_t E, int64_t k, int64_t D, int prec, void* stream) {
   if (int rc = check_moe("md_moe_combine_fwd", D, E)) return rc;
   if (B * T == 0) return 0;
   if (!h2 || !gval || !inv || (xout && !xres)) return md_set_error(MD_ERR_INVALID, "md_moe_combine_fwd: null pointer");
   if (E <= 8)
-    moe_combine_fwd_kernel<8><<<warp_grid(B * T), 256, 0, ST(stream)>>>(CBF(h2), gval, inv, xres, gate, ldmod, xout,
-                                                                        BF(ymoe), (int)B, (int)T, (int)E, (int)k, (int)D);
+    MD_WITH_ACT(prec, moe_combine_fwd_kernel<8, AT><<<warp_grid(B * T), 256, 0, ST(stream)>>>(
+                          CAP(AT, h2), gval, inv, xres, gate, ldmod, xout, AP(AT, ymoe), (int)B, (int)T, (int)E, (int)k, (int)D));
   else
-    moe_combine_fwd_kernel<16><<<warp_grid(B * T), 256, 0, ST(stream)>>>(CBF(h2), gval, inv, xres, gate, ldmod, xout,
-                                                                         BF(ymoe), (int)B, (int)T, (int)E, (int)k, (int)D);
+    MD_WITH_ACT(prec, moe_combine_fwd_kernel<16, AT><<<warp_grid(B * T), 256, 0, ST(stream)>>>(
+                          CAP(AT, h2), gval, inv, xres, gate, ldmod, xout, AP(AT, ymoe), (int)B, (int)T, (int)E, (int)k, (int)D));
   return check_launch("md_moe_combine_fwd");
 }
 
 extern "C" int md_moe_combine_bwd(const void* dy, const void* h2, const float* gval, const int32_t* idx, void* dh2,
-                                  float* dgval, int64_t B, int64_t T, int64_t E, int64_t k, int64_t D, void* stream) {
+                                  float* dgval, int64_t B, int64_t T, int64_t E, int64_t k, int64_t D, int prec,
+                                  void* stream) {
   if (int rc = check_moe("md_moe_combine_bwd", D, E)) return rc;
   if (B * k == 0) return 0;
   if (!dy || !h2 || !gval || !idx || !dh2 || !dgval)
     return md_set_error(MD_ERR_INVALID, "md_moe_combine_bwd: null pointer");
-  moe_combine_bwd_kernel<<<warp_grid(B * E * k), 256, 0, ST(stream)>>>(CBF(dy), CBF(h2), gval, idx, BF(dh2), dgval,
-                                                                       (int)B, (int)T, (int)E, (int)k, (int)D);
+  MD_WITH_ACT(prec, moe_combine_bwd_kernel<AT><<<warp_grid(B * E * k), 256, 0, ST(stream)>>>(
+                        CAP(AT, dy), CAP(AT, h2), gval, idx, AP(AT, dh2), dgval, (int)B, (int)T, (int)E, (int)k, (int)D));
   return check_launch("md_moe_combine_bwd");
 }
 
 extern "C" int md_moe_dx_bwd(const void* dxin, const int32_t* inv, const float* dgval, const float* probs,
                              const float* wg, float* dscores, void* dx, int64_t B, int64_t T, int64_t E, int64_t k,
-                             int64_t D, void* stream) {
+                             int64_t D, int prec, void* stream) {
   if (int rc = check_moe("md_moe_dx_bwd", D, E)) return rc;
   if (B * T == 0) return 0;
   if (!dxin || !inv || !dgval || !probs || !wg || !dscores || !dx)
@@ -444,25 +450,27 @@ extern "C" int md_moe_dx_bwd(const void* dxin, const int32_t* inv, const float* 
   if (smem > 200 * 1024) return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_dx_bwd: E*D too large for shared memory");
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(moe_dx_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(moe_dx_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_dx_bwd_kernel<8, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_dx_bwd_kernel<16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_dx_bwd_kernel<8, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_dx_bwd_kernel<16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
   if (E <= 8)
-    moe_dx_bwd_kernel<8><<<warp_grid(B * T), 256, smem, ST(stream)>>>(CBF(dxin), inv, dgval, probs, wg, dscores, BF(dx),
-                                                                      (int)B, (int)T, (int)E, (int)k, (int)D);
+    MD_WITH_ACT(prec, moe_dx_bwd_kernel<8, AT><<<warp_grid(B * T), 256, smem, ST(stream)>>>(
+                          CAP(AT, dxin), inv, dgval, probs, wg, dscores, AP(AT, dx), (int)B, (int)T, (int)E, (int)k, (int)D));
   else
-    moe_dx_bwd_kernel<16><<<warp_grid(B * T), 256, smem, ST(stream)>>>(CBF(dxin), inv, dgval, probs, wg, dscores, BF(dx),
-                                                                       (int)B, (int)T, (int)E, (int)k, (int)D);
+    MD_WITH_ACT(prec, moe_dx_bwd_kernel<16, AT><<<warp_grid(B * T), 256, smem, ST(stream)>>>(
+                          CAP(AT, dxin), inv, dgval, probs, wg, dscores, AP(AT, dx), (int)B, (int)T, (int)E, (int)k, (int)D));
   return check_launch("md_moe_dx_bwd");
 }
 
 extern "C" int md_moe_gate_wgrad(const float* dscores, const void* x, float* dwg, int64_t rows, int64_t D, int64_t E,
-                                 void* stream) {
+                                 int prec, void* stream) {
   if (int rc = check_moe("md_moe_gate_wgrad", D, E)) return rc;
   if (rows == 0) return 0;
   if (!dscores || !x || !dwg) return md_set_error(MD_ERR_INVALID, "md_moe_gate_wgrad: null pointer");
-  moe_gate_wgrad_kernel<<<(unsigned)((rows + 127) / 128), 256, 0, ST(stream)>>>(dscores, CBF(x), dwg, rows, (int)D,
-                                                                               (int)E);
+  MD_WITH_ACT(prec, moe_gate_wgrad_kernel<AT><<<(unsigned)((rows + 127) / 128), 256, 0, ST(stream)>>>(dscores, CAP(AT, x), dwg,
+                                                                                                     rows, (int)D, (int)E));
   return check_launch("md_moe_gate_wgrad");
 }

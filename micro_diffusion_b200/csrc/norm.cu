@@ -2,7 +2,7 @@
 // All HBM-bound: one warp per row, 16-byte vector loads, warp-shuffle reductions, fp32 statistics.
 // Reference semantics: create_norm (utils.py:71-78), modulate (utils.py:28-30), DiTBlock.forward
 // (dit.py:232-239), ln_q/ln_k over the full hidden width (utils.py:183-186, 122-125).
-#include "common.cuh"
+#include "act.cuh"
 
 namespace md {
 
@@ -45,12 +45,12 @@ __device__ __forceinline__ float4 ld4(const void* base, long long elem_off) {
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 // ------------------------------------------------------------------------------------------ ln_fwd
-template <int VEC, bool EXACT, bool XBF>
+template <int VEC, bool EXACT, bool XBF, typename AT>
 __global__ void __launch_bounds__(128)
-ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, const __nv_bfloat16* __restrict__ yadd,
+ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, const AT* __restrict__ yadd,
               const float* __restrict__ gadd, float* __restrict__ xnew, const float* __restrict__ gamma,
               const float* __restrict__ shift, const float* __restrict__ scale, long long ldmod, long long T,
-              void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int D,
+              AT* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int D,
               float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 2;
@@ -67,7 +67,7 @@ ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, 
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const int i = lane + 32 * j;
-        ya[j] = (EXACT || i < nvec) ? ld4<true>(yadd, src * D + 4LL * i) : f4zero();
+        ya[j] = (EXACT || i < nvec) ? ld4a(yadd + src * D + 4LL * i) : f4zero();
       }
       const float* gt = gadd ? gadd + (row / T) * ldmod : nullptr;
 #pragma unroll
@@ -120,7 +120,7 @@ ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, 
           const float4 a = *reinterpret_cast<const float4*>(sh + 4 * i);
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
-        store4_bf16(y, row * D + 4LL * i, o);
+        st4a(y + row * D + 4LL * i, o);
       }
     }
   }
@@ -130,9 +130,9 @@ ln_fwd_kernel(const void* __restrict__ x, const int32_t* __restrict__ src_rows, 
 // grid (ceil(T / rpb), samples); 4 warps share the block's rows.  Per-column partials A = sum dy,
 // Bc = sum dy*xhat over the block's rows (all of one sample, so scale is constant): dshift += A,
 // dscale += gamma*Bc, dgamma += (1+scale)*Bc.
-template <int VEC, bool EXACT, bool XBF>
+template <int VEC, bool EXACT, bool XBF, typename AT>
 __global__ void __launch_bounds__(128)
-ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const int32_t* __restrict__ src_rows,
+ln_bwd_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const int32_t* __restrict__ src_rows,
               const float* __restrict__ gamma, const float* __restrict__ scale, long long ldmod, long long T,
               const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ dx, int dx_mode,
               float* __restrict__ dgamma, float* __restrict__ dshift, float* __restrict__ dscale, long long rows,
@@ -174,7 +174,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const int
     for (int j = 0; j < VEC; ++j) {
       const int i = lane + 32 * j;
       const bool ok = EXACT || i < nvec;
-      d[j] = ok ? ld4<true>(dy, row * D + 4LL * i) : f4zero();
+      d[j] = ok ? ld4a(dy + row * D + 4LL * i) : f4zero();
       xh[j] = ok ? ld4<XBF>(x, src * D + 4LL * i) : f4zero();
     }
     if (dx != nullptr && dx_mode != 1) {
@@ -209,7 +209,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const int
           o.x = rs * (d[j].x - m1 - xh[j].x * m2); o.y = rs * (d[j].y - m1 - xh[j].y * m2);
           o.z = rs * (d[j].z - m1 - xh[j].z * m2); o.w = rs * (d[j].w - m1 - xh[j].w * m2);
           if (dx_mode == 1) {
-            store4_bf16(dx, drow * D + 4LL * i, o);
+            st4a(reinterpret_cast<AT*>(dx) + drow * D + 4LL * i, o);
           } else {
             o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w;
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(dx) + drow * D + 4LL * i) = o;
@@ -257,25 +257,24 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return r;
 }
 // VEC = uint4 groups per lane (8 bf16 each): W <= 256 * VEC
-template <int VEC>
+template <int VEC, typename AT>
 __global__ void __launch_bounds__(128)
-rownorm_fwd_kernel(__nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ rstd_out, long long rows, int W,
-                   float eps) {
+rownorm_fwd_kernel(AT* __restrict__ x, long long ld, float* __restrict__ rstd_out, long long rows, int W, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = W >> 3;
   for (long long row = 1LL * blockIdx.x * 4 + warp; row < rows; row += 1LL * gridDim.x * 4) {
-    __nv_bfloat16* p = x + row * ld;
-    uint4 raw[VEC];
+    AT* p = x + row * ld;
+    V8<AT> raw[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int i = lane + 32 * j;
-      raw[j] = i < nvec ? *reinterpret_cast<const uint4*>(p + 8 * i) : make_uint4(0, 0, 0, 0);
+      raw[j] = i < nvec ? ldv8(p + 8 * i) : zerov8<AT>();
     }
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float v[8];
-      unpack8(raw[j], v);
+      unpackv8(raw[j], v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += v[e];
     }
@@ -285,7 +284,7 @@ rownorm_fwd_kernel(__nv_bfloat16* __restrict__ x, long long ld, float* __restric
     for (int j = 0; j < VEC; ++j) {
       if (lane + 32 * j < nvec) {
         float v[8];
-        unpack8(raw[j], v);
+        unpackv8(raw[j], v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) ss += (v[e] - mean) * (v[e] - mean);
       }
@@ -297,38 +296,38 @@ rownorm_fwd_kernel(__nv_bfloat16* __restrict__ x, long long ld, float* __restric
       const int i = lane + 32 * j;
       if (i < nvec) {
         float v[8];
-        unpack8(raw[j], v);
+        unpackv8(raw[j], v);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean) * rstd;
-        *reinterpret_cast<uint4*>(p + 8 * i) = pack8(v);
+        st8(p + 8 * i, v);
       }
     }
   }
 }
 
-template <int VEC>
+template <int VEC, typename AT>
 __global__ void __launch_bounds__(128)
-rownorm_bwd_kernel(__nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ xhat,
-                   long long ld_x, const float* __restrict__ rstd, long long rows, int W) {
+rownorm_bwd_kernel(AT* __restrict__ dy, long long ld_dy, const AT* __restrict__ xhat, long long ld_x,
+                   const float* __restrict__ rstd, long long rows, int W) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = W >> 3;
   for (long long row = 1LL * blockIdx.x * 4 + warp; row < rows; row += 1LL * gridDim.x * 4) {
-    __nv_bfloat16* pd = dy + row * ld_dy;
-    const __nv_bfloat16* px = xhat + row * ld_x;
-    uint4 rd[VEC], rx[VEC];
+    AT* pd = dy + row * ld_dy;
+    const AT* px = xhat + row * ld_x;
+    V8<AT> rd[VEC], rx[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int i = lane + 32 * j;
-      rd[j] = i < nvec ? *reinterpret_cast<const uint4*>(pd + 8 * i) : make_uint4(0, 0, 0, 0);
-      rx[j] = i < nvec ? *reinterpret_cast<const uint4*>(px + 8 * i) : make_uint4(0, 0, 0, 0);
+      rd[j] = i < nvec ? ldv8(pd + 8 * i) : zerov8<AT>();
+      rx[j] = i < nvec ? ldv8(px + 8 * i) : zerov8<AT>();
     }
     const float rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float d[8], xh[8];
-      unpack8(rd[j], d);
-      unpack8(rx[j], xh);
+      unpackv8(rd[j], d);
+      unpackv8(rx[j], xh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         s1 += d[e];
@@ -341,22 +340,22 @@ rownorm_bwd_kernel(__nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_b
       const int i = lane + 32 * j;
       if (i < nvec) {
         float d[8], xh[8];
-        unpack8(rd[j], d);
-        unpack8(rx[j], xh);
+        unpackv8(rd[j], d);
+        unpackv8(rx[j], xh);
 #pragma unroll
         for (int e = 0; e < 8; ++e) d[e] = rs * (d[e] - m1 - xh[e] * m2);
-        *reinterpret_cast<uint4*>(pd + 8 * i) = pack8(d);
+        st8(pd + 8 * i, d);
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------- gate_bwd
-template <int VEC, bool EXACT>
+template <int VEC, bool EXACT, typename AT>
 __global__ void __launch_bounds__(128)
-gate_bwd_kernel(const float* __restrict__ dres, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
-                long long ldmod, long long T, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate,
-                long long rows, int D, int rpb) {
+gate_bwd_kernel(const float* __restrict__ dres, const AT* __restrict__ y, const float* __restrict__ gate,
+                long long ldmod, long long T, AT* __restrict__ dy, float* __restrict__ dgate, long long rows, int D,
+                int rpb) {
   extern __shared__ float red[];  // [4][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long smp = blockIdx.y;
@@ -381,7 +380,7 @@ gate_bwd_kernel(const float* __restrict__ dres, const __nv_bfloat16* __restrict_
       const int i = lane + 32 * j;
       const bool ok = EXACT || i < nvec;
       d[j] = ok ? *reinterpret_cast<const float4*>(dres + row * D + 4LL * i) : f4zero();
-      if (need) yv[j] = ok ? ld4<true>(y, row * D + 4LL * i) : f4zero();
+      if (need) yv[j] = ok ? ld4a(y + row * D + 4LL * i) : f4zero();
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -391,8 +390,7 @@ gate_bwd_kernel(const float* __restrict__ dres, const __nv_bfloat16* __restrict_
           acc[j].x += d[j].x * yv[j].x; acc[j].y += d[j].y * yv[j].y;
           acc[j].z += d[j].z * yv[j].z; acc[j].w += d[j].w * yv[j].w;
         }
-        store4_bf16(dy, row * D + 4LL * i,
-                    make_float4(d[j].x * g[j].x, d[j].y * g[j].y, d[j].z * g[j].z, d[j].w * g[j].w));
+        st4a(dy + row * D + 4LL * i, make_float4(d[j].x * g[j].x, d[j].y * g[j].y, d[j].z * g[j].z, d[j].w * g[j].w));
       }
     }
   }
@@ -436,24 +434,25 @@ static int rows_per_block(long long T, long long samples) {
 
 extern "C" int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const void* y_add, const float* gate_add,
                          float* x_new, const float* gamma, const float* shift, const float* scale, int64_t ldmod,
-                         int64_t T, void* y, float* mean, float* rstd, int64_t rows, int64_t D, float eps,
+                         int64_t T, void* y, float* mean, float* rstd, int64_t rows, int64_t D, float eps, int prec,
                          void* stream) {
   if (int rc = check_ln_dims("md_ln_fwd", rows, D, T)) return rc;
   if (rows == 0) return 0;
   if (!x || !y) return md_set_error(MD_ERR_INVALID, "md_ln_fwd: null pointer");
   if (y_add != nullptr && (x_new == nullptr || x_bf16)) return md_set_error(MD_ERR_INVALID, "md_ln_fwd: residual add needs x_new and f32 x");
-  const __nv_bfloat16* yadd = reinterpret_cast<const __nv_bfloat16*>(y_add);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = row_grid(rows);
-#define LN_FWD(VEC, EXACT)                                                                                             \
-  do {                                                                                                                 \
-    if (x_bf16)                                                                                                        \
-      ln_fwd_kernel<VEC, EXACT, true><<<grid, 128, 0, st>>>(x, src_rows, yadd, gate_add, x_new, gamma, shift, scale,  \
-                                                            ldmod, T, y, mean, rstd, rows, static_cast<int>(D), eps); \
-    else                                                                                                               \
-      ln_fwd_kernel<VEC, EXACT, false><<<grid, 128, 0, st>>>(x, src_rows, yadd, gate_add, x_new, gamma, shift, scale, \
-                                                             ldmod, T, y, mean, rstd, rows, static_cast<int>(D), eps);\
-  } while (0)
+#define LN_FWD(VEC, EXACT)                                                                                              \
+  MD_WITH_ACT(prec, do {                                                                                                \
+    if (x_bf16)                                                                                                         \
+      ln_fwd_kernel<VEC, EXACT, true, AT><<<grid, 128, 0, st>>>(x, src_rows, CAP(AT, y_add), gate_add, x_new, gamma,   \
+                                                                shift, scale, ldmod, T, AP(AT, y), mean, rstd, rows,   \
+                                                                static_cast<int>(D), eps);                             \
+    else                                                                                                                \
+      ln_fwd_kernel<VEC, EXACT, false, AT><<<grid, 128, 0, st>>>(x, src_rows, CAP(AT, y_add), gate_add, x_new, gamma,  \
+                                                                 shift, scale, ldmod, T, AP(AT, y), mean, rstd, rows,  \
+                                                                 static_cast<int>(D), eps);                            \
+  } while (0))
   if (D == 1024) LN_FWD(8, true);
   else if (D == 768) LN_FWD(6, true);
   else if (D == 512) LN_FWD(4, true);
@@ -465,7 +464,7 @@ extern "C" int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, con
 
 extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_t* src_rows, const float* gamma,
                          const float* scale, int64_t ldmod, int64_t T, const float* mean, const float* rstd, void* dx,
-                         int dx_mode, float* dgamma, float* dshift, float* dscale, int64_t rows, int64_t D,
+                         int dx_mode, float* dgamma, float* dshift, float* dscale, int64_t rows, int64_t D, int prec,
                          void* stream) {
   if (int rc = check_ln_dims("md_ln_bwd", rows, D, T)) return rc;
   if (rows == 0) return 0;
@@ -477,17 +476,17 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
   dim3 grid(static_cast<unsigned>((T + rpb - 1) / rpb), static_cast<unsigned>(rows / T));
   const size_t smem = 4 * D * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define LN_BWD(VEC, EXACT)                                                                                            \
-  do {                                                                                                                \
-    if (x_bf16)                                                                                                       \
-      ln_bwd_kernel<VEC, EXACT, true><<<grid, 128, smem, st>>>(dy, x, src_rows, gamma, scale, ldmod, T, mean, rstd,  \
-                                                               dx, dx_mode, dgamma, dshift, dscale, rows,            \
-                                                               static_cast<int>(D), rpb);                            \
-    else                                                                                                              \
-      ln_bwd_kernel<VEC, EXACT, false><<<grid, 128, smem, st>>>(dy, x, src_rows, gamma, scale, ldmod, T, mean, rstd, \
-                                                                dx, dx_mode, dgamma, dshift, dscale, rows,           \
-                                                                static_cast<int>(D), rpb);                           \
-  } while (0)
+#define LN_BWD(VEC, EXACT)                                                                                             \
+  MD_WITH_ACT(prec, do {                                                                                               \
+    if (x_bf16)                                                                                                        \
+      ln_bwd_kernel<VEC, EXACT, true, AT><<<grid, 128, smem, st>>>(CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T,  \
+                                                                   mean, rstd, dx, dx_mode, dgamma, dshift, dscale,   \
+                                                                   rows, static_cast<int>(D), rpb);                   \
+    else                                                                                                               \
+      ln_bwd_kernel<VEC, EXACT, false, AT><<<grid, 128, smem, st>>>(CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T, \
+                                                                    mean, rstd, dx, dx_mode, dgamma, dshift, dscale,  \
+                                                                    rows, static_cast<int>(D), rpb);                  \
+  } while (0))
   if (D == 1024) LN_BWD(8, true);
   else if (D == 768) LN_BWD(6, true);
   else if (D == 512) LN_BWD(4, true);
@@ -497,41 +496,36 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
   return check_launch("md_ln_bwd");
 }
 
-extern "C" int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, float eps, void* stream) {
+extern "C" int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, float eps, int prec,
+                              void* stream) {
   if (rows == 0) return 0;
   if (!x || !rstd) return md_set_error(MD_ERR_INVALID, "md_rownorm_fwd: null pointer");
   if (W % 8 != 0 || W > 2048 || ld % 8 != 0)
     return md_set_error(MD_ERR_UNSUPPORTED, "md_rownorm_fwd: need W % 8 == 0, W <= 2048, ld % 8 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (W <= 1024)
-    rownorm_fwd_kernel<4><<<row_grid(rows), 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, rstd, rows,
-                                                          static_cast<int>(W), eps);
+    MD_WITH_ACT(prec, rownorm_fwd_kernel<4, AT><<<row_grid(rows), 128, 0, st>>>(AP(AT, x), ld, rstd, rows, static_cast<int>(W), eps));
   else
-    rownorm_fwd_kernel<8><<<row_grid(rows), 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(x), ld, rstd, rows,
-                                                          static_cast<int>(W), eps);
+    MD_WITH_ACT(prec, rownorm_fwd_kernel<8, AT><<<row_grid(rows), 128, 0, st>>>(AP(AT, x), ld, rstd, rows, static_cast<int>(W), eps));
   return check_launch("md_rownorm_fwd");
 }
 
 extern "C" int md_rownorm_bwd(void* dy, int64_t ld_dy, const void* xhat, int64_t ld_x, const float* rstd, int64_t rows,
-                              int64_t W, void* stream) {
+                              int64_t W, int prec, void* stream) {
   if (rows == 0) return 0;
   if (!dy || !xhat || !rstd) return md_set_error(MD_ERR_INVALID, "md_rownorm_bwd: null pointer");
   if (W % 8 != 0 || W > 2048 || ld_dy % 8 != 0 || ld_x % 8 != 0)
     return md_set_error(MD_ERR_UNSUPPORTED, "md_rownorm_bwd: need W % 8 == 0, W <= 2048, ld % 8 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (W <= 1024)
-    rownorm_bwd_kernel<4><<<row_grid(rows), 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(dy), ld_dy,
-                                                          reinterpret_cast<const __nv_bfloat16*>(xhat), ld_x, rstd, rows,
-                                                          static_cast<int>(W));
+    MD_WITH_ACT(prec, rownorm_bwd_kernel<4, AT><<<row_grid(rows), 128, 0, st>>>(AP(AT, dy), ld_dy, CAP(AT, xhat), ld_x, rstd, rows, static_cast<int>(W)));
   else
-    rownorm_bwd_kernel<8><<<row_grid(rows), 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(dy), ld_dy,
-                                                          reinterpret_cast<const __nv_bfloat16*>(xhat), ld_x, rstd, rows,
-                                                          static_cast<int>(W));
+    MD_WITH_ACT(prec, rownorm_bwd_kernel<8, AT><<<row_grid(rows), 128, 0, st>>>(AP(AT, dy), ld_dy, CAP(AT, xhat), ld_x, rstd, rows, static_cast<int>(W)));
   return check_launch("md_rownorm_bwd");
 }
 
 extern "C" int md_gate_bwd(const float* dres, const void* y, const float* gate, int64_t ldmod, int64_t T, void* dy,
-                           float* dgate, int64_t rows, int64_t D, void* stream) {
+                           float* dgate, int64_t rows, int64_t D, int prec, void* stream) {
   if (int rc = check_ln_dims("md_gate_bwd", rows, D, T)) return rc;
   if (rows == 0) return 0;
   if (!dres || !dy) return md_set_error(MD_ERR_INVALID, "md_gate_bwd: null pointer");
@@ -540,10 +534,9 @@ extern "C" int md_gate_bwd(const float* dres, const void* y, const float* gate, 
   dim3 grid(static_cast<unsigned>((T + rpb - 1) / rpb), static_cast<unsigned>(rows / T));
   const size_t smem = 4 * D * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(y);
-  __nv_bfloat16* dyb = reinterpret_cast<__nv_bfloat16*>(dy);
-#define GATE(VEC, EXACT) \
-  gate_bwd_kernel<VEC, EXACT><<<grid, 128, smem, st>>>(dres, yb, gate, ldmod, T, dyb, dgate, rows, static_cast<int>(D), rpb)
+#define GATE(VEC, EXACT)                                                                                               \
+  MD_WITH_ACT(prec, gate_bwd_kernel<VEC, EXACT, AT><<<grid, 128, smem, st>>>(dres, CAP(AT, y), gate, ldmod, T, AP(AT, dy), \
+                                                                             dgate, rows, static_cast<int>(D), rpb))
   if (D == 1024) GATE(8, true);
   else if (D == 768) GATE(6, true);
   else if (D == 512) GATE(4, true);

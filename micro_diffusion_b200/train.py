@@ -110,6 +110,7 @@ def trainer_kwargs(cfg: dict) -> Dict[str, Any]:
         load_path=tr.get("load_path"), load_weights_only=bool(tr.get("load_weights_only", False)),
         load_strict_model_weights=bool(tr.get("load_strict_model_weights", True)),
         load_ignore_keys=tuple(tr.get("load_ignore_keys") or ()),
+        save_num_checkpoints_to_keep=tr.get("save_num_checkpoints_to_keep"),
     )
 
 

@@ -87,25 +87,52 @@ def _drop_ignored(tree: dict, patterns: Sequence[str]) -> List[str]:
     return dropped
 
 
-def save_checkpoint(path: str, model, optimizer: Optional[FlatAdamW], batch: int, rank: int = 0) -> None:
-    """Rank 0 writes; parameters are replicated so there is nothing to gather."""
+def _rng_state(device) -> dict:
+    st = {"torch": torch.get_rng_state()}
+    if torch.device(device).type == "cuda":
+        st["cuda"] = torch.cuda.get_rng_state(device)
+    return st
+
+
+def save_checkpoint(path: str, model, optimizer: Optional[FlatAdamW], batch: int, rank: int = 0, loader=None,
+                    world: int = 1, keep: Optional[int] = None) -> None:
+    """Rank 0 writes; parameters are replicated so there is nothing to gather except the per-rank RNG states
+    (every rank calls this).  `loader.state_dict()` (epoch, batch in epoch) and the RNG states are what Composer's
+    checkpoint restores so that a resumed run continues the sample / noise / mask streams instead of replaying them.
+    `keep` = Composer's save_num_checkpoints_to_keep (configs/res_256_pretrain.yaml:112): older ba*.pt are removed."""
+    rng = [_rng_state(model.dit.store.device)]
+    if world > 1:
+        import torch.distributed as dist
+        gathered = [None] * world
+        dist.all_gather_object(gathered, rng[0])
+        rng = gathered
     if rank != 0:
         return
     sd = {f"dit.{k}": v.detach().cpu() for k, v in model.dit.state_dict().items()}
     state = {"model": sd, "timestamp": {"batch": int(batch)}}
+    if loader is not None and hasattr(loader, "state_dict"):
+        state["dataset_state"] = loader.state_dict()
     if optimizer is not None:
         state["optimizers"] = {"FlatAdamW": {"exp_avg": optimizer.m.cpu(), "exp_avg_sq": optimizer.v.cpu(),
                                              "step": optimizer.t,
                                              "layout": list(model.dit.store.layout.slots.keys())}}
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     tmp = path + ".tmp"
-    torch.save({"state": state, "rng": {"torch": torch.get_rng_state()}}, tmp)
+    torch.save({"state": state, "rng": rng}, tmp)
     os.replace(tmp, path)
+    if keep is not None and keep > 0:
+        folder = os.path.dirname(os.path.abspath(path))
+        olds = sorted((f for f in os.listdir(folder) if f.startswith("ba") and f.endswith(".pt") and f[2:-3].isdigit()),
+                      key=lambda f: int(f[2:-3]))
+        for f in olds[:-keep]:
+            os.remove(os.path.join(folder, f))
 
 
 def load_checkpoint(path: str, model, optimizer: Optional[FlatAdamW] = None, load_weights_only: bool = False,
-                    load_strict_model_weights: bool = True, load_ignore_keys: Sequence[str] = ()) -> int:
-    """Returns the batch count to resume from (0 with `load_weights_only`)."""
+                    load_strict_model_weights: bool = True, load_ignore_keys: Sequence[str] = (), loader=None,
+                    rank: int = 0) -> int:
+    """Returns the batch count to resume from (0 with `load_weights_only`).  A full load also restores this rank's
+    RNG state and the loader position saved by `save_checkpoint` (dropped like any other entry by `load_ignore_keys`)."""
     ckpt = torch.load(path, map_location="cpu", weights_only=False)
     if load_ignore_keys:
         _drop_ignored(ckpt, list(load_ignore_keys))
@@ -124,6 +151,14 @@ def load_checkpoint(path: str, model, optimizer: Optional[FlatAdamW] = None, loa
         optimizer.m.copy_(opt["exp_avg"])
         optimizer.v.copy_(opt["exp_avg_sq"])
         optimizer.t = int(opt["step"])
+    ds_state = ckpt["state"].get("dataset_state")
+    if loader is not None and ds_state is not None and hasattr(loader, "load_state_dict"):
+        loader.load_state_dict(ds_state)
+    rng = ckpt.get("rng")
+    if isinstance(rng, list) and rank < len(rng) and rng[rank] is not None:
+        torch.set_rng_state(rng[rank]["torch"])
+        if "cuda" in rng[rank] and torch.device(model.dit.store.device).type == "cuda":
+            torch.cuda.set_rng_state(rng[rank]["cuda"], model.dit.store.device)
     return int(ckpt["state"].get("timestamp", {}).get("batch", 0))
 
 
@@ -142,7 +177,8 @@ class Trainer:
                  load_path: Optional[str] = None, load_weights_only: bool = False,
                  load_strict_model_weights: bool = True, load_ignore_keys: Sequence[str] = (),
                  log_every: int = 50, log_fn: Callable[[str], None] = print,
-                 eval_dataloader: Optional[Iterable[Dict[str, torch.Tensor]]] = None, eval_interval="0ba"):
+                 eval_dataloader: Optional[Iterable[Dict[str, torch.Tensor]]] = None, eval_interval="0ba",
+                 save_num_checkpoints_to_keep: Optional[int] = None):
         import torch.distributed as dist
         self.model = model
         self.loader = train_dataloader
@@ -153,6 +189,7 @@ class Trainer:
         lr_multiplier(scheduler, 0, 1, 2)  # validate the name early
         self.microbatch = device_train_microbatch_size
         self.save_folder, self.save_interval = save_folder, parse_batches(save_interval)
+        self.save_keep = save_num_checkpoints_to_keep if (save_num_checkpoints_to_keep or 0) > 0 else None
         self.log_every, self.log = log_every, log_fn
         self.eval_loader, self.eval_interval = eval_dataloader, parse_batches(eval_interval)
         self.last_eval_loss: Optional[float] = None
@@ -163,7 +200,7 @@ class Trainer:
         self.batch = 0
         if load_path:
             self.batch = load_checkpoint(load_path, model, self.optimizer, load_weights_only,
-                                         load_strict_model_weights, load_ignore_keys)
+                                         load_strict_model_weights, load_ignore_keys, loader=self.loader, rank=self.rank)
 
     def lr_at(self, batch: int) -> float:
         return self.optimizer.lr * lr_multiplier(self.scheduler, batch, self.t_warmup, self.t_max, self.alpha, self.alpha_f)
@@ -180,8 +217,15 @@ class Trainer:
         total = torch.zeros(2, dtype=torch.float64, device=dev)  # [sum of batch losses, batches]
         for batch in self.eval_loader:
             batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
-            loss = self.model.eval_forward(batch)[0]
-            total[0] += loss.detach().double()
+            # eval runs unmasked (4x the backbone tokens of training): split like training does so that the
+            # reference's eval_batch_size fits beside the weights; the batch loss is the sample-weighted mean
+            n = batch["image_latents"].shape[0]
+            acc = torch.zeros((), dtype=torch.float64, device=dev)
+            for s0 in range(0, n, self.microbatch):
+                mb = {k: (v[s0:s0 + self.microbatch] if torch.is_tensor(v) else v) for k, v in batch.items()}
+                nb = mb["image_latents"].shape[0]
+                acc += self.model.eval_forward(mb)[0].detach().double() * (nb / n)
+            total[0] += acc
             total[1] += 1
         if self.world > 1:
             dist.all_reduce(total)
@@ -190,6 +234,13 @@ class Trainer:
             raise RuntimeError("eval_dataloader yielded no batches")
         self.last_eval_loss = float(total[0] / total[1])
         return self.last_eval_loss
+
+    def _raise_if_nonfinite(self, loss: Optional[float] = None) -> None:
+        """NaNCatcher.after_loss (callbacks.py:47-64) without a per-step host sync: md_adamw refuses to apply a step
+        whose gradient norm is not finite and raises a device flag; the flag (and the loss, when it is read anyway) is
+        checked at log and checkpoint time, so a poisoned update is never applied and never saved."""
+        if (loss is not None and loss != loss) or int(self.optimizer.nonfinite.item()) != 0:
+            raise RuntimeError("Train loss contains a NaN.")  # callbacks.py:52
 
     def fit(self, until: Optional[int] = None) -> float:
         """Train to `max_duration` (or stop early after batch `until`, schedule unchanged); returns the last logged loss."""
@@ -210,8 +261,7 @@ class Trainer:
                 n0 += batch["image_latents"].shape[0] * self.world
                 if self.batch % self.log_every == 0 or self.batch == stop:
                     last = float(loss)  # the only host sync of the loop
-                    if last != last:
-                        raise RuntimeError("Train loss contains a NaN.")  # callbacks.py:52
+                    self._raise_if_nonfinite(last)
                     dt = time.perf_counter() - t0
                     if self.rank == 0:
                         self.log(f"batch {self.batch}/{self.t_max} loss {last:.4f} lr {self.optimizer.lr_now:.3e} "
@@ -222,8 +272,9 @@ class Trainer:
                     if self.rank == 0:
                         self.log(f"batch {self.batch}/{self.t_max} eval loss {ev:.4f}")
                 if self.save_folder and self.batch % self.save_interval == 0:
+                    self._raise_if_nonfinite()  # never write a checkpoint after a skipped (NaN / Inf) step
                     save_checkpoint(os.path.join(self.save_folder, f"ba{self.batch}.pt"), self.model, self.optimizer,
-                                    self.batch, self.rank)
+                                    self.batch, self.rank, loader=self.loader, world=self.world, keep=self.save_keep)
                 if self.batch >= stop:
                     break
             if not progressed:

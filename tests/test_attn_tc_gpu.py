@@ -13,7 +13,8 @@ BF16 = torch.bfloat16
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk", [(2, 3, 128, 128), (1, 1, 128, 64), (2, 2, 256, 256), (3, 4, 64, 64), (2, 5, 256, 77),
-                                       (2, 3, 100, 200), (1, 2, 64, 77), (2, 2, 1024, 77)])
+                                       (2, 3, 100, 200), (1, 2, 64, 77), (2, 2, 1024, 77), (2, 3, 64, 64), (2, 2, 77, 77), (3, 2, 50, 33),
+                                       (40, 8, 256, 256), (64, 16, 64, 77), (37, 6, 130, 16)])
 def test_attn_fwd_tc_matches_contract(B, H, Tq, Tk):
     from micro_diffusion_b200.ops import CudaOps
     from oracle.emu_ops import EmuOps
@@ -38,7 +39,8 @@ def test_attn_fwd_tc_matches_contract(B, H, Tq, Tk):
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk", [(1, 1, 128, 128), (2, 2, 256, 256), (3, 4, 64, 64), (2, 5, 256, 77), (2, 3, 100, 200),
-                                       (1, 2, 64, 77), (1, 2, 512, 77)])
+                                       (1, 2, 64, 77), (1, 2, 512, 77), (2, 3, 64, 64), (2, 2, 77, 77), (3, 2, 50, 33), (20, 8, 256, 256),
+                                       (64, 16, 64, 77), (40, 16, 64, 64), (37, 6, 130, 16), (2, 2, 300, 144)])
 def test_attn_bwd_tc_matches_contract(B, H, Tq, Tk):
     from micro_diffusion_b200.ops import CudaOps
     from oracle.emu_ops import EmuOps

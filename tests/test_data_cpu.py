@@ -133,3 +133,38 @@ def test_device_loader_partial_batch_multi_dir_and_error_surfacing(tmp_path):
     json.dump(idx, open(os.path.join(tmp_path / "z", "index.json"), "w"))
     with pytest.raises(ValueError):
         LatentsDataset(str(tmp_path / "z"), image_size=256)
+
+
+def test_device_loader_resumes_sample_and_drop_streams(tmp_path):
+    """a resumed run must continue the shuffled sample order and the caption-drop stream from the position
+    the checkpoint recorded (epoch, batch in epoch) instead of replaying epoch 0 from the start."""
+    from micro_diffusion_b200.data import DeviceBatchLoader, LatentsDataset
+    _make(tmp_path, n=24, with512=False)
+    ds = LatentsDataset(str(tmp_path), image_size=256, cap_drop_prob=0.5)
+
+    def fresh():
+        return DeviceBatchLoader(ds, 4, "cpu", shuffle=True, seed=5)
+    ref = fresh()
+    stream = []
+    for _ in range(2):  # two epochs of 6 batches
+        stream += [{k: v.clone() for k, v in b.items()} for b in ref]
+    for consumed in (1, 4, 6, 8):
+        a = fresh()
+        it, n, state = iter(a), 0, None
+        while n < consumed:
+            try:
+                next(it)
+                n += 1
+            except StopIteration:
+                it = iter(a)
+        state = a.state_dict()
+        it.close()
+        assert state["epoch"] * 6 + state["batch_in_epoch"] == consumed
+        b = fresh()
+        b.load_state_dict(state)
+        rest = []
+        while len(rest) + consumed < 12:
+            rest += [x for x in b]
+        for got, want in zip(rest, stream[consumed:]):
+            assert torch.equal(got["image_latents"], want["image_latents"])
+            assert torch.equal(got["drop_caption_mask"], want["drop_caption_mask"])

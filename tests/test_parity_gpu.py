@@ -41,12 +41,40 @@ def test_cuda_path_matches_oracle_and_golden(name):
         assert pc.rel_l2(grads[k], g) < 2 * fx["ref_amp_bf16_grad_rel_max"] + 2e-2, k
 
 
-def _zoo_case(factory, head_dim, input_size, in_channels, mask_ratio, B=2, pos_interp_scale=1.0, p_mean=-0.6, p_std=1.2):
+def _high_ops(device):
+    from micro_diffusion_b200.ops import CudaOps
+    return CudaOps(device, precision="high")
+
+
+@pytest.mark.parametrize("name", list(configs.PARITY_CONFIGS))
+def test_high_precision_mode_meets_the_stated_tolerance(name):
+    """north_star's gate: 1e-3 relative on the loss AND on the denoiser output, through the SAME CUDA path (same host
+    sequencing, same kernels, same .so) in its high-precision mode -- MD_PRECISION=high: fp32 saved activations, every
+    GEMM a 3-way bf16 split on the tcgen05 kernel, attention in fp32.  The bf16-mode numbers of the same
+    case are printed by test_cuda_path_matches_oracle_and_golden."""
+    fx = torch.load(os.path.join(pc.GOLDEN, f"parity_{name}.pt"), weights_only=False)
+    loss, grads, den, ld = pc.product_run(name, ops_factory=_high_ops, device=DEV)
+    ops = ld.dit.engine.ops
+    assert ops.prec == 1 and not ops.is_emulation and ops.launches > 100
+    lrel = abs(loss - fx["loss"]) / fx["loss"]
+    drel = pc.rel_l2(den, fx["denoised_unmasked"])
+    sd_cpu = {k: v.detach().cpu() for k, v in ld.dit.state_dict().items()}
+    oloss, ograds, oden, _ = pc.oracle_run(name, sd_cpu)
+    errs, med, worst = pc.grad_report(grads, ograds)
+    print(f"\n[{name} high] loss cuda {loss:.7f} reference {fx['loss']:.7f} rel {lrel:.2e} | D_x relL2 {drel:.2e} | "
+          f"grads median {med:.2e} worst {worst:.2e} ({errs[0][1]})")
+    assert lrel < 1e-3 and drel < 1e-3
+    assert med < 1e-3 and worst < 2e-2, errs[:5]
+
+
+def _zoo_case(factory, head_dim, input_size, in_channels, mask_ratio, B=2, pos_interp_scale=1.0, p_mean=-0.6, p_std=1.2,
+              ops_factory=None):
     """A zoo model (dit.py:630-709) on the B200 against the fp32 port on the same seeded weights, batch and draws:
     loss, unmasked D_x and every parameter gradient."""
     from micro_diffusion_b200.models.model import LatentDiffusion, PrecomputedLatentStubs
     from oracle import port, weights
-    net = factory(input_size=input_size, in_channels=in_channels, pos_interp_scale=pos_interp_scale)
+    net = factory(input_size=input_size, in_channels=in_channels, pos_interp_scale=pos_interp_scale,
+                  ops_factory=ops_factory)
     net.load_state_dict(weights.synth_state_dict(net.state_dict(), seed=7))
     sd_cpu = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.to(DEV)
@@ -81,6 +109,16 @@ def _zoo_case(factory, head_dim, input_size, in_channels, mask_ratio, B=2, pos_i
     lrel = abs(float(loss) - float(oloss)) / float(oloss)
     drel = pc.rel_l2(den, oden)
     return float(loss), float(oloss), lrel, drel, med, worst, errs
+
+
+def test_tiny_zoo_model_high_precision_meets_the_stated_tolerance():
+    """BASELINE.json configs[0] (MicroDiT_Tiny_2, res 256, mask 0.75, batch 4) through the high-precision mode: 1e-3."""
+    from micro_diffusion_b200.models.dit import MicroDiT_Tiny_2
+    loss, oloss, lrel, drel, med, worst, errs = _zoo_case(MicroDiT_Tiny_2, 32, 32, 4, 0.75, B=4, ops_factory=_high_ops)
+    print(f"\n[Tiny_2 high] loss cuda {loss:.7f} oracle {oloss:.7f} rel {lrel:.2e} D_x relL2 {drel:.2e} "
+          f"grads median {med:.2e} worst {worst:.2e} ({errs[0][1]})")
+    assert lrel < 1e-3 and drel < 1e-3
+    assert med < 2e-3 and worst < 5e-2, errs[:5]
 
 
 def test_tiny_zoo_model_matches_oracle():

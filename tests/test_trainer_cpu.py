@@ -137,7 +137,12 @@ def test_eval_interval_runs_the_eval_pass_without_touching_training_state():
     b2.dit.load_state_dict(b.dit.state_dict())
     b2.eval()
     torch.manual_seed(11)
-    want = sum(float(b2.eval_forward(x)[0]) for x in ev) / 2
+
+    def batch_loss(x):  # evaluate() splits an eval batch into device_train_microbatch_size pieces (sample-weighted mean)
+        n, mb = x["image_latents"].shape[0], kw["device_train_microbatch_size"]
+        return sum(float(b2.eval_forward({k: v[s:s + mb] for k, v in x.items()})[0].detach()) *
+                   (min(mb, n - s) / n) for s in range(0, n, mb))
+    want = sum(batch_loss(x) for x in ev) / 2
     torch.manual_seed(11)
     got = Trainer(b2, [], max_duration="1ba", log_fn=lambda s: None, eval_dataloader=ev, **kw).evaluate()
     assert got == pytest.approx(want, rel=1e-6)

@@ -17,13 +17,19 @@ from micro_diffusion_b200.ops import CudaOps  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--no-tc", action="store_true")
 ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--only-tc", action="store_true")
+ap.add_argument("--fwd-only", action="store_true")
+ap.add_argument("--bwd-only", action="store_true")
+ap.add_argument("--shapes", default="", help="comma list of H:Tq:Tk (default: the C2/C3 set)")
+ap.add_argument("--iters", type=int, default=10)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 ops = CudaOps(dev)
 BF = torch.bfloat16
 
 
-def timeit(fn, iters=10):
+def timeit(fn, iters=None):
+    iters = iters or args.iters
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
@@ -46,16 +52,26 @@ def bench(B, H, Tq, Tk, hd=64):
     delta = torch.empty(B, H, Tq, device=dev)
     ff, fb = 4 * B * H * Tq * Tk * hd, 10 * B * H * Tq * Tk * hd
     line = f"B={B} H={H} Tq={Tq} Tk={Tk}:"
-    for tc in ([False] if args.no_tc else [False, True]):
+    for tc in ([False] if args.no_tc else ([True] if args.only_tc else [False, True])):
         ops.attn_tc = tc
-        tf = timeit(lambda: ops.attn_fwd(q[:, :hs], kv[:, :hs], kv[:, hs:], o, lse, B, H, Tq, Tk, hd))
-        tb = timeit(lambda: ops.attn_bwd(do, q[:, :hs], kv[:, :hs], kv[:, hs:], o, lse, delta, dq, dkv[:, :hs], dkv[:, hs:],
-                                         B, H, Tq, Tk, hd))
+        tf = tb = float("nan")
+        if not args.bwd_only:
+            tf = timeit(lambda: ops.attn_fwd(q[:, :hs], kv[:, :hs], kv[:, hs:], o, lse, B, H, Tq, Tk, hd))
+        if not args.fwd_only:
+            if args.bwd_only:
+                ops.attn_fwd(q[:, :hs], kv[:, :hs], kv[:, hs:], o, lse, B, H, Tq, Tk, hd)
+            tb = timeit(lambda: ops.attn_bwd(do, q[:, :hs], kv[:, :hs], kv[:, hs:], o, lse, delta, dq, dkv[:, :hs],
+                                             dkv[:, hs:], B, H, Tq, Tk, hd))
         line += (f"  [{'tcgen05' if tc else 'mma.sync'}] fwd {tf * 1e3:7.1f} us {ff / tf / 1e9:6.0f} TF/s"
                  f" | bwd {tb * 1e3:7.1f} us {fb / tb / 1e9:6.0f} TF/s")
     print(line, flush=True)
 
 
+if args.shapes:
+    for spec in args.shapes.split(","):
+        H, Tq, Tk = (int(x) for x in spec.split(":"))
+        bench(args.batch, H, Tq, Tk)
+    sys.exit(0)
 for shp in [(args.batch, 12, 256, 256), (args.batch, 12, 256, 77), (args.batch, 16, 64, 64), (args.batch, 16, 64, 77),
             (args.batch, 16, 256, 256), (args.batch, 16, 256, 77)]:
     bench(*shp)
