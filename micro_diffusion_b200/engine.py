@@ -422,7 +422,8 @@ class Engine:
                       raw_t=None, cap_out=None, prompt=None):
         o, st, cfg = self.ops, self.store, self.cfg
         P = st.p
-        st.refresh_copies(o, self.weights_token() if self.weights_token is not None else None)
+        wtoken = self.weights_token() if self.weights_token is not None else None
+        st.refresh_copies(o, wtoken, part="front")
         B, C, Hh, Ww = lat.shape
         p, D, Dm = cfg.patch_size, cfg.dim, cfg.mixer_dim
         T = (Hh // p) * (Ww // p)
@@ -504,6 +505,7 @@ class Engine:
         else:
             xb = xm
         # ---- backbone (dit.py:510-511)
+        st.refresh_copies(o, wtoken, part="back")
         c.block_sv = []
         kv_b = prompt.kv_b if kvn else self._kv_fwd("kv.blocks", s.ybf, len(cfg.blocks), 2 * D)
         for i, bs in enumerate(cfg.blocks):

@@ -47,6 +47,7 @@ class ParamLayout:
     """Name -> (offset, shape) in the flat buffers, plus the GEMM groups."""
 
     ALIGN = 8  # elements: 16 B for bf16 TMA bases, 32 B for fp32 vector loads
+    RANGE_ALIGN = 1024  # boundaries of the gradient-exchange ranges: every range splits evenly over up to 128 ranks
 
     def __init__(self, cfg: DiTConfig):
         self.cfg = cfg
@@ -62,13 +63,35 @@ class ParamLayout:
         self.order: List[Tuple[str, Tuple[int, ...]]] = ada_w + ada_b + kv_m + kv_b + rest
         self.reference_order = [s[0] for s in specs]
         self.slots: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        # The flat buffer is exchanged in a few contiguous ranges (train_step.GradReducer): "back" = the stacked backbone
+        # K/V projection + everything from the first blocks.* / final_layer.* tensor to the end (final once the backbone
+        # backward is done, needed last by the forward), "front" = the rest.  Range boundaries are padded to RANGE_ALIGN
+        # so that each range reduce-scatters / all-gathers in equal 16-byte-aligned shares.
+        def is_back_rest(nm):
+            return nm.startswith("blocks.") or nm.startswith("final_layer.")
+        bounds = set()
+        if kv_b:
+            bounds.add(kv_b[0][0])
+        first_back = next((nm for nm, _ in rest if is_back_rest(nm)), None)
+        if first_back is not None:
+            bounds.add(first_back)
+            i0 = [nm for nm, _ in rest].index(first_back)
+            assert all(is_back_rest(nm) for nm, _ in rest[i0:]), "blocks.* / final_layer.* must close the parameter order"
+        after_kv_b = rest[0][0] if rest else None
+        if kv_b and after_kv_b is not None:
+            bounds.add(after_kv_b)
         off = 0
+        ra = self.RANGE_ALIGN
         for name, shape in self.order:
             n = _numel(shape)
+            if name in bounds:
+                off = (off + ra - 1) // ra * ra
             assert off % self.ALIGN == 0
             self.slots[name] = (off, tuple(shape))
             off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        self.total = off
+        self.total = (off + ra - 1) // ra * ra
+        self.back_start = self.slots[first_back][0] if first_back is not None else self.total
+        self.kv_back = (self.slots[kv_b[0][0]][0], self.slots[after_kv_b][0]) if (kv_b and after_kv_b) else None
 
         # adaLN stack
         self.ada_rows = sum(s[1][0] for s in ada_w)
@@ -129,7 +152,8 @@ class ParamStore:
         self.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.wb = torch.zeros(n, dtype=lowp_dtype, device=self.device)
         self.wbt = torch.zeros(n, dtype=lowp_dtype, device=self.device)
-        self._copies_version = None
+        self._copies_version: Dict[str, object] = {}
+        self.param_ready: Dict[str, object] = {}  # part -> CUDA event of a pending parameter all-gather
         self.p: Dict[str, torch.Tensor] = {}  # fp32 views (reference shapes)
         self.g: Dict[str, torch.Tensor] = {}  # grad views
         for name, (off, shape) in layout.slots.items():
@@ -160,17 +184,34 @@ class ParamStore:
         """fp32 gradient view of a group in its own layout."""
         return self._gview(self.grad, self.layout.groups[name])
 
-    def refresh_copies(self, ops, token=None, force=False) -> bool:
+    def is_back(self, offset: int) -> bool:
+        """True for tensors of the "back" exchange ranges (backbone blocks, final layer, stacked backbone K/V)."""
+        lay = self.layout
+        return offset >= lay.back_start or (lay.kv_back is not None and lay.kv_back[0] <= offset < lay.kv_back[1])
+
+    def refresh_copies(self, ops, token=None, force=False, part=None) -> bool:
         """Re-derive the bf16 operand copies if the master weights changed since the last call.
         `token` is any value that changes whenever a parameter is written (models/dit.py sums the
-        parameters' autograd version counters, which every in-place optimizer / load_state_dict update bumps)."""
+        parameters' autograd version counters, which every in-place optimizer / load_state_dict update bumps).
+        `part` = "front" | "back" | None (both): the forward refreshes the front part (stem, patch mixer) when it starts
+        and the back part (backbone, final layer) right before the backbone, so that a sharded optimizer's parameter
+        all-gather of the back range (train_step.GradReducer.gather_params) overlaps the patch-mixer forward.  Each part
+        first makes the compute stream wait for that range's all-gather event, if one is pending."""
         v = token if token is not None else self.flat._version
-        if not force and self._copies_version == v:
-            return False
-        for g in self.layout.groups.values():
-            src = self.flat[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
-            wb = self.wb[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
-            wbt = self.wbt[g.offset: g.offset + g.numel].view(g.batch, g.cols, g.rows) if g.need_t else None
-            ops.cast_transpose(src, wb, wbt)
-        self._copies_version = v
-        return True
+        done = False
+        for pt in (("front", "back") if part is None else (part,)):
+            ev = self.param_ready.pop(pt, None)
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+            if not force and self._copies_version.get(pt) == v:
+                continue
+            for g in self.layout.groups.values():
+                if self.is_back(g.offset) != (pt == "back"):
+                    continue
+                src = self.flat[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
+                wb = self.wb[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
+                wbt = self.wbt[g.offset: g.offset + g.numel].view(g.batch, g.cols, g.rows) if g.need_t else None
+                ops.cast_transpose(src, wb, wbt)
+            self._copies_version[pt] = v
+            done = True
+        return done

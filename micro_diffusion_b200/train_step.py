@@ -1,12 +1,16 @@
 """A Composer-free training step over the drop-in model: microbatching, data-parallel gradient mean over NCCL,
 global-norm clipping and AdamW -- what composer.Trainer does around `model(batch)` in the reference
 (train.py:103-123; configs/res_256_pretrain.yaml:6-8 clip 0.25, :50-57 AdamW, :111 microbatch 256, :117-118
-FSDP SHARD_GRAD_OP, whose gradient reduce-scatter + parameter all-gather is numerically the mean of the rank
-gradients: a replicated all-reduce, which B200's 180 GB makes affordable -- 18.6 GB for fp32 params+grads+Adam).
+FSDP SHARD_GRAD_OP: gradient reduce-scatter, optimizer step on the local shard, parameter all-gather).
 
-The gradient exchange is ONE collective per step on the flat gradient buffer (params.ParamStore.grad), issued
-in reverse-memory-order buckets on a side stream as soon as the last microbatch's backward has finished writing
-them, so that it overlaps the rest of that backward (the path shards by batch: no activation traffic).
+Default with more than one rank ("sharded", the SHARD_GRAD_OP arithmetic on replicated weights): the flat gradient
+buffer (params.ParamStore.grad) is REDUCE-SCATTERED (mean) in a few contiguous ranges on a side stream -- the backbone
+ranges from inside the last microbatch's backward, as soon as they are final, so that they overlap the patch-mixer and
+stem backward -- each rank runs clip + AdamW on its 1/N of every range, and the updated fp32 parameters are ALL-GATHERED
+on the side stream: the front range (stem, patch mixer) first, the backbone range under the next step's patch-mixer
+forward (params.ParamStore.refresh_copies waits per part).  The path shards by batch: no activation traffic.
+MD_SHARD_OPT=0 (or a world size that does not divide the range alignment) falls back to the replicated form: one
+all-reduce (mean) per range and the full AdamW on every rank.
 """
 from __future__ import annotations
 
@@ -31,18 +35,38 @@ class FlatAdamW:
         self.t = 0
 
     @torch.no_grad()
-    def step(self, lr: Optional[float] = None):
+    def step(self, lr: Optional[float] = None, reducer: Optional["GradReducer"] = None):
+        """`reducer` with `shard` set: the gradient is only valid on this rank's shares (reduce-scatter), so clip + AdamW
+        run on those segments -- the squared norm is summed over ranks -- and the updated parameters are all-gathered."""
         eng = self.dit.engine
         st, o = eng.store, eng.ops
         self.t += 1
+        sharded = reducer is not None and reducer.shard
+        segs = reducer.owned if sharded else [(0, st.flat.numel())]
         # the squared gradient norm is always taken: it scales the clip AND guards the update -- a non-finite norm
         # (NaN / Inf loss, callbacks.py:47-64) makes md_adamw leave weights and moments untouched and raise `nonfinite`
         self.sumsq.zero_()
-        o.sumsq(st.grad, self.sumsq)
-        o.adamw(st.flat, st.grad, self.m, self.v, self.sumsq, float(self.clip or 0.0),
-                float(lr if lr is not None else self.lr), self.betas[0], self.betas[1], self.eps, self.wd, self.t,
-                nonfinite=self.nonfinite)
+        for a, b in segs:
+            o.sumsq(st.grad[a:b], self.sumsq)
+        if sharded:
+            dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM, group=reducer.group)
+        for a, b in segs:
+            o.adamw(st.flat[a:b], st.grad[a:b], self.m[a:b], self.v[a:b], self.sumsq, float(self.clip or 0.0),
+                    float(lr if lr is not None else self.lr), self.betas[0], self.betas[1], self.eps, self.wd, self.t,
+                    nonfinite=self.nonfinite)
+        if sharded:
+            reducer.gather_params(st)
+            self.sharded_by = reducer
         self.dit.mark_weights_dirty()
+
+    sharded_by = None  # the GradReducer whose shares the moments m / v are valid on (None: valid everywhere)
+
+    @torch.no_grad()
+    def gather_state(self):
+        """Make m / v complete on every rank (checkpoints): all-gather of the owned shares."""
+        if self.sharded_by is not None:
+            self.sharded_by.gather_buffer(self.m)
+            self.sharded_by.gather_buffer(self.v)
 
     def zero_grad(self):
         self.dit.store.grad.zero_()
@@ -57,7 +81,7 @@ class GradReducer:
     handles the remainder and joins the streams."""
 
     def __init__(self, store, buckets: int = 4, group=None, ops=None, reserve_sms: Optional[int] = None,
-                 overlap: Optional[bool] = None):
+                 overlap: Optional[bool] = None, shard: Optional[bool] = None):
         """`ops` (the model's CudaOps) + `reserve_sms`: while the early all-reduce is in flight the persistent GEMM grids
         leave that many SMs to NCCL's CTAs -- a statically scheduled 148-CTA grid whose last CTAs cannot become resident
         until the collective's CTAs retire would otherwise run its tail at half speed."""
@@ -93,6 +117,18 @@ class GradReducer:
         self.buckets = buckets
         self.stream = torch.cuda.Stream(device=self.grad.device) if self.grad.is_cuda else None
         self._early_done = False
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        ra = lay.RANGE_ALIGN
+        can_shard = (self.world > 1 and ra % (8 * self.world) == 0 and n % ra == 0
+                     and all(a % ra == 0 and b % ra == 0 for a, b in self.early + self.late))
+        want = (os.environ.get("MD_SHARD_OPT", "1") != "0") if shard is None else bool(shard)
+        self.shard = bool(want and can_shard)
+        # this rank's share of every bucket: [a + r * (b - a) / W, a + (r + 1) * (b - a) / W)
+        self.owned = [self._mine(a, b) for a, b in self._split(self.early) + self._split(self.late)] if self.shard else []
+
+    def _mine(self, a, b):
+        ch = (b - a) // self.world
+        return (a + self.rank * ch, a + (self.rank + 1) * ch)
 
     def _split(self, ranges):
         out = []
@@ -103,15 +139,55 @@ class GradReducer:
         return out
 
     def _allreduce(self, ranges):
-        if self.stream is None:
+        """Mean over ranks of every bucket of `ranges`: all-reduce, or (sharded) reduce-scatter in place -- afterwards
+        only this rank's share of each bucket holds the mean, the rest of the bucket is scratch."""
+        if self.stream is None:  # gloo (CPU tests): no AVG, no reduce_scatter_tensor -- same arithmetic through all_reduce
             for a, b in self._split(ranges):
                 dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.SUM, group=self.group)
-                self.grad[a:b].div_(self.world)
+                if self.shard:
+                    ma, mb = self._mine(a, b)
+                    mine = self.grad[ma:mb] / self.world
+                    self.grad[a:b].fill_(float("nan"))  # what a reduce-scatter leaves undefined must not be read
+                    self.grad[ma:mb] = mine
+                else:
+                    self.grad[a:b].div_(self.world)
             return
         self.stream.wait_stream(torch.cuda.current_stream(self.grad.device))
         with torch.cuda.stream(self.stream):
             for a, b in self._split(ranges):
-                dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.AVG, group=self.group)
+                if self.shard:
+                    ma, mb = self._mine(a, b)
+                    dist.reduce_scatter_tensor(self.grad[ma:mb], self.grad[a:b], op=dist.ReduceOp.AVG, group=self.group)
+                else:
+                    dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.AVG, group=self.group)
+
+    def gather_buffer(self, buf):
+        """All-gather the owned shares of a flat buffer laid out like the gradient (optimizer moments), in place."""
+        for a, b in self._split(self.early) + self._split(self.late):
+            ma, mb = self._mine(a, b)
+            dist.all_gather_into_tensor(buf[a:b], buf[ma:mb].clone(), group=self.group)
+
+    def gather_params(self, store):
+        """All-gather the updated parameters: front ranges first, then the backbone ranges; on the side stream, with one
+        event per part that ParamStore.refresh_copies waits on -- the backbone part travels under the next step's
+        patch-mixer forward."""
+        flat = store.flat
+        parts = (("front", self._split(self.late)), ("back", self._split(self.early)))
+        if self.stream is None:
+            for _, subs in parts:
+                for a, b in subs:
+                    ma, mb = self._mine(a, b)
+                    dist.all_gather_into_tensor(flat[a:b], flat[ma:mb].clone(), group=self.group)
+            return
+        self.stream.wait_stream(torch.cuda.current_stream(flat.device))
+        with torch.cuda.stream(self.stream):
+            for part, subs in parts:
+                for a, b in subs:
+                    ma, mb = self._mine(a, b)
+                    dist.all_gather_into_tensor(flat[a:b], flat[ma:mb], group=self.group)  # in place (NCCL allows it)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                store.param_ready[part] = ev
 
     def reduce_early(self):
         """Called from inside the LAST microbatch's backward once the backbone gradients are final."""
@@ -153,6 +229,6 @@ def train_step(model, batch: Dict[str, torch.Tensor], optimizer: FlatAdamW, redu
         total = loss.detach() * (n / B) if total is None else total + loss.detach() * (n / B)
     if reducer is not None:
         reducer.reduce()
-    optimizer.step(lr)
+    optimizer.step(lr, reducer)
     optimizer.zero_grad()
     return total

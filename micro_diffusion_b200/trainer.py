@@ -101,6 +101,8 @@ def save_checkpoint(path: str, model, optimizer: Optional[FlatAdamW], batch: int
     checkpoint restores so that a resumed run continues the sample / noise / mask streams instead of replaying them.
     `keep` = Composer's save_num_checkpoints_to_keep (configs/res_256_pretrain.yaml:112): older ba*.pt are removed."""
     rng = [_rng_state(model.dit.store.device)]
+    if optimizer is not None:
+        optimizer.gather_state()  # sharded optimizer: every rank takes part in completing the moments
     if world > 1:
         import torch.distributed as dist
         gathered = [None] * world
@@ -108,6 +110,8 @@ def save_checkpoint(path: str, model, optimizer: Optional[FlatAdamW], batch: int
         rng = gathered
     if rank != 0:
         return
+    for ev in list(model.dit.store.param_ready.values()):  # a parameter all-gather may still be in flight
+        ev.synchronize()
     sd = {f"dit.{k}": v.detach().cpu() for k, v in model.dit.state_dict().items()}
     state = {"model": sd, "timestamp": {"batch": int(batch)}}
     if loader is not None and hasattr(loader, "state_dict"):

@@ -29,14 +29,15 @@ def _batch(B, seed):
     return weights.synth_batch(B, 4, 32, seed=seed)
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, shard):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
     from micro_diffusion_b200.train_step import FlatAdamW, GradReducer, train_step
     ld = _build("P")
     opt = FlatAdamW(ld.dit, lr=1e-3, clip_norm=0.25, eps=1e-2)
-    red = GradReducer(ld.dit.store, buckets=3)
+    red = GradReducer(ld.dit.store, buckets=3, shard=shard)
+    assert red.shard == shard
     full = _batch(4, 5)
     mine = {k: v[rank * 2:(rank + 1) * 2].clone() for k, v in full.items()}
     torch.manual_seed(100 + rank)
@@ -49,17 +50,34 @@ def _worker(rank, world, port, out_path):
     assert red._early_done and red.late and red.early
     red.reduce()
     g = ld.dit.store.grad.clone()
-    opt.step()
-    if rank == 0:
-        torch.save({"grad": g, "flat": ld.dit.store.flat.clone(), "loss": float(loss)}, out_path)
+    opt.step(None, red)
+    ld.dit.store.refresh_copies(ld.dit.engine.ops, None, force=True)  # consumes the all-gather events (none on gloo)
+    opt.gather_state()
+    torch.save({"grad": g, "flat": ld.dit.store.flat.clone(), "loss": float(loss), "owned": red.owned,
+                "m": opt.m.clone()}, out_path + f".{rank}")
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_gradient_mean_matches_single_process(tmp_path):
-    out = str(tmp_path / "rank0.pt")
-    mp.start_processes(_worker, args=(2, _free_port(), out), nprocs=2, join=True, start_method="spawn")
-    got = torch.load(out)
+@pytest.mark.parametrize("shard", [False, True])
+def test_two_rank_gradient_mean_matches_single_process(tmp_path, shard):
+    """shard=False: all-reduce + replicated AdamW.  shard=True (the default with NCCL): reduce-scatter, clip + AdamW on
+    each rank's shares with the norm summed over ranks, parameter all-gather -- the SHARD_GRAD_OP arithmetic
+    (configs/res_256_pretrain.yaml:117-118).  Both must reproduce the single-process step over the whole batch."""
+    out = str(tmp_path / "rank.pt")
+    mp.start_processes(_worker, args=(2, _free_port(), out, shard), nprocs=2, join=True, start_method="spawn")
+    got, got1 = torch.load(out + ".0"), torch.load(out + ".1")
+    if shard:
+        # only the owned shares of a reduce-scattered gradient are defined; together they cover the buffer exactly once
+        cover = torch.zeros_like(got["grad"], dtype=torch.int32)
+        merged = torch.zeros_like(got["grad"])
+        for r in (got, got1):
+            for a, b in r["owned"]:
+                cover[a:b] += 1
+                merged[a:b] = r["grad"][a:b]
+        assert int(cover.min()) == 1 and int(cover.max()) == 1
+        got["grad"] = merged
+        assert torch.equal(got["flat"], got1["flat"]) and torch.equal(got["m"], got1["m"])
     # single process: same per-half draws, gradient of the mean of the two half-losses
     from micro_diffusion_b200.train_step import FlatAdamW
     ld = _build("P")

@@ -54,7 +54,7 @@ def test_gradient_accumulation_and_zero_grad_semantics():
         assert torch.allclose(p.grad, g1[k], rtol=1e-5, atol=1e-7), k
         assert p.grad.data_ptr() == ld.dit.store.g[k].data_ptr()
     # an optimizer step bumps the flat version -> bf16 operand copies are refreshed on the next forward
-    v0 = ld.dit.store._copies_version
+    v0 = dict(ld.dit.store._copies_version)
     with torch.no_grad():
         for p in ld.dit.parameters():
             p.add_(0.01 * p.grad)
