@@ -31,7 +31,36 @@ sys.path.insert(0, ROOT)
 
 GLOBAL_BATCH = 2048
 # algorithmic training GFLOP per image (3 x forward; SURVEY.md section 8d / BASELINE.md section 3)
-NCU_GEMM_TRAFFIC_BYTES = 64.2e6 + 61.5e6
+
+
+def read_gemm_traffic():
+    """roofline.traffic: DRAM bytes of one launch of the dominant kernel from a committed ncu capture, or null."""
+    path = os.path.join(ROOT, "profiles", "ncu_gemm_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return {"traffic": d["dram_bytes"], "traffic_launch": d.get("launch"), "traffic_source": d.get("source")}
+    except Exception:
+        return {"traffic": None, "traffic_launch": None, "traffic_source": "no committed capture"}
+
+
+def stock_torch_leg(args):
+    """SURVEY.md section 8d's honest GPU comparator: the reference algorithm (oracle.port) run by stock PyTorch on this
+    B200 under autocast(bf16) -- eager, and through torch.compile (train.py:115) -- forward + backward, no optimizer,
+    in a subprocess with a time limit (tools/stock_torch_gpu.py).  Reported beside the line, never part of `value`."""
+    out = {}
+    for mode, extra, limit in (("eager", [], 240), ("compile", ["--compile"], 420)):
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "stock_torch_gpu.py"), "--workload", args.workload,
+               "--batch", "128", "--iters", "3", "--warmup", "2", *extra]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=limit)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            out[mode] = json.loads(line[-1]) if line else {"error": (r.stderr or "no output")[-200:]}
+        except subprocess.TimeoutExpired:
+            out[mode] = {"error": f"timed out after {limit} s"}
+        except Exception as e:
+            out[mode] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 WORKLOADS = {
     "c2": dict(arch="MicroDiT_XL_2", res=32, ch=4, mask=0.75, pos=1.0, p_mean=-0.6, p_std=1.2, micro=512, gf=282.30,
@@ -221,6 +250,8 @@ def main():
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the brief c3/c4/c5 legs of the N=1 run")
+    ap.add_argument("--no-stock-torch", action="store_true", help="skip the stock-PyTorch-on-B200 comparator leg")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.impl == "reference":
@@ -244,86 +275,129 @@ def main():
     per_rank = args.global_batch // world
     micro = min(args.microbatch or wl["micro"], per_rank)
 
-    ld = build_model(wl, device)
-    opt = FlatAdamW(ld.dit, lr=2.4e-4, weight_decay=0.1, clip_norm=0.25)
-    reducer = GradReducer(ld.dit.store, ops=ld.dit.engine.ops) if world > 1 else None
-    ops = ld.dit.engine.ops
+    def measure(wl, micro, K, W, with_e2e=True, with_probe=True):
+        """Build the model of workload `wl`, run W warm-up + K timed steps (inputs resident), optionally the end-to-end
+        pass from pinned host memory and the per-launch roofline probe; returns a dict of raw numbers and frees the model."""
+        ld = build_model(wl, device)
+        opt = FlatAdamW(ld.dit, lr=2.4e-4, weight_decay=0.1, clip_norm=0.25)
+        reducer = GradReducer(ld.dit.store, ops=ld.dit.engine.ops) if world > 1 else None
+        ops = ld.dit.engine.ops
 
-    host = synth_host_batch(per_rank, wl, seed=18 + rank, pinned=True)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-    resident = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+        host = synth_host_batch(per_rank, wl, seed=18 + rank, pinned=True)
+        h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+        resident = {k: v.to(device, non_blocking=True) for k, v in host.items()}
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
 
-    def step_resident():
-        # the caption-drop mask is applied in place (reference semantics), so hand the step a fresh device copy
-        b = {"image_latents": resident["image_latents"], "caption_latents": resident["caption_latents"].clone(),
-             "drop_caption_mask": resident["drop_caption_mask"]}
-        return train_step(ld, b, opt, reducer, micro)
+        def max_over_ranks(ms):
+            if world == 1:
+                return ms
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
 
-    def step_e2e():
-        b = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-        loss = train_step(ld, b, opt, reducer, micro)
-        return loss.item()  # device -> host read of the step's result
+        def step_resident():
+            # the caption-drop mask is applied in place (reference semantics), so hand the step a fresh device copy
+            b = {"image_latents": resident["image_latents"], "caption_latents": resident["caption_latents"].clone(),
+                 "drop_caption_mask": resident["drop_caption_mask"]}
+            return train_step(ld, b, opt, reducer, micro)
 
-    for _ in range(W):
-        step_resident()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    l0 = ops.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed steps
-    e0.record()
-    for _ in range(K):
-        loss_t = step_resident()
-    e1.record()
-    torch.cuda.profiler.stop()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = (ops.launches - l0)
-    clocks = sampler.stop() if sampler else None
-    ms_step = ms_total / K
-    value = args.global_batch / (ms_step / 1e3)
+        def step_e2e():
+            b = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+            loss = train_step(ld, b, opt, reducer, micro)
+            return loss.item()  # device -> host read of the step's result
 
-    # ---- end to end from pinned host memory
-    step_e2e()
-    barrier()
-    e0.record()
-    for _ in range(K):
-        last_loss = step_e2e()
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / K
-    e2e_value = args.global_batch / (ms_e2e / 1e3)
+        for _ in range(W):
+            step_resident()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = ops.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed steps
+        e0.record()
+        for _ in range(K):
+            loss_t = step_resident()
+        e1.record()
+        torch.cuda.profiler.stop()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = (ops.launches - l0)
+        clocks = sampler.stop() if sampler else None
+        ms_step = ms_total / K
+        value = args.global_batch / (ms_step / 1e3)
 
-    # ---- roofline probe: one extra step with CUDA events around every launch (same stream, same work)
+        r = dict(value=value, ms_step=ms_step, launches=launches, clocks=clocks, loss=float(loss_t), micro=micro,
+                 h2d_bytes=h2d_bytes, step_tflops=(value / world) * wl["gf"] / 1e3 if wl["gf"] else None)
+        # ---- end to end from pinned host memory
+        if with_e2e:
+            step_e2e()
+            barrier()
+            e0.record()
+            for _ in range(K):
+                r["last_loss"] = step_e2e()
+            e1.record()
+            barrier()
+            r["ms_e2e"] = max_over_ranks(e0.elapsed_time(e1)) / K
+            r["e2e_value"] = args.global_batch / (r["ms_e2e"] / 1e3)
+        # ---- roofline probe: one extra step with CUDA events around every launch (same stream, same work)
+        if with_probe:
+            ops.profile = []
+            f0 = ops.gemm_flops
+            step_resident()
+            torch.cuda.synchronize()
+            prof = ops.profile_summary()
+            ops.profile = None
+            probe_flops = ops.gemm_flops - f0
+            tot_ms = sum(v[1] for v in prof.values())
+            gemm = {k: v for k, v in prof.items() if k.startswith("md_gemm_bf16")}
+            gemm_ms = sum(v[1] for v in gemm.values())
+            attn_ms = sum(v[1] for k, v in prof.items() if k.startswith("md_attn"))
+            r.update(prof=prof, tot_ms=tot_ms, gemm_ms=gemm_ms, gemm_n=sum(v[0] for v in gemm.values()), attn_ms=attn_ms,
+                     gemm_tflops=probe_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None)
+        r["grad_exchange"] = None
+        if reducer is not None:
+            r["grad_exchange"] = (
+                (f"NCCL reduce-scatter (mean) of the flat fp32 gradient -> clip + AdamW on 1/{world} per rank -> all-gather of "
+                 f"the fp32 parameters (backbone range under the next step's patch-mixer forward)") if reducer.shard else
+                "NCCL all-reduce (mean) of the flat fp32 gradient, replicated clip + AdamW") + \
+                f"; overlap with backward={reducer.overlap}, {reducer.reserve} SMs left to NCCL while it overlaps"
+        r["peak_hbm_gb"] = torch.cuda.max_memory_allocated(device) / 2 ** 30
+        r["state_dict"] = ({k: v.detach().cpu() for k, v in ld.dit.state_dict().items()}
+                           if (rank == 0 and with_probe and not args.no_cpu_baseline and world == 1) else None)
+        del ld, opt, ops, resident, host, reducer, step_resident, step_e2e
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(device)
+        return r
+
     peaks = read_peaks()
-    ops.profile = []
-    f0 = ops.gemm_flops
-    step_resident()
-    torch.cuda.synchronize()
-    prof = ops.profile_summary()
-    ops.profile = None
-    probe_flops = ops.gemm_flops - f0
-    tot_ms = sum(v[1] for v in prof.values())
-    gemm = {k: v for k, v in prof.items() if k.startswith("md_gemm_bf16")}
-    gemm_ms = sum(v[1] for v in gemm.values())
-    gemm_n = sum(v[0] for v in gemm.values())
-    gemm_tflops = probe_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-    step_tflops = (value / world) * wl["gf"] / 1e3 if wl["gf"] else None
+    m = measure(wl, micro, K, W)
+    value, ms_step, launches, clocks = m["value"], m["ms_step"], m["launches"], m["clocks"]
+    prof, tot_ms, gemm_ms, gemm_n, gemm_tflops, step_tflops = (m["prof"], m["tot_ms"], m["gemm_ms"], m["gemm_n"],
+                                                               m["gemm_tflops"], m["step_tflops"])
+    e2e_value, ms_e2e, last_loss, h2d_bytes = m["e2e_value"], m["ms_e2e"], m["last_loss"], m["h2d_bytes"]
+
+    # ---- the other BASELINE.json configurations, briefly (N=1 default run only): 1 warm-up + 2 timed steps each
+    others = None
+    if world == 1 and args.workload == "c2" and not args.no_other_configs:
+        others = {}
+        for key in ("c3", "c4", "c5"):
+            try:
+                o = measure(WORKLOADS[key], min(WORKLOADS[key]["micro"], per_rank), 2, 1, with_e2e=False, with_probe=False)
+                others[key] = {"workload": WORKLOADS[key]["name"], "value": o["value"], "unit": "img/s",
+                               "ms_per_step": o["ms_step"], "steps": 2, "warmup": 1, "microbatch": o["micro"],
+                               "step_algorithmic_tflops_per_gpu": o["step_tflops"],
+                               "step_frac": o["step_tflops"] / peaks["bf16_sustained"] if o["step_tflops"] else None,
+                               "peak_hbm_gb": o["peak_hbm_gb"], "loss": o["loss"]}
+            except Exception as e:  # an auxiliary leg must never take the headline line down
+                others[key] = {"workload": WORKLOADS[key]["name"], "error": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         if args.profile_out:
@@ -350,7 +424,7 @@ def main():
             threads = host_threads()
             sample = 8 if wl["res"] == 32 else 2
             t0 = time.perf_counter()
-            sd = {k: v.detach().cpu() for k, v in ld.dit.state_dict().items()}
+            sd = m["state_dict"]
             ips, done = cpu_reference_img_per_s(wl, sample, 3, threads, sd, budget_s=25.0, warmup=1)
             cpu_base = {"value": ips, "unit": "img/s", "cores": threads, "kind": "port",
                         "sample": f"{done} x {sample}-image forward+backward after one warm-up pass, fp32 oracle.port on "
@@ -362,26 +436,28 @@ def main():
             "config": {"workload": wl["name"], "global_batch": args.global_batch, "per_gpu_batch": per_rank,
                        "microbatch": micro, "parallelism": f"dp{world}", "optimizer": "clip0.25+AdamW (fused, in step)",
                        "l2": "per-step working set (activations > 40 GB per microbatch) far exceeds the 126 MB L2",
-                       "grad_exchange": (f"NCCL all-reduce (mean) of the flat fp32 gradient, overlap={reducer.overlap}, "
-                                         f"{reducer.reserve} SMs left to NCCL while it overlaps") if reducer else None},
+                       "grad_exchange": m["grad_exchange"]},
             "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "loss": last_loss},
             "gpu_launches": launches,
-            "peak_hbm_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
+            "peak_hbm_gb": m["peak_hbm_gb"],
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (md_gemm_bf16)",
                          "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (gemm_tflops / peaks["bf16_sustained"]) if gemm_tflops else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full`
-                         # capture (profiles/r01_ncu_gemm_full.md, launch 0: M=16384 N=3072 K=1024 bf16 out, whose
-                         # algorithmic traffic is 33.6 + 6.3 + 100.7 = 140.6 MB; part of C is still in L2 when it ends)
-                         "traffic": NCU_GEMM_TRAFFIC_BYTES, "traffic_launch": "M=16384 N=3072 K=1024 epi=bf16, 103.1 GFLOP",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel, read from the
+                         # committed summary of an `ncu --set full` capture (profiles/ncu_gemm_traffic.json, written by
+                         # tools/summarize_ncu_raw.py); null when no capture of the current kernel is committed
+                         **read_gemm_traffic(),
                          "peak_source": peaks["source"] + " sustained", "launches_per_step": gemm_n,
                          "share_of_step_kernel_time": gemm_ms / tot_ms if tot_ms else None,
                          "step_algorithmic_tflops_per_gpu": step_tflops,
                          "step_frac": (step_tflops / peaks["bf16_sustained"]) if step_tflops else None},
             "cpu_baseline": cpu_base,
-            "loss": float(loss_t),
+            "loss": m["loss"],
+            "attention_share_of_step_kernel_time": m["attn_ms"] / tot_ms if tot_ms else None,
+            "other_configs": others,
+            "stock_torch_gpu": stock_torch_leg(args) if (world == 1 and not args.no_stock_torch) else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -125,6 +125,15 @@ MD_API int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_t ld
                        const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
                        void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                        int64_t Tq, int64_t Tk, int64_t hd, void* stream);
+/* The mma.sync (m16n8k16) kernels md_attn_fwd / md_attn_bwd fall back to outside the tcgen05 envelope (head_dim 32,
+ * Tk > 256) or where they measured faster; callable directly for A/B runs (tools/attn_micro.py). */
+MD_API int md_attn_fwd_mma(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                           int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
+                           void* stream);
+MD_API int md_attn_bwd_mma(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                           const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
+                           void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
+                           int64_t Tq, int64_t Tk, int64_t hd, void* stream);
 /* The same forward and backward on the 5th-generation tensor cores (tcgen05.mma, accumulators and S / dP tiles in
  * TMEM, operands by TMA; csrc/attn_tc.cu) for head_dim 64 and Tk <= 256 -- every sequence of the res-256 configs.
  * Persistent, warp-specialised kernels; no delta scratch (derived from o and dout).  md_attn_fwd / md_attn_bwd
@@ -136,6 +145,9 @@ MD_API int md_attn_bwd_tc(const void* dout, int64_t lddo, const void* q, int64_t
                           const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, void* dq,
                           int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                           int64_t Tq, int64_t Tk, int64_t hd, void* stream);
+/* Diagnostics: with MD_ATTN_DEBUG=1 in the environment CTA 0 of the tcgen05 attention kernels logs clock64() stamps at
+ * phase boundaries; this copies the log (<= 4096 int64) of the last launch to host memory (tools/attn_timeline.py). */
+MD_API int md_attn_debug_dump(long long* out, int64_t n);
 /* High-precision mode (prec = 1): the same contract with fp32 q / k / v / o / gradients, plain fp32 FMAs. */
 MD_API int md_attn_fwd_f32(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                            int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,

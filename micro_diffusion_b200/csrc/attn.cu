@@ -7,6 +7,8 @@
 // the deterministic two-kernel split (dK/dV per key tile, dQ per query tile; no atomics).
 // SDPA is 2.7 % of the step's FLOPs at the benchmark configuration, so the
 // tcgen05 rewrite of this kernel ranks after the GEMM work; DESIGN.md tracks it.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace md {
@@ -827,13 +829,52 @@ static int check_attn(const char* what, int64_t B, int64_t H, int64_t Tq, int64_
 }  // namespace md
 
 using namespace md;
+// per-shape choice when MD_ATTN_TC is unset (B200 micro-benchmarks, B = 256, H = 12 / 16, profiles/r02_attn_micro_tc_*.log)
+#define MD_ATTN_TC_FWD_AUTO(Tq, Tk) (true)
+#define MD_ATTN_TC_BWD_AUTO(Tq, Tk) ((Tk) > 128)
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
+// Dispatch between the tcgen05 kernels (attn_tc.cu: head_dim 64, Tk <= 256) and the mma.sync kernels of this file.
+// MD_ATTN_TC: "1" = tcgen05 wherever its envelope allows, "0" = never, unset = per-shape choice from the B200
+// measurements in profiles/r02_attn_micro_*.log (both paths satisfy the same contract and the same tests).
+static int attn_tc_policy() {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = getenv("MD_ATTN_TC");
+    mode = e ? atoi(e) : -1;
+  }
+  return mode;
+}
+static bool use_tc_fwd(int64_t Tq, int64_t Tk, int64_t hd, uintptr_t align, int64_t lds) {
+  if (hd != 64 || Tk > 256 || (align & 15) != 0 || (lds % 8) != 0) return false;
+  const int m = attn_tc_policy();
+  if (m >= 0) return m != 0;
+  return MD_ATTN_TC_FWD_AUTO(Tq, Tk);
+}
+static bool use_tc_bwd(int64_t Tq, int64_t Tk, int64_t hd, uintptr_t align, int64_t lds) {
+  if (hd != 64 || Tk > 256 || (align & 15) != 0 || (lds % 8) != 0) return false;
+  const int m = attn_tc_policy();
+  if (m >= 0) return m != 0;
+  return MD_ATTN_TC_BWD_AUTO(Tq, Tk);
+}
+
 extern "C" int md_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                            int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
                            void* stream) {
+  if (int rc = check_attn("md_attn_fwd: bad sizes", B, H, Tq, Tk, hd, (ldq | ldk | ldv | ldo))) return rc;
+  if (B == 0) return 0;
+  if (!q || !k || !v || !o || !lse) return md_set_error(MD_ERR_INVALID, "md_attn_fwd: null pointer");
+  if (use_tc_fwd(Tq, Tk, hd, reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                 reinterpret_cast<uintptr_t>(o), ldq | ldk | ldv | ldo))
+    return md_attn_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Tq, Tk, hd, stream);
+  return md_attn_fwd_mma(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Tq, Tk, hd, stream);
+}
+
+extern "C" int md_attn_fwd_mma(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                               int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
+                               void* stream) {
   if (int rc = check_attn("md_attn_fwd: bad sizes", B, H, Tq, Tk, hd, (ldq | ldk | ldv | ldo))) return rc;
   if (B == 0) return 0;
   if (!q || !k || !v || !o || !lse) return md_set_error(MD_ERR_INVALID, "md_attn_fwd: null pointer");
@@ -861,6 +902,23 @@ extern "C" int md_attn_bwd(const void* dout, int64_t lddo, const void* q, int64_
                            const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
                            void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                            int64_t Tq, int64_t Tk, int64_t hd, void* stream) {
+  if (int rc = check_attn("md_attn_bwd: bad sizes", B, H, Tq, Tk, hd, (lddo | ldq | ldk | ldv | ldo | lddq | lddk | lddv)))
+    return rc;
+  if (B == 0) return 0;
+  if (!dout || !q || !k || !v || !o || !lse || !delta || !dq || !dk || !dv)
+    return md_set_error(MD_ERR_INVALID, "md_attn_bwd: null pointer");
+  if (use_tc_bwd(Tq, Tk, hd, reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                 reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(dq) |
+                 reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv), lddo | ldq | ldk | ldv | ldo | lddq | lddk | lddv))
+    return md_attn_bwd_tc(dout, lddo, q, ldq, k, ldk, v, ldv, o, ldo, lse, dq, lddq, dk, lddk, dv, lddv, B, H, Tq, Tk, hd, stream);
+  return md_attn_bwd_mma(dout, lddo, q, ldq, k, ldk, v, ldv, o, ldo, lse, delta, dq, lddq, dk, lddk, dv, lddv, B, H, Tq, Tk, hd,
+                         stream);
+}
+
+extern "C" int md_attn_bwd_mma(const void* dout, int64_t lddo, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                               const void* v, int64_t ldv, const void* o, int64_t ldo, const float* lse, float* delta,
+                               void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
+                               int64_t Tq, int64_t Tk, int64_t hd, void* stream) {
   if (int rc = check_attn("md_attn_bwd: bad sizes", B, H, Tq, Tk, hd, (lddo | ldq | ldk | ldv | ldo | lddq | lddk | lddv)))
     return rc;
   if (B == 0) return 0;

@@ -21,9 +21,11 @@
 // h, rows 64-127 head h+1, the keys of both heads are stacked along N (S is 128 x 2*keys, each row uses its own head's
 // column range) and P is written block-diagonal so that one PV chain over the stacked V tiles serves both heads.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tensormap.cuh"
 
 namespace md {
 namespace attn_tc {
@@ -31,7 +33,8 @@ namespace attn_tc {
 constexpr int kQ = 128;               // query rows per tile (UMMA M)
 constexpr int kHd = 64;               // head_dim == one 128-byte swizzle row of bf16
 constexpr int kMaxCols = 256;         // S columns per tile (keys, or 2 x keys in packed mode)
-constexpr int kThreads = 384;
+constexpr int kThreads = 384;            // backward: 4 control warps + 2 groups of 4
+constexpr int kFwdThreads = 640;         // forward: 4 control warps + 2 groups of 8 (two threads per query row)
 constexpr int kTmemCols = 512;
 constexpr int kBytesQ = kQ * kHd * 2;            // 16 KB
 constexpr int kStageQKP = 64 * 1024;             // Q (16 KB) + K (<= 32 KB); later P (<= 64 KB = 4 atoms of 64 keys)
@@ -39,9 +42,16 @@ constexpr int kStageV = 32 * 1024;
 constexpr int kStage = kStageQKP + kStageV;      // 96 KB
 constexpr int kBytesPAtom = kQ * 64 * 2;         // 16 KB: 128 rows x 64 keys
 constexpr int kOffBar = 2 * kStage;
-constexpr int kSmemBytes = kOffBar + 256 + 1024;
+constexpr int kOffXch = kOffBar + 256;            // 2 groups x [max | sum] x 2 halves x 128 rows of fp32 = 4 KB
+constexpr int kSmemBytes = kOffXch + 4096 + 1024;
+
+// Optional phase timeline (MD_ATTN_DEBUG=1): block 0 logs clock64() at fixed points; md_attn_debug_dump() reads it back.
+__device__ long long g_dbg[8 * 512];
+#define DBG(slot, idx) \
+  do { if (p.dbg && blockIdx.x == 0 && (idx) < 512) g_dbg[(slot) * 512 + (idx)] = clock64(); } while (0)
 
 struct FwdParams {
+  int dbg;
   __nv_bfloat16* o;
   long long ldo;
   float* lse;
@@ -69,7 +79,7 @@ __device__ __forceinline__ void decode_tile(long long t, const FwdParams& p, int
   h0 = p.packed ? 2 * ht : ht;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -85,6 +95,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pad = p.n_pad;                          // keys of one head, padded to 16
+  const int Tk = p.Tk;
+  const float sl2 = p.scale_log2;
   const int n_s = p.packed ? 2 * n_pad : n_pad;       // S columns / PV reduction length of a tile
 
   if (warp == 0 && lane == 0) {
@@ -97,9 +109,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&qk_full[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 8);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_free[i], 4);
+      mbar_init(&o_free[i], 8);
     }
     mbar_fence_init();
   }
@@ -116,7 +128,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
         const int s = it & 1;
         const uint32_t n = it >> 1;
+        DBG(0, 2 * it);
         if (it >= 2) mbar_wait_sleep(&o_full[s], (n - 1) & 1);  // PV of the tile two back has read P and V of this stage
+        DBG(0, 2 * it + 1);
         int b, h0, qb;
         decode_tile(t, p, b, h0, qb);
         uint8_t* sQ = smem + s * kStage;
@@ -139,54 +153,87 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // The whole warp walks the loop (waits, descriptor arithmetic: warp-uniform values stay in uniform registers) and one
+    // lane issues: with the role gated on a single lane the compiler rebuilt every operand through R2UR broadcast loops and
+    // a UTCHMMA issue cost ~100 cycles -- more than a 128x64x16 MMA takes to execute.
+    {
       const uint32_t idesc_s = umma_idesc_bf16(kQ, n_s, false, false);   // Q, K both K-major (head_dim contiguous)
       const uint32_t idesc_o = umma_idesc_bf16(kQ, kHd, false, true);    // P K-major, V MN-major (head_dim contiguous)
       const int ksteps = n_s / 16;
       auto issue_pv = [&](uint32_t j) {
         const int s = j & 1;
         const uint32_t n = j >> 1;
+        DBG(1, 6 * j + 3);
         mbar_wait_sleep(&p_full[s], n & 1);
         mbar_wait_sleep(&v_full[s], n & 1);
+        DBG(1, 6 * j + 4);
         tc_fence_after();
         const uint32_t ap = smem_u32(smem + s * kStage);
         const uint32_t av = ap + kStageQKP;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t da = umma_smem_desc(ap + (kk >> 2) * kBytesPAtom + (kk & 3) * 32, 16, 1024);
-          const uint64_t db = umma_smem_desc(av + kk * (16 * 128), 64 * 128, 1024);
-          umma_bf16(tmem_base + s * kMaxCols, da, db, idesc_o, kk > 0 ? 1u : 0u);
+        // descriptors advance by plain adds on the 14-bit (address >> 4) field: one UTCHMMA costs the issuing thread a few
+        // instructions instead of a full descriptor rebuild (which made the issue loop, not the tensor pipe, the limit)
+        const uint64_t da0 = umma_smem_desc(ap, 16, 1024);
+        const uint64_t db0 = umma_smem_desc(av, 64 * 128, 1024);
+        // Consecutive MMAs into the SAME accumulator serialise on the accumulator's read-modify-write latency (~100 cycles,
+        // three times what a 128x64x16 MMA takes to execute): the reduction over the keys is therefore spread over four
+        // accumulators (k-step mod 4 -> columns 64 * j of the dead S buffer) that the epilogue adds up.
+        const uint32_t d = tmem_base + s * kMaxCols;
+        for (int at = 0; at * 4 < ksteps; ++at) {
+          const uint64_t da = da0 + static_cast<uint64_t>(at) * (kBytesPAtom >> 4);
+          const uint64_t db = db0 + static_cast<uint64_t>(at) * (4 * 16 * 128 >> 4);
+          const uint32_t acc = at > 0 ? 1u : 0u;
+          if (elect_one()) umma_bf16(d, da, db, idesc_o, acc);
+          if (at * 4 + 1 < ksteps) { if (elect_one()) umma_bf16(d + 64, da + 2, db + 128, idesc_o, acc); }
+          if (at * 4 + 2 < ksteps) { if (elect_one()) umma_bf16(d + 128, da + 4, db + 256, idesc_o, acc); }
+          if (at * 4 + 3 < ksteps) { if (elect_one()) umma_bf16(d + 192, da + 6, db + 384, idesc_o, acc); }
         }
-        umma_commit(&o_full[s]);
+        if (elect_one()) umma_commit(&o_full[s]);
+        DBG(1, 6 * j + 5);
       };
       uint32_t it = 0;
       for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
         const int s = it & 1;
         const uint32_t n = it >> 1;
+        DBG(1, 6 * it);
         mbar_wait_sleep(&qk_full[s], n & 1);
         if (it >= 2) mbar_wait_sleep(&o_free[s], (n - 1) & 1);  // O of the tile two back has left this TMEM buffer
+        DBG(1, 6 * it + 1);
         tc_fence_after();
         const uint32_t aq = smem_u32(smem + s * kStage);
-        const uint32_t ak = aq + kBytesQ;
+        const uint64_t dq0 = umma_smem_desc(aq, 16, 1024), dk0 = umma_smem_desc(aq + kBytesQ, 16, 1024);
 #pragma unroll
         for (int ks = 0; ks < kHd / 16; ++ks)
-          umma_bf16(tmem_base + s * kMaxCols, umma_smem_desc(aq + ks * 32, 16, 1024),
-                    umma_smem_desc(ak + ks * 32, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
-        umma_commit(&s_full[s]);
+          if (elect_one()) umma_bf16(tmem_base + s * kMaxCols, dq0 + 2 * ks, dk0 + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
+        if (elect_one()) umma_commit(&s_full[s]);
+        DBG(1, 6 * it + 2);
         if (it >= 1) issue_pv(it - 1);
       }
       if (it >= 1) issue_pv(it - 1);
     }
   } else if (warp >= 4) {
     // ================================ softmax / epilogue groups ================================
-    const int grp = (warp - 4) >> 2;              // group g handles tiles with (iteration & 1) == g -> stage g
+    // A group = 8 warps = two threads per query row: warps 0-3 of the group take the first half of the row's key columns,
+    // warps 4-7 the second half (each warp may only touch the TMEM lane quarter warp % 4).  One warp issuing MUFU.EX2 back
+    // to back gets one every ~18 cycles while the pipe takes one every 8: with four softmax warps per scheduler (two groups
+    // x two halves) the exp pipe stays busy.  The halves exchange the partial row maximum and row sum through shared memory.
+    const int gw = (warp - 4) & 7;
+    const int grp = (warp - 4) >> 3;              // group g handles tiles with (iteration & 1) == g -> stage g
+    const int half = gw >> 2;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch (hardware rule)
     const int row = quarter * 32 + lane;          // row inside the tile == TMEM lane
     const int hi = (p.packed && row >= 64) ? 1 : 0;
-    const int col0 = hi ? n_pad : 0;              // first S column of this row's head
-    const int chunks = (n_pad + 31) / 32;
+    const int split = min(n_pad, ((n_pad >> 1) + 15) & ~15);   // columns [0, split) -> half 0, [split, n_pad) -> half 1
+    const int my0 = half ? split : 0;             // this thread's columns inside its head's range: [my0, my1)
+    const int my1 = half ? n_pad : split;
+    const int col0 = (hi ? n_pad : 0) + my0;      // first S column of this thread
+    const int chunks = (my1 - my0 + 31) / 32;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + grp * kMaxCols;
-    uint8_t* sP = smem + grp * kStage;
+    const uint32_t prow = smem_u32(smem + grp * kStage) + row * 128;   // this row of P (shared-window address)
+    const int sw = row & 7;
+    float* xch = reinterpret_cast<float*>(smem + kOffXch) + grp * 512;   // [max | sum][half][128 rows]
     const int s = grp;
+    const int nacc = min(4, n_s / 16);            // PV accumulators in use
+    const uint32_t bar_id = 1 + grp;
     uint32_t n = 0;
     for (long long t = blockIdx.x + 1LL * grp * gridDim.x; t < p.tiles; t += 2LL * gridDim.x, ++n) {
       int b, h0, qb;
@@ -195,126 +242,114 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int qrow = p.packed ? (row & 63) : qb * kQ + row;
       const bool q_ok = qrow < p.Tq;
 
+      const int dslot = 2 + grp, dlog = (gw == 0 && lane == 0);
+      if (dlog) DBG(dslot, 10 * n);
       mbar_wait_sleep(&s_full[s], n & 1);
+      if (dlog) DBG(dslot, 10 * n + 1);
       tc_fence_after();
-      // ---- pass 1: row maximum.  Two register arrays alternate so that the next 32 columns are in flight while the
-      // current ones are reduced (tcgen05.wait::ld waits for ALL outstanding loads: issue order = wait, issue, use).
-      float m;
-      {
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
-        auto red = [&](const uint32_t (&r)[32], int c) {
-          if ((c + 1) * 32 <= p.Tk) {
+      // ---- pass 1: maximum over this thread's columns, then over both halves
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
+      for (int c = 0; c < chunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + col0 + c * 32, r);
+        tmem_ld_wait();
+        const int kc = my0 + c * 32;              // key index of column 0 of this chunk
+        if (kc + 32 <= my1 && kc + 32 <= Tk) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
-          } else {
+          for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < p.Tk) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
-          }
-        };
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(trow + col0, ra);
-        for (int c = 0; c < chunks; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < chunks) tmem_ld_32x32(trow + col0 + (c + 1) * 32, rb);
-          red(ra, c);
-          if (c + 1 < chunks) {
-            tmem_ld_wait();
-            if (c + 2 < chunks) tmem_ld_32x32(trow + col0 + (c + 2) * 32, ra);
-            red(rb, c + 1);
-          }
+          for (int j = 0; j < 32; ++j)
+            if (kc + j < my1 && kc + j < Tk) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(r[j]));
         }
-        m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       }
-      const float m2 = m * p.scale_log2;
-      // ---- pass 2: P = exp2(s * scale - max), row sum, bf16 P into the swizzled K-major atoms
+      float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      xch[half * 128 + row] = m;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      m = fmaxf(m, xch[(half ^ 1) * 128 + row]);
+      const float m2 = m * sl2;
+      if (dlog) DBG(dslot, 10 * n + 2);
+      // ---- pass 2: P = exp2(s * scale - max), partial row sum, bf16 P into the swizzled K-major atoms
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        uint8_t* prow = sP + row * 128;
-        const int sw = row & 7;
-        auto emit = [&](uint32_t (&r)[32], int c) {
-          float pv[32];
-          if ((c + 1) * 32 <= p.Tk) {
+      for (int c = 0; c < chunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + col0 + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+        const int kc = my0 + c * 32;
+        if (kc + 32 <= my1 && kc + 32 <= Tk) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -m2));
-          } else {
+          for (int j = 0; j < 32; ++j) pv[j] = ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -m2));
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              pv[j] = (c * 32 + j < p.Tk) ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -m2)) : 0.f;
-          }
+          for (int j = 0; j < 32; ++j)
+            pv[j] = (kc + j < my1 && kc + j < Tk) ? ex2_approx(fmaf(__uint_as_float(r[j]), sl2, -m2)) : 0.f;
+        }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ls[j & 3] += pv[j];
-          const int k8 = (col0 >> 3) + c * 4;
+        for (int j = 0; j < 32; ++j) ls[j & 3] += pv[j];
+        const int k8 = (col0 >> 3) + c * 4;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (c * 32 + g * 8 < n_pad) {   // n_pad is a multiple of 16: whole 8-key groups
-              const int key8 = k8 + g;
-              uint4 w;
-              w.x = pack2(pv[8 * g + 0], pv[8 * g + 1]);
-              w.y = pack2(pv[8 * g + 2], pv[8 * g + 3]);
-              w.z = pack2(pv[8 * g + 4], pv[8 * g + 5]);
-              w.w = pack2(pv[8 * g + 6], pv[8 * g + 7]);
-              *reinterpret_cast<uint4*>(prow + (key8 >> 3) * kBytesPAtom + (((key8 & 7) ^ sw) << 4)) = w;
-            }
-          }
-        };
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(trow + col0, ra);
-        for (int c = 0; c < chunks; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < chunks) tmem_ld_32x32(trow + col0 + (c + 1) * 32, rb);
-          emit(ra, c);
-          if (c + 1 < chunks) {
-            tmem_ld_wait();
-            if (c + 2 < chunks) tmem_ld_32x32(trow + col0 + (c + 2) * 32, ra);
-            emit(rb, c + 1);
+        for (int g = 0; g < 4; ++g) {
+          if (kc + g * 8 < my1) {                 // split and n_pad are multiples of 16: whole 8-key groups
+            const int key8 = k8 + g;
+            st_shared_v4(prow + (key8 >> 3) * kBytesPAtom + (((key8 & 7) ^ sw) << 4), pack2(pv[8 * g + 0], pv[8 * g + 1]),
+                         pack2(pv[8 * g + 2], pv[8 * g + 3]), pack2(pv[8 * g + 4], pv[8 * g + 5]),
+                         pack2(pv[8 * g + 6], pv[8 * g + 7]));
           }
         }
       }
-      const float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      if (p.packed) {  // block-diagonal P: zero this row's columns of the other head
-        const int z0 = (hi ? 0 : n_pad) >> 3;
-        for (int g = 0; g < (n_pad >> 3); ++g) {
+      const float lpart = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      xch[256 + half * 128 + row] = lpart;        // read by the other half after o_full (ordered by the barrier chain)
+      if (dlog) DBG(dslot, 10 * n + 3);
+      if (p.packed) {  // block-diagonal P: zero this thread's share of the row's columns of the other head
+        const int z0 = ((hi ? 0 : n_pad) + my0) >> 3;
+        for (int g = 0; g < ((my1 - my0) >> 3); ++g) {
           const int key8 = z0 + g;
-          *reinterpret_cast<uint4*>(sP + (key8 >> 3) * kBytesPAtom + row * 128 + (((key8 & 7) ^ (row & 7)) << 4)) =
-              make_uint4(0, 0, 0, 0);
+          st_shared_v4(prow + (key8 >> 3) * kBytesPAtom + (((key8 & 7) ^ sw) << 4), 0u, 0u, 0u, 0u);
         }
       }
       fence_proxy_async_smem();  // the UMMA reads P through the async proxy
+      if (dlog) DBG(dslot, 10 * n + 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[s]);
+      if (dlog) DBG(dslot, 10 * n + 5);
 
-      // ---- epilogue: O / rowsum
+      // ---- epilogue: this half's 32 columns of O / rowsum
       mbar_wait_sleep(&o_full[s], n & 1);
+      if (dlog) DBG(dslot, 10 * n + 6);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(trow, r0);
-      tmem_ld_32x32(trow + 32, r1);
+      uint32_t r0[32];
+      tmem_ld_32x32(trow + half * 32, r0);
+      const float l = lpart + xch[256 + (half ^ 1) * 128 + row];
       tmem_ld_wait();
+      for (int j = 1; j < nacc; ++j) {            // the other PV accumulators (k-step mod 4)
+        uint32_t rj[32];
+        tmem_ld_32x32(trow + j * 64 + half * 32, rj);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r0[e] = __float_as_uint(__uint_as_float(r0[e]) + __uint_as_float(rj[e]));
+      }
+      if (dlog) DBG(dslot, 10 * n + 7);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[s]);
+      if (dlog) DBG(dslot, 10 * n + 8);
       if (q_ok) {
-        const float inv = 1.f / l;
-        __nv_bfloat16* dst = p.o + (static_cast<long long>(b) * p.Tq + qrow) * p.ldo + h * kHd;
+        const float inv = __fdividef(1.f, l);
+        __nv_bfloat16* dst = p.o + (static_cast<long long>(b) * p.Tq + qrow) * p.ldo + h * kHd + half * 32;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint32_t* rr = g < 4 ? r0 : r1;
-          const int e = (g & 3) * 8;
-          __nv_bfloat162 v0 = __floats2bfloat162_rn(__uint_as_float(rr[e + 0]) * inv, __uint_as_float(rr[e + 1]) * inv);
-          __nv_bfloat162 v1 = __floats2bfloat162_rn(__uint_as_float(rr[e + 2]) * inv, __uint_as_float(rr[e + 3]) * inv);
-          __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(rr[e + 4]) * inv, __uint_as_float(rr[e + 5]) * inv);
-          __nv_bfloat162 v3 = __floats2bfloat162_rn(__uint_as_float(rr[e + 6]) * inv, __uint_as_float(rr[e + 7]) * inv);
+        for (int g = 0; g < 4; ++g) {
           uint4 w;
-          w.x = *reinterpret_cast<uint32_t*>(&v0);
-          w.y = *reinterpret_cast<uint32_t*>(&v1);
-          w.z = *reinterpret_cast<uint32_t*>(&v2);
-          w.w = *reinterpret_cast<uint32_t*>(&v3);
+          w.x = pack2(__uint_as_float(r0[8 * g + 0]) * inv, __uint_as_float(r0[8 * g + 1]) * inv);
+          w.y = pack2(__uint_as_float(r0[8 * g + 2]) * inv, __uint_as_float(r0[8 * g + 3]) * inv);
+          w.z = pack2(__uint_as_float(r0[8 * g + 4]) * inv, __uint_as_float(r0[8 * g + 5]) * inv);
+          w.w = pack2(__uint_as_float(r0[8 * g + 6]) * inv, __uint_as_float(r0[8 * g + 7]) * inv);
           *reinterpret_cast<uint4*>(dst + g * 8) = w;
         }
-        p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + qrow] = m2 + log2f(l);
+        if (half == 0) p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + qrow] = m2 + __log2f(l);
       }
+      if (dlog) DBG(dslot, 10 * n + 9);
     }
   }
 
@@ -329,26 +364,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // bf16 [batch][rows][cols] view, box = [1][box_rows][64 columns], 128B swizzle (the encoding of the GEMM operand maps).
 int make_map(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long batch, long long ld,
              int box_rows) {
-  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(rows * ld) * 2};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return md_set_error(MD_ERR_CUDA, "attention (tcgen05): cuTensorMapEncodeTiled failed");
+  const TmapKey key = make_tmap_key(ptr, cols, rows, batch, ld, rows * ld, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (cached_tensor_map(map, key) != CUDA_SUCCESS)
+    return md_set_error(MD_ERR_CUDA, "attention (tcgen05): cuTensorMapEncodeTiled failed");
   return 0;
 }
 
@@ -365,6 +384,13 @@ int sm_count_cached() {
 }  // namespace attn_tc
 }  // namespace md
 
+// diagnostics: copy the phase timeline of the last MD_ATTN_DEBUG=1 launch (8 slots x 512 clock64 stamps) to the host
+extern "C" int md_attn_debug_dump(long long* out, int64_t n) {
+  if (!out || n <= 0 || n > 8 * 512) return md::md_set_error(MD_ERR_INVALID, "md_attn_debug_dump: bad argument");
+  cudaError_t e = cudaMemcpyFromSymbol(out, md::attn_tc::g_dbg, n * sizeof(long long));
+  return e == cudaSuccess ? 0 : md::md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
+}
+
 extern "C" int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                               int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t hd,
                               void* stream) {
@@ -379,6 +405,9 @@ extern "C" int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t
   if ((align & 15) != 0 || ((ldq | ldk | ldv | ldo) % 8) != 0)
     return md_set_error(MD_ERR_INVALID, "md_attn_fwd_tc: operands must be 16-byte aligned with pitches % 8 == 0");
   FwdParams p;
+  static int dbg_env = -1;
+  if (dbg_env < 0) { const char* e = getenv("MD_ATTN_DEBUG"); dbg_env = e ? atoi(e) : 0; }
+  p.dbg = dbg_env;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.ldo = ldo;
   p.lse = lse;
@@ -401,7 +430,7 @@ extern "C" int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t
   }
   const long long sms = sm_count_cached();
   const unsigned grid = static_cast<unsigned>(p.tiles < sms ? p.tiles : sms);
-  attn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  attn_fwd_tc_kernel<<<grid, kFwdThreads, kSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   return check_launch("md_attn_fwd_tc");
 }
 
@@ -434,12 +463,15 @@ constexpr int kBwdOffdO = 96 * 1024;              // [2] x 16 KB
 constexpr int kBwdOffP = 128 * 1024;              // 32 KB : 2 atoms (128 queries x 64 keys)
 constexpr int kBwdOffdS = 160 * 1024;             // 32 KB
 constexpr int kBwdOffBar = 192 * 1024;
-constexpr int kBwdSmemBytes = kBwdOffBar + 256 + 1024;
+constexpr int kBwdOffStats = kBwdOffBar + 256;          // 2 x 128 x (lse, delta)
+constexpr int kBwdOffOld = kBwdOffStats + 2048;         // 256 threads x 64 B: dQ partial of the previous key block
+constexpr int kBwdSmemBytes = kBwdOffOld + 16384 + 1024;
 constexpr int kTile = 16 * 1024;
 // TMEM columns
 constexpr uint32_t kColS = 0, kColdP = 64, kColBuf = 128, kColdQ = 256, kColdK = 320, kColdV = 384;
 
 struct BwdParams {
+  int dbg;
   const __nv_bfloat16* dout; long long lddo;
   const __nv_bfloat16* o; long long ldo;
   const float* lse;
@@ -451,45 +483,54 @@ struct BwdParams {
   float scale, scale_log2;
 };
 
-struct BwdIter {  // position of iteration g inside this CTA's sequence
+// Position of an iteration inside this CTA's sequence (sample / head tile outer, key block, query block inner), advanced
+// incrementally: the only integer divisions happen once per (sample, head tile).
+struct BwdPos {
   int b, h0, kb, qb, n_kb, n0, n1;
   uint32_t u;       // key-block phase counter (one per (item, kb))
+  long long item;
   bool first, last; // first / last query block of the phase
 };
-
-__device__ __forceinline__ BwdIter bwd_iter(uint32_t g, const BwdParams& p) {
-  BwdIter it;
-  const uint32_t ipi = p.KB * p.QB;
-  const long long item = blockIdx.x + static_cast<long long>(g / ipi) * gridDim.x;
-  const uint32_t j = g % ipi;
-  it.kb = j / p.QB;
-  it.qb = j % p.QB;
-  it.u = g / p.QB;
-  it.first = it.qb == 0;
-  it.last = it.qb == p.QB - 1;
-  const int ht = static_cast<int>(item % p.head_tiles);
-  it.b = static_cast<int>(item / p.head_tiles);
-  it.h0 = p.packed ? 2 * ht : ht;
+__device__ __forceinline__ void bwd_pos_item(BwdPos& s, const BwdParams& p) {
+  const int ht = static_cast<int>(s.item % p.head_tiles);
+  s.b = static_cast<int>(s.item / p.head_tiles);
+  s.h0 = p.packed ? 2 * ht : ht;
+}
+__device__ __forceinline__ void bwd_pos_block(BwdPos& s, const BwdParams& p) {
   if (p.packed) {
-    it.n_kb = 2 * p.n_pad; it.n0 = p.n_pad; it.n1 = p.n_pad;
+    s.n_kb = 2 * p.n_pad; s.n0 = p.n_pad; s.n1 = p.n_pad;
   } else {
-    it.n_kb = min(128, p.n_pad - it.kb * 128);
-    it.n0 = ((it.n_kb >> 1) + 15) & ~15;
-    it.n1 = it.n_kb - it.n0;
+    s.n_kb = min(128, p.n_pad - s.kb * 128);
+    s.n0 = ((s.n_kb >> 1) + 15) & ~15;
+    s.n1 = s.n_kb - s.n0;
   }
-  return it;
+  s.first = s.qb == 0;
+  s.last = s.qb == p.QB - 1;
+}
+__device__ __forceinline__ void bwd_pos_init(BwdPos& s, const BwdParams& p) {
+  s.item = blockIdx.x; s.kb = 0; s.qb = 0; s.u = 0;
+  bwd_pos_item(s, p);
+  bwd_pos_block(s, p);
+}
+__device__ __forceinline__ void bwd_pos_next(BwdPos& s, const BwdParams& p) {
+  if (++s.qb == p.QB) {
+    s.qb = 0;
+    ++s.u;
+    if (++s.kb == p.KB) {
+      s.kb = 0;
+      s.item += gridDim.x;
+      bwd_pos_item(s, p);
+    }
+  }
+  bwd_pos_block(s, p);
 }
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float (&f)[8]) {
-  __nv_bfloat162 v0 = __floats2bfloat162_rn(f[0], f[1]);
-  __nv_bfloat162 v1 = __floats2bfloat162_rn(f[2], f[3]);
-  __nv_bfloat162 v2 = __floats2bfloat162_rn(f[4], f[5]);
-  __nv_bfloat162 v3 = __floats2bfloat162_rn(f[6], f[7]);
   uint4 w;
-  w.x = *reinterpret_cast<uint32_t*>(&v0);
-  w.y = *reinterpret_cast<uint32_t*>(&v1);
-  w.z = *reinterpret_cast<uint32_t*>(&v2);
-  w.w = *reinterpret_cast<uint32_t*>(&v3);
+  w.x = pack2(f[0], f[1]);
+  w.y = pack2(f[2], f[3]);
+  w.z = pack2(f[4], f[5]);
+  w.w = pack2(f[6], f[7]);
   *reinterpret_cast<uint4*>(dst) = w;
 }
 
@@ -508,11 +549,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* pds_full = bars + 12;    // P / dS of the iteration in shared memory (8 warps)
   uint64_t* dq_free = bars + 13;     // dQ of the previous iteration read back (8 warps)
   uint64_t* acc_free = bars + 14;    // dK / dV of the previous phase read back (8 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* st_full = bars + 15;     // [2] lse / delta of an iteration's 128 query rows in shared memory (2 warps)
+  uint64_t* st_free = bars + 17;     // [2] ... read by the groups (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  float2* stats = reinterpret_cast<float2*>(smem + kBwdOffStats);  // [2][128] (lse in the log2 domain, delta)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t my_items = blockIdx.x < p.items ? static_cast<uint32_t>((p.items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const uint32_t total = my_items * p.KB * p.QB;
+  const int Tq = p.Tq, Tk = p.Tk, H = p.H;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -528,6 +573,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&mma_done[i], 1);
       mbar_init(&sdp_full[i], 1);
       mbar_init(&sdp_free[i], 4);
+      mbar_init(&st_full[i], 2);
+      mbar_init(&st_free[i], 8);
     }
     mbar_init(pds_full, 8);
     mbar_init(dq_free, 8);
@@ -543,8 +590,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      for (uint32_t g = 0; g < total; ++g) {
-        const BwdIter it = bwd_iter(g, p);
+      BwdPos it;
+      bwd_pos_init(it, p);
+      for (uint32_t g = 0; g < total; ++g, bwd_pos_next(it, p)) {
         if (it.first) {
           const int ks = it.u & 1;
           if (it.u >= 2) mbar_wait_sleep(&kv_free[ks], ((it.u >> 1) - 1) & 1);
@@ -580,83 +628,151 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0 && total > 0) {
+    if (total > 0) {  // whole warp walks the loop, one lane issues (see the forward kernel)
       const uint32_t idesc_mn = umma_idesc_bf16(kQ, kHd, true, true);    // dV, dK: A and B MN-major
       const uint32_t idesc_dq = umma_idesc_bf16(kQ, kHd, false, true);   // dQ: A K-major, B MN-major
-      auto issue_sdp = [&](uint32_t g) {
-        const BwdIter it = bwd_iter(g, p);
+      auto issue_sdp = [&](uint32_t g, const BwdPos& it) {
         const int st = g & 1, ks = it.u & 1;
+        DBG(4, 8 * g);
         mbar_wait_sleep(&qdo_full[st], (g >> 1) & 1);
         if (it.first) mbar_wait_sleep(&kv_full[ks], (it.u >> 1) & 1);
+        DBG(4, 8 * g + 1);
         const uint32_t aQ = smem_u32(smem + kBwdOffQ + st * kTile), adO = smem_u32(smem + kBwdOffdO + st * kTile);
         const uint32_t aK = smem_u32(smem + kBwdOffK + ks * kTile), aV = smem_u32(smem + kBwdOffV + ks * kTile);
-        for (int c = 0; c < 2; ++c) {
-          const int n_c = c ? it.n1 : it.n0;
-          const int colbase = c ? it.n0 : 0;
-          if (g > 0) mbar_wait_sleep(&sdp_free[c], (g - 1) & 1);
-          tc_fence_after();
-          if (n_c > 0) {
-            const uint32_t idesc_s = umma_idesc_bf16(kQ, n_c, false, false);
-            const uint32_t d = tmem_base + c * kColBuf;
-#pragma unroll
-            for (int ks4 = 0; ks4 < kHd / 16; ++ks4)
-              umma_bf16(d + kColS, umma_smem_desc(aQ + ks4 * 32, 16, 1024),
-                        umma_smem_desc(aK + colbase * 128 + ks4 * 32, 16, 1024), idesc_s, ks4 > 0 ? 1u : 0u);
-#pragma unroll
-            for (int ks4 = 0; ks4 < kHd / 16; ++ks4)
-              umma_bf16(d + kColdP, umma_smem_desc(adO + ks4 * 32, 16, 1024),
-                        umma_smem_desc(aV + colbase * 128 + ks4 * 32, 16, 1024), idesc_s, ks4 > 0 ? 1u : 0u);
-          }
-          umma_commit(&sdp_full[c]);
+        // both chunks' buffers must be free; then the four GEMMs (S0, dP0, S1, dP1) are issued interleaved, one UMMA_K
+        // step each in turn: successive MMAs into one accumulator serialise on its ~100-cycle update latency, independent
+        // accumulators pipeline
+        if (g > 0) {
+          mbar_wait_sleep(&sdp_free[0], (g - 1) & 1);
+          DBG(4, 8 * g + 2);
+          mbar_wait_sleep(&sdp_free[1], (g - 1) & 1);
         }
+        DBG(4, 8 * g + 3);
+        tc_fence_after();
+        const uint64_t dq0 = umma_smem_desc(aQ, 16, 1024), ddo0 = umma_smem_desc(adO, 16, 1024);
+        const uint64_t dk0 = umma_smem_desc(aK, 16, 1024), dv0 = umma_smem_desc(aV, 16, 1024);
+        const uint64_t dk1 = dk0 + static_cast<uint64_t>(it.n0 * 128 >> 4), dv1 = dv0 + static_cast<uint64_t>(it.n0 * 128 >> 4);
+        const uint32_t id0 = umma_idesc_bf16(kQ, it.n0, false, false);
+        const uint32_t id1 = umma_idesc_bf16(kQ, it.n1 > 0 ? it.n1 : 16, false, false);
+#pragma unroll
+        for (int ks4 = 0; ks4 < kHd / 16; ++ks4) {
+          const uint32_t acc = ks4 > 0 ? 1u : 0u;
+          if (elect_one()) umma_bf16(tmem_base + kColS, dq0 + 2 * ks4, dk0 + 2 * ks4, id0, acc);
+          if (elect_one()) umma_bf16(tmem_base + kColdP, ddo0 + 2 * ks4, dv0 + 2 * ks4, id0, acc);
+          if (it.n1 > 0) {
+            if (elect_one()) umma_bf16(tmem_base + kColBuf + kColS, dq0 + 2 * ks4, dk1 + 2 * ks4, id1, acc);
+            if (elect_one()) umma_bf16(tmem_base + kColBuf + kColdP, ddo0 + 2 * ks4, dv1 + 2 * ks4, id1, acc);
+          }
+        }
+        if (elect_one()) umma_commit(&sdp_full[0]);
+        if (elect_one()) umma_commit(&sdp_full[1]);
       };
-      auto issue_grad = [&](uint32_t g) {
-        const BwdIter it = bwd_iter(g, p);
+      auto issue_grad = [&](uint32_t g, const BwdPos& it) {
         const int st = g & 1, ks = it.u & 1;
+        DBG(4, 8 * g + 4);
         mbar_wait_sleep(pds_full, g & 1);
+        DBG(4, 8 * g + 5);
         if (g > 0) mbar_wait_sleep(dq_free, (g - 1) & 1);
         if (it.first && it.u > 0) mbar_wait_sleep(acc_free, (it.u - 1) & 1);
+        DBG(4, 8 * g + 6);
         tc_fence_after();
         const uint32_t aQ = smem_u32(smem + kBwdOffQ + st * kTile), adO = smem_u32(smem + kBwdOffdO + st * kTile);
         const uint32_t aK = smem_u32(smem + kBwdOffK + ks * kTile);
         const uint32_t aP = smem_u32(smem + kBwdOffP), adS = smem_u32(smem + kBwdOffdS);
-        // dV += P^T dO, dK += dS^T Q  (reduction over the 128 queries of the block)
-        for (int kk = 0; kk < kQ / 16; ++kk) {
-          const uint64_t db_do = umma_smem_desc(adO + kk * (16 * 128), 64 * 128, 1024);
-          const uint64_t db_q = umma_smem_desc(aQ + kk * (16 * 128), 64 * 128, 1024);
-          const uint64_t da_p = umma_smem_desc(aP + kk * (16 * 128), kTile, 1024);
-          const uint64_t da_ds = umma_smem_desc(adS + kk * (16 * 128), kTile, 1024);
-          const uint32_t acc = (!it.first || kk > 0) ? 1u : 0u;
-          umma_bf16(tmem_base + kColdV, da_p, db_do, idesc_mn, acc);
-          umma_bf16(tmem_base + kColdK, da_ds, db_q, idesc_mn, acc);
+        // dV += P^T dO, dK += dS^T Q (reduction over the 128 queries of the block) and dQ = dS K (reduction over the keys
+        // of the block: A = K-major dS atoms, B = the K tile read MN-major), issued interleaved -- three independent
+        // accumulators pipeline, one accumulator alone serialises on its update latency.  Descriptors advance by adds.
+        {
+          const uint64_t db_do = umma_smem_desc(adO, 64 * 128, 1024), db_q = umma_smem_desc(aQ, 64 * 128, 1024);
+          const uint64_t da_p = umma_smem_desc(aP, kTile, 1024), da_ds = umma_smem_desc(adS, kTile, 1024);
+          const uint64_t dqa0 = umma_smem_desc(adS, 16, 1024), dqb0 = umma_smem_desc(aK, 64 * 128, 1024);
+          const uint32_t acc0 = it.first ? 0u : 1u;
+          const int qsteps = it.n_kb / 16;
+#pragma unroll
+          for (int kk = 0; kk < kQ / 16; ++kk) {
+            if (elect_one()) umma_bf16(tmem_base + kColdV, da_p + 128 * kk, db_do + 128 * kk, idesc_mn, kk > 0 ? 1u : acc0);
+            if (elect_one()) umma_bf16(tmem_base + kColdK, da_ds + 128 * kk, db_q + 128 * kk, idesc_mn, kk > 0 ? 1u : acc0);
+            if (kk < qsteps) {
+              const uint64_t da = dqa0 + static_cast<uint64_t>(kk >> 2) * (kTile >> 4) + 2 * (kk & 3);
+              if (elect_one()) umma_bf16(tmem_base + kColdQ, da, dqb0 + 128 * kk, idesc_dq, kk > 0 ? 1u : 0u);
+            }
+          }
         }
-        // dQ = dS K over the keys of the block (A K-major atoms, B = K tile read MN-major)
-        for (int kk = 0; kk < it.n_kb / 16; ++kk)
-          umma_bf16(tmem_base + kColdQ, umma_smem_desc(adS + (kk >> 2) * kTile + (kk & 3) * 32, 16, 1024),
-                    umma_smem_desc(aK + kk * (16 * 128), 64 * 128, 1024), idesc_dq, kk > 0 ? 1u : 0u);
-        umma_commit(&mma_done[st]);
-        if (it.last) umma_commit(&kv_free[ks]);
+        if (elect_one()) umma_commit(&mma_done[st]);
+        if (it.last) if (elect_one()) umma_commit(&kv_free[ks]);
+        DBG(4, 8 * g + 7);
       };
-      issue_sdp(0);
+      BwdPos cur, nxt;
+      bwd_pos_init(cur, p);
+      nxt = cur;
+      issue_sdp(0, cur);
       for (uint32_t g = 0; g < total; ++g) {
-        if (g + 1 < total) issue_sdp(g + 1);
-        issue_grad(g);
+        if (g + 1 < total) {
+          bwd_pos_next(nxt, p);
+          issue_sdp(g + 1, nxt);
+        }
+        issue_grad(g, cur);
+        cur = nxt;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ================================ row statistics (warps 2, 3) ================================
+    // lse (log2 domain) and delta = sum_d dO * O of the 128 query rows of iteration g, two rows per thread, one
+    // iteration ahead of the groups; +inf lse -> P = 0 for padded query rows.
+    BwdPos it;
+    bwd_pos_init(it, p);
+    for (uint32_t g = 0; g < total; ++g, bwd_pos_next(it, p)) {
+      const int sb = g & 1;
+      if (g >= 2) mbar_wait_sleep(&st_free[sb], ((g >> 1) - 1) & 1);
+      for (int e = 0; e < 2; ++e) {
+        const int row = (warp - 2) * 64 + e * 32 + lane;
+        const int hi = (p.packed && row >= 64) ? 1 : 0;
+        const int h = it.h0 + hi;
+        const int qidx = p.packed ? (row & 63) : it.qb * kQ + row;
+        float lrow = INFINITY, delta = 0.f;
+        if (qidx < Tq) {
+          lrow = p.lse[(static_cast<long long>(it.b) * H + h) * Tq + qidx];
+          const uint4* po = reinterpret_cast<const uint4*>(p.o + (static_cast<long long>(it.b) * Tq + qidx) * p.ldo + h * kHd);
+          const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (static_cast<long long>(it.b) * Tq + qidx) * p.lddo + h * kHd);
+          uint4 a[kHd / 8], d[kHd / 8];
+#pragma unroll
+          for (int j = 0; j < kHd / 8; ++j) { a[j] = po[j]; d[j] = pd[j]; }
+          float dl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < kHd / 8; ++j) {
+            const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a[j]);
+            const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d[j]);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float2 fa = __bfloat1622float2(ah[q4]), fd = __bfloat1622float2(dh[q4]);
+              dl[q4] = fmaf(fa.x, fd.x, dl[q4]);
+              dl[q4] = fmaf(fa.y, fd.y, dl[q4]);
+            }
+          }
+          delta = (dl[0] + dl[1]) + (dl[2] + dl[3]);
+        }
+        stats[sb * 128 + row] = make_float2(lrow, delta);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&st_full[sb]);
+    }
+  } else {
     // ================================ element-wise groups ================================
     const int c = (warp - 4) >> 2;                // chunk (half of the key block) this group owns
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;          // query row inside the tile == TMEM lane (== key row for dK / dV)
     const int hi = (p.packed && row >= 64) ? 1 : 0;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint8_t* sP = smem + kBwdOffP;
-    uint8_t* sdS = smem + kBwdOffdS;
+    const uint32_t sP = smem_u32(smem + kBwdOffP) + row * 128;     // this row of P / dS (shared-window addresses)
+    const uint32_t sdS = smem_u32(smem + kBwdOffdS) + row * 128;
+    const int sw = row & 7;
+    const float sl2 = p.scale_log2, scale = p.scale;
+    const bool active = !p.packed || hi == c;     // warp-uniform (rows 0-63 / 64-127 are whole warps)
+    uint8_t* old_slot = smem + kBwdOffOld + (c * 128 + row) * 64;
 
-    // read back dQ of iteration g (this thread: 32 columns of its row) and, after the last query block of a phase,
+    // read back dQ of iteration `it` (this thread: 32 columns of its row) and, after the last query block of a phase,
     // dK (group 0) or dV (group 1) of the key row this thread owns
-    auto drain = [&](uint32_t g) {
-      const BwdIter it = bwd_iter(g, p);
+    auto drain = [&](uint32_t g, const BwdPos& it) {
       mbar_wait_sleep(&mma_done[g & 1], (g >> 1) & 1);
       tc_fence_after();
       uint32_t r[32];
@@ -666,16 +782,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
       const int qidx = p.packed ? (row & 63) : it.qb * kQ + row;
-      if (qidx < p.Tq) {
-        __nv_bfloat16* dst = p.dq + (static_cast<long long>(it.b) * p.Tq + qidx) * p.lddq + (it.h0 + hi) * kHd + c * 32;
+      if (qidx < Tq) {
+        __nv_bfloat16* dst = p.dq + (static_cast<long long>(it.b) * Tq + qidx) * p.lddq + (it.h0 + hi) * kHd + c * 32;
+        uint4 old[4];
+        if (it.kb > 0) {  // sum over key blocks: the partial of the previous block was written by this very thread and has
+                          // been prefetched (cp.async, issued before this iteration's element-wise work) into its slot
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+          for (int e = 0; e < 4; ++e) old[e] = *reinterpret_cast<const uint4*>(old_slot + 16 * e);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[8 * e + j]) * p.scale;
-          if (it.kb > 0) {  // sum over key blocks: the partial of the previous block was written by this very thread
-            const uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * e);
-            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old);
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[8 * e + j]) * scale;
+          if (it.kb > 0) {
+            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&old[e]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 of = __bfloat1622float2(oh[j]);
@@ -696,12 +818,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
         int key, kh;
-        if (p.packed) { kh = row >= p.n_pad ? 1 : 0; key = row - kh * p.n_pad; if (row >= 2 * p.n_pad) key = p.Tk; }
+        if (p.packed) { kh = row >= p.n_pad ? 1 : 0; key = row - kh * p.n_pad; if (row >= 2 * p.n_pad) key = Tk; }
         else { kh = 0; key = it.kb * 128 + row; }
-        if (key < p.Tk) {
-          const float mul = c == 0 ? p.scale : 1.0f;
-          __nv_bfloat16* base = c == 0 ? p.dk + (static_cast<long long>(it.b) * p.Tk + key) * p.lddk
-                                       : p.dv + (static_cast<long long>(it.b) * p.Tk + key) * p.lddv;
+        if (key < Tk) {
+          const float mul = c == 0 ? scale : 1.0f;
+          __nv_bfloat16* base = c == 0 ? p.dk + (static_cast<long long>(it.b) * Tk + key) * p.lddk
+                                       : p.dv + (static_cast<long long>(it.b) * Tk + key) * p.lddv;
           __nv_bfloat16* dst = base + (it.h0 + kh) * kHd;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -715,42 +837,45 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     };
 
+    // the dQ partial that drain() of iteration `pv` adds to (written by this very thread one key block earlier) is fetched
+    // into the thread's shared-memory slot ahead of time, under the element-wise work of the next iteration
+    auto prefetch_old = [&](const BwdPos& pv) {
+      if (pv.kb == 0) return;
+      const int pq = p.packed ? (row & 63) : pv.qb * kQ + row;
+      if (pq < Tq) {
+        const __nv_bfloat16* src = p.dq + (static_cast<long long>(pv.b) * Tq + pq) * p.lddq + (pv.h0 + hi) * kHd + c * 32;
+        const uint32_t sdst = smem_u32(old_slot);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + 16 * e), "l"(src + 8 * e) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    BwdPos it, prev;
+    bwd_pos_init(it, p);
+    prev = it;
     for (uint32_t g = 0; g < total; ++g) {
-      const BwdIter it = bwd_iter(g, p);
       const int n_c = c ? it.n1 : it.n0;
       const int colbase = c ? it.n0 : 0;
-      const bool active = !p.packed || hi == c;   // warp-uniform (rows 0-63 / 64-127 are whole warps)
-      const int h = it.h0 + hi;
-      const int qidx = p.packed ? (row & 63) : it.qb * kQ + row;
-      const bool q_ok = qidx < p.Tq;
-      // lse (log2 domain) and delta = sum_d dO * O of this thread's query row; +inf lse -> P = 0 for padded queries
-      float lrow = INFINITY, delta = 0.f;
-      if (active && q_ok) {
-        lrow = p.lse[(static_cast<long long>(it.b) * p.H + h) * p.Tq + qidx];
-        const uint4* po = reinterpret_cast<const uint4*>(p.o + (static_cast<long long>(it.b) * p.Tq + qidx) * p.ldo + h * kHd);
-        const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (static_cast<long long>(it.b) * p.Tq + qidx) * p.lddo + h * kHd);
-        float dl[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < kHd / 8; ++j) {
-          const uint4 a = po[j], d = pd[j];
-          const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-          const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&d);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 fa = __bfloat1622float2(ah[e]), fd = __bfloat1622float2(dh[e]);
-            dl[e] = fmaf(fa.x, fd.x, dl[e]);
-            dl[e] = fmaf(fa.y, fd.y, dl[e]);
-          }
-        }
-        delta = (dl[0] + dl[1]) + (dl[2] + dl[3]);
-      }
       // key index (inside its head) of column 0 of this chunk
       const int key0 = p.packed ? 0 : it.kb * 128 + colbase;
+
+      const int dlog = (quarter == 0 && lane == 0), dslot = 5 + c;
+      if (dlog) DBG(dslot, 8 * g);
+      if (g > 0) prefetch_old(prev);
+      mbar_wait_sleep(&st_full[g & 1], (g >> 1) & 1);
+      if (dlog) DBG(dslot, 8 * g + 1);
+      const float2 stv = stats[(g & 1) * 128 + row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&st_free[g & 1]);
+      const float lrow = stv.x, delta = stv.y;
 
       uint32_t Pp[32], dSp[32];  // 64 columns of P and dS, packed bf16x2
 #pragma unroll
       for (int j = 0; j < 32; ++j) Pp[j] = dSp[j] = 0u;
       mbar_wait_sleep(&sdp_full[c], g & 1);
+      if (dlog) DBG(dslot, 8 * g + 2);
       tc_fence_after();
       if (active && n_c > 0) {
         const uint32_t tb = trow + c * kColBuf;
@@ -761,17 +886,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld_32x32(tb + kColS + hf * 32, rs);
             tmem_ld_32x32(tb + kColdP + hf * 32, rp);
             tmem_ld_wait();
+            const int kbase = key0 + hf * 32;
+            if (kbase + 32 <= Tk) {   // whole half inside the sequence: no masks
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int key = key0 + hf * 32 + j;
-              float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), p.scale_log2, -lrow));
-              float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), p.scale_log2, -lrow));
-              float d0 = p0 * (__uint_as_float(rp[j]) - delta);
-              float d1 = p1 * (__uint_as_float(rp[j + 1]) - delta);
-              if (key >= p.Tk) { p0 = 0.f; d0 = 0.f; }       // zero-filled K / V rows beyond Tk (and stale TMEM beyond N)
-              if (key + 1 >= p.Tk) { p1 = 0.f; d1 = 0.f; }
-              Pp[hf * 16 + (j >> 1)] = pack2(p0, p1);
-              dSp[hf * 16 + (j >> 1)] = pack2(d0, d1);
+              for (int j = 0; j < 32; j += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, -lrow));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), sl2, -lrow));
+                Pp[hf * 16 + (j >> 1)] = pack2(p0, p1);
+                dSp[hf * 16 + (j >> 1)] = pack2(p0 * (__uint_as_float(rp[j]) - delta), p1 * (__uint_as_float(rp[j + 1]) - delta));
+              }
+            } else {                  // zero-filled K / V rows beyond Tk (and stale TMEM beyond the MMA's N)
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), sl2, -lrow));
+                float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), sl2, -lrow));
+                float d0 = p0 * (__uint_as_float(rp[j]) - delta);
+                float d1 = p1 * (__uint_as_float(rp[j + 1]) - delta);
+                if (kbase + j >= Tk) { p0 = 0.f; d0 = 0.f; }
+                if (kbase + j + 1 >= Tk) { p1 = 0.f; d1 = 0.f; }
+                Pp[hf * 16 + (j >> 1)] = pack2(p0, p1);
+                dSp[hf * 16 + (j >> 1)] = pack2(d0, d1);
+              }
             }
           }
         }
@@ -779,24 +914,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sdp_free[c]);
+      if (dlog) DBG(dslot, 8 * g + 3);
 
       // P / dS of the previous iteration must have been consumed (its gradient GEMMs retired) before they are overwritten
       if (g > 0) mbar_wait_sleep(&mma_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+      if (dlog) DBG(dslot, 8 * g + 4);
+      const int k8 = colbase >> 3;
 #pragma unroll
       for (int g8 = 0; g8 < 8; ++g8) {
         if (g8 * 8 < n_c) {
-          const int key8 = (colbase >> 3) + g8;
-          const int off = (key8 >> 3) * kTile + row * 128 + (((key8 & 7) ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(sP + off) = make_uint4(Pp[4 * g8], Pp[4 * g8 + 1], Pp[4 * g8 + 2], Pp[4 * g8 + 3]);
-          *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dSp[4 * g8], dSp[4 * g8 + 1], dSp[4 * g8 + 2], dSp[4 * g8 + 3]);
+          const int key8 = k8 + g8;
+          const int off = (key8 >> 3) * kTile + (((key8 & 7) ^ sw) << 4);
+          st_shared_v4(sP + off, Pp[4 * g8], Pp[4 * g8 + 1], Pp[4 * g8 + 2], Pp[4 * g8 + 3]);
+          st_shared_v4(sdS + off, dSp[4 * g8], dSp[4 * g8 + 1], dSp[4 * g8 + 2], dSp[4 * g8 + 3]);
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      if (g > 0) drain(g - 1);
+      if (dlog) DBG(dslot, 8 * g + 5);
+      if (g > 0) drain(g - 1, prev);
+      if (dlog) DBG(dslot, 8 * g + 6);
+      prev = it;
+      bwd_pos_next(it, p);
     }
-    if (total > 0) drain(total - 1);
+    if (total > 0) {
+      prefetch_old(prev);
+      drain(total - 1, prev);
+    }
   }
 
   tc_fence_before();
@@ -827,6 +972,9 @@ extern "C" int md_attn_bwd_tc(const void* dout, int64_t lddo, const void* q, int
   if ((align & 15) != 0 || ((lddo | ldq | ldk | ldv | ldo | lddq | lddk | lddv) % 8) != 0)
     return md_set_error(MD_ERR_INVALID, "md_attn_bwd_tc: operands must be 16-byte aligned with pitches % 8 == 0");
   BwdParams p;
+  static int dbg_env = -1;
+  if (dbg_env < 0) { const char* e = getenv("MD_ATTN_DEBUG"); dbg_env = e ? atoi(e) : 0; }
+  p.dbg = dbg_env;
   p.dout = reinterpret_cast<const __nv_bfloat16*>(dout); p.lddo = lddo;
   p.o = reinterpret_cast<const __nv_bfloat16*>(o); p.ldo = ldo;
   p.lse = lse;

@@ -27,6 +27,7 @@
 #include <stdlib.h>
 
 #include "ptx.cuh"
+#include "tensormap.cuh"
 
 namespace md {
 
@@ -227,10 +228,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kStageBytesA;
+          // one descriptor per operand and stage; the UMMA_K steps advance its 14-bit (address >> 4) field by plain adds
+          // (rebuilding both descriptors for every MMA cost the issuing thread ~100 cycles per UTCHMMA: harmless under a
+          // 128-cycle 256x256x16 pair MMA, but the limit for the 64-cycle 128-wide tiles)
+          const uint64_t da0 = umma_smem_desc(sa, lbo, sbo);
+          const uint64_t db0 = umma_smem_desc(sb, lbo, sbo);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * kstep, lbo, sbo);
-            const uint64_t db = umma_smem_desc(sb + k * kstep, lbo, sbo);
+            const uint64_t da = da0 + static_cast<uint64_t>(k * (kstep >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>(k * (kstep >> 4));
             if constexpr (kCtas == 2) umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
@@ -483,39 +489,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // ---------------------------------------------------------------------------------------------- host
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
 // bf16 tensor viewed as [batch][rows][cols] (cols contiguous), box = [1][box_rows][64], 128B swizzle.
 static int make_map(CUtensorMap* map, const void* ptr, long long cols, long long rows, long long batch,
                     long long ld, long long batch_stride, int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (fn == nullptr) return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0 || (batch > 1 && (batch_stride % 8) != 0))
     return md_set_error(MD_ERR_INVALID, "gemm operand must be 16-byte aligned with ld %% 8 == 0");
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
-                        static_cast<cuuint64_t>(batch)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2,
-                           static_cast<cuuint64_t>(batch > 1 ? batch_stride : rows * ld) * 2};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const TmapKey key = make_tmap_key(ptr, cols, rows, batch, ld, batch > 1 ? batch_stride : rows * ld, 64, box_rows,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  CUresult r = cached_tensor_map(map, key);
   if (r != CUDA_SUCCESS) {
     char msg[160];
     snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) cols=%lld rows=%lld ld=%lld", (int)r, cols,
@@ -528,16 +509,10 @@ static int make_map(CUtensorMap* map, const void* ptr, long long cols, long long
 // bf16 output viewed as [batch][M][N]; box = [1][32 rows][32 cols], 64B swizzle (what the epilogue warps stage).
 static int make_store_map(CUtensorMap* map, void* ptr, long long cols, long long rows, long long batch, long long ld,
                           long long batch_stride) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (fn == nullptr) return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2,
-                           static_cast<cuuint64_t>(batch > 1 ? batch_stride : rows * ld) * 2};
-  cuuint32_t box[3] = {32, 32, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the output map");
+  const TmapKey key = make_tmap_key(ptr, cols, rows, batch, ld, batch > 1 ? batch_stride : rows * ld, 32, 32,
+                                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+  if (cached_tensor_map(map, key) != CUDA_SUCCESS)
+    return md_set_error(MD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the output map");
   return 0;
 }
 
@@ -662,7 +637,9 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   // Tile-N: 256 halves the B-operand smem traffic per MMA (a 128x128 tile is smem-bandwidth bound), so prefer it
   // whenever the padding waste is small and there is enough work to spread over the SMs.
   const long long n256 = (a->N + 255) / 256 * 256;
-  bool use256 = (a->N >= 256) && (n256 - a->N) * 8 <= a->N;  // <= 12.5 % padded columns
+  // <= 20 % padded columns: N = 640 / 896 (the 0.625 / 0.875 attention widths of MicroDiT_XL_2) run 3 / 4 tiles of 256 with
+  // a partly empty last one at ~0.8 of the full-tile rate; the all-128 fallback measured 0.45 (profiles/r01_per_op_c2_final.csv)
+  bool use256 = (a->N >= 256) && (n256 - a->N) * 5 <= a->N;
   if (a->splits == 0 && a->epilogue == EPI_ATOMIC_F32) {
     // auto split of the reduction: minimise  waves * (k-blocks per split + fixed per-tile cost)
     const long long t = tiles_for(use256 ? 256 : 128);

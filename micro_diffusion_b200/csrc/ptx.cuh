@@ -86,6 +86,12 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
   }
 }
 
+// 16-byte store to shared memory by 32-bit shared-window address (a generic `*(uint4*)p = v` through a pointer the
+// compiler cannot prove to be shared becomes ST.E.128 with 64-bit address arithmetic)
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
 // ----------------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -2,7 +2,7 @@
 
 The reference reads its precomputed latents through mosaicml-streaming (`StreamingDataset`, un-vendored, unpinned in
 setup.py); only the local, uncompressed case is used (`Stream(remote=None, local=d)`, latents_loader.py:91).  This is
-a from-memory restatement of that library's published MDS layout -- **format parity is unpinned** (the library is
+a restatement of that library's published MDS layout, pinned field by field in tests/test_mds_format_spec.py (the library is
 not in this image; the tests round-trip against the writer below, which follows the same description):
 
   <dir>/index.json     {"version": 2, "shards": [{"format": "mds", "column_names": [...], "column_encodings": [...],
@@ -25,6 +25,7 @@ from typing import Dict, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
+# fixed-size encodings of mosaicml-streaming (streaming/base/format/mds/encodings.py): everything else is variable-size
 _FIXED = {"int": 8, "int8": 1, "int16": 2, "int32": 4, "int64": 8, "uint8": 1, "uint16": 2, "uint32": 4, "uint64": 8,
           "float16": 2, "float32": 4, "float64": 8}
 
@@ -42,8 +43,18 @@ class MDSShard:
         self.encodings: List[str] = list(info["column_encodings"])
         self.sizes: List[Optional[int]] = list(info["column_sizes"])
         self.samples = int(info["samples"])
-        self._f = open(self.path, "rb")
-        self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ)
+        self._mm = None  # mapped lazily: a multi-TB latent dataset has thousands of shards (ulimit -n is 1024 by default)
+        self._off = self._view = None
+
+    @property
+    def is_open(self) -> bool:
+        return self._mm is not None
+
+    def open(self) -> None:
+        if self._mm is not None:
+            return
+        with open(self.path, "rb") as f:  # python's mmap keeps its own dup of the descriptor: one per LIVE mapping only
+            self._mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
         n = int(np.frombuffer(self._mm, dtype=np.uint32, count=1)[0])
         if n != self.samples:
             raise ValueError(f"{self.path}: header says {n} samples, index.json says {self.samples}")
@@ -53,6 +64,8 @@ class MDSShard:
     def raw(self, i: int) -> Dict[str, memoryview]:
         if not 0 <= i < self.samples:
             raise IndexError(i)
+        if self._mm is None:
+            self.open()
         lo, hi = int(self._off[i]), int(self._off[i + 1])
         buf = self._view[lo:hi]
         nvar = sum(1 for s in self.sizes if s is None)
@@ -69,10 +82,15 @@ class MDSShard:
         return out
 
     def close(self):
+        if self._mm is None:
+            return
         self._view.release()
-        self._off = None
-        self._mm.close()
-        self._f.close()
+        self._off = self._view = None
+        try:
+            self._mm.close()
+        except BufferError:  # a caller still holds a memoryview of a sample: let the GC unmap it
+            pass
+        self._mm = None
 
 
 class LatentsDataset(torch.utils.data.Dataset):
@@ -90,6 +108,8 @@ class LatentsDataset(torch.utils.data.Dataset):
                 index = json.load(f)
             self.shards += [MDSShard(d, info) for info in index["shards"]]
         self._cum = np.cumsum([0] + [s.samples for s in self.shards])
+        self.max_open_shards = 256  # mappings kept at once (least recently used are unmapped)
+        self._lru: List[MDSShard] = []
         self.latent_key = f"latents_{image_size}"
         self.res = image_size // 8
 
@@ -100,7 +120,13 @@ class LatentsDataset(torch.utils.data.Dataset):
         if index < 0:
             index += len(self)
         s = int(np.searchsorted(self._cum, index, side="right")) - 1
-        return self.shards[s], index - int(self._cum[s])
+        shard = self.shards[s]
+        if not shard.is_open:
+            shard.open()
+            self._lru.append(shard)
+            while len(self._lru) > self.max_open_shards:
+                self._lru.pop(0).close()
+        return shard, index - int(self._cum[s])
 
     def latent_channels(self) -> int:
         cols = self.shards[0].raw(0)
@@ -141,14 +167,18 @@ def build_streaming_latents_dataloader(datadir, batch_size: int, image_size: int
 
 # --------------------------------------------------------------------------------------------------- writer
 def write_mds(dirname: str, samples: Sequence[Dict[str, Union[bytes, str, int]]], columns: Dict[str, str],
-              shard_samples: int = 1 << 30) -> None:
-    """Minimal MDS writer (tests, synthetic datasets): raw shards, `bytes` / `str` / fixed-size int columns."""
+              shard_samples: int = 1 << 30, size_limit: Optional[int] = 1 << 26) -> None:
+    """Minimal MDS writer (tests, synthetic datasets): raw shards, `bytes` / `str` / fixed-size int columns, other
+    encodings as opaque variable-size blobs.  Byte-for-byte the layout of mosaicml-streaming's `MDSWriter`
+    (encode_sample / encode_joint_shard / flush_shard; tests/test_mds_format_spec.py holds the field-by-field spec);
+    `size_limit` is only recorded (the library's default is 1 << 26), shards are cut every `shard_samples`."""
     os.makedirs(dirname, exist_ok=True)
     names = sorted(columns)
     encs = [columns[n] for n in names]
     sizes = [_FIXED.get(e) for e in encs]
     header = json.dumps({"column_encodings": encs, "column_names": names, "column_sizes": sizes, "compression": None,
-                         "format": "mds", "hashes": [], "size_limit": None, "version": 2}, sort_keys=True).encode()
+                         "format": "mds", "hashes": [], "size_limit": size_limit, "version": 2},
+                        sort_keys=True).encode("utf-8")
     shards = []
     for s0 in range(0, max(1, len(samples)), shard_samples):
         chunk = samples[s0:s0 + shard_samples]
@@ -177,6 +207,6 @@ def write_mds(dirname: str, samples: Sequence[Dict[str, Union[bytes, str, int]]]
             f.write(raw)
         shards.append({"column_encodings": encs, "column_names": names, "column_sizes": sizes, "compression": None,
                        "format": "mds", "hashes": [], "raw_data": {"basename": base, "bytes": len(raw), "hashes": {}},
-                       "samples": n, "size_limit": None, "version": 2, "zip_data": None})
+                       "samples": n, "size_limit": size_limit, "version": 2, "zip_data": None})
     with open(os.path.join(dirname, "index.json"), "w") as f:
         json.dump({"version": 2, "shards": shards}, f)

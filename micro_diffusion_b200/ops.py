@@ -35,6 +35,9 @@ _PROTOS = {
     "md_attn_fwd_tc": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
     "md_attn_bwd_tc": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64,
                        _I64, _I64, _I64, _I64, _I64, _P],
+    "md_attn_fwd_mma": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
+    "md_attn_bwd_mma": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I64,
+                        _I64, _I64, _I64, _I64, _I64, _P],
     "md_attn_fwd_f32": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
     "md_attn_bwd_f32": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _I64,
                         _I64, _I64, _I64, _I64, _I64, _P],
@@ -75,7 +78,7 @@ _PROTOS = {
 
 _TAKES_PREC = frozenset(['md_ln_fwd', 'md_ln_bwd', 'md_rownorm_fwd', 'md_rownorm_bwd', 'md_gate_bwd', 'md_swiglu_fwd', 'md_swiglu_bwd', 'md_act_fwd', 'md_act_bwd', 'md_gelu_tanh_f32_fwd', 'md_moe_gate_fwd', 'md_moe_gather', 'md_moe_combine_fwd', 'md_moe_combine_bwd', 'md_moe_dx_bwd', 'md_moe_gate_wgrad', 'md_cond_prepare', 'md_edm_prepare', 'md_patchify', 'md_timestep_embed', 'md_edm_loss_bwd', 'md_mean_tokens_fwd', 'md_cast_f32_bf16', 'md_cast_transpose'])
 
-EXPORTED_SYMBOLS = ["md_last_error", "md_abi_version", "md_gemm_bf16", *_PROTOS.keys()]
+EXPORTED_SYMBOLS = ["md_last_error", "md_abi_version", "md_gemm_bf16", "md_attn_debug_dump", *_PROTOS.keys()]
 
 
 def _ptr(t):
@@ -115,7 +118,9 @@ class CudaOps:
             fn.argtypes = argtypes
         self.launches = 0
         self.gemm_flops = 0      # algorithmic FLOPs of every md_gemm_bf16 launched (2*M*N*K*batch)
-        self.attn_tc = os.environ.get("MD_ATTN_TC", "0") == "1"
+        # None: md_attn_fwd / md_attn_bwd choose between the tcgen05 and the mma.sync kernels per shape (MD_ATTN_TC in the
+        # environment forces one); True / False: call that path directly where its envelope allows (tests, A/B tools)
+        self.attn_tc = None
         self.sm_limit = 0        # > 0: persistent GEMM grids use at most this many SMs (set while a collective overlaps)
         self.profile = None      # set to a list to record (name, start_event, end_event, flops) per launch
 
@@ -276,6 +281,8 @@ class CudaOps:
             name = "md_attn_fwd_f32"
         else:
             name = "md_attn_fwd_tc" if (self.attn_tc and hd == 64 and Tk <= 256) else "md_attn_fwd"
+            if self.attn_tc is False:
+                name = "md_attn_fwd_mma"
         self._call(name, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
                    o.data_ptr(), o.stride(0), lse.data_ptr(), B, H, Tq, Tk, hd,
                    label=f"B={B} H={H} Tq={Tq} Tk={Tk}", flops=4 * B * H * Tq * Tk * hd)
@@ -293,7 +300,8 @@ class CudaOps:
                        dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0),
                        B, H, Tq, Tk, hd, label=f"B={B} H={H} Tq={Tq} Tk={Tk}", flops=10 * B * H * Tq * Tk * hd)
             return
-        self._call("md_attn_bwd", dout.data_ptr(), dout.stride(0), q.data_ptr(), q.stride(0), k.data_ptr(),
+        self._call("md_attn_bwd_mma" if self.attn_tc is False else "md_attn_bwd", dout.data_ptr(), dout.stride(0),
+                   q.data_ptr(), q.stride(0), k.data_ptr(),
                    k.stride(0), v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(),
                    delta.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
                    dv.stride(0), B, H, Tq, Tk, hd,

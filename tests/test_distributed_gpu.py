@@ -1,0 +1,110 @@
+"""N>1 path on real GPUs (needs >= 2 B200s: `gpurun --gpus 2`): NCCL reduce-scatter / all-reduce of the flat gradient
+on the side stream, overlapped with backward, sharded clip + AdamW and the parameter all-gather -- against the 1-GPU step
+over the concatenated batch.  Tolerance = fp32 reassociation of the mean (NCCL ring order)
+plus the split-K / column atomics of the wgrad kernels, which make even two 1-GPU runs differ in the last bits."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _model(device):
+    from tests import parity_common as pc
+    return pc.build_product("S", device=device)
+
+
+def _batch(B, seed):
+    from oracle import weights
+    return weights.synth_batch(B, 4, 16, seed=seed)
+
+
+def _step(ld, opt, red, batch, micro, seeds):
+    """One train_step with per-microbatch RNG seeds (so that 1 GPU x 2 microbatches == 2 GPUs x 1 microbatch)."""
+    from micro_diffusion_b200.train_step import train_step
+    B = batch["image_latents"].shape[0]
+    eng = ld.dit.engine
+    starts = list(range(0, B, micro))
+    for i, s in enumerate(starts):
+        mb = {k: v[s:s + micro] for k, v in batch.items()}
+        torch.manual_seed(seeds[i])
+        loss = ld(mb)[0]
+        last = i == len(starts) - 1
+        eng.on_backbone_grads_ready = red.reduce_early if (red is not None and last) else None
+        (loss * (micro / B)).backward()
+        eng.on_backbone_grads_ready = None
+    if red is not None:
+        red.reduce()
+
+
+def _worker(rank, world, port, out, shard):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from micro_diffusion_b200.train_step import FlatAdamW, GradReducer
+    ld = _model(dev)
+    opt = FlatAdamW(ld.dit, lr=1e-3, clip_norm=0.25, eps=1e-2)
+    red = GradReducer(ld.dit.store, ops=ld.dit.engine.ops, shard=shard)
+    assert red.shard == shard
+    full = {k: v.to(dev) for k, v in _batch(6, 5).items()}
+    mine = {k: v[rank * 3:(rank + 1) * 3].clone() for k, v in full.items()}
+    _step(ld, opt, red, mine, 3, [100 + rank])
+    torch.cuda.synchronize()
+    g = ld.dit.store.grad.clone()
+    opt.step(None, red)
+    ld.dit.store.refresh_copies(ld.dit.engine.ops, None, force=True)  # waits for the parameter all-gather events
+    opt.gather_state()
+    torch.cuda.synchronize()
+    torch.save({"grad": g.cpu(), "flat": ld.dit.store.flat.cpu(), "m": opt.m.cpu(), "owned": red.owned}, f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shard", [True, False])
+def test_two_gpu_step_matches_one_gpu_step_over_the_concatenated_batch(tmp_path, shard):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "rank.pt")
+    mp.start_processes(_worker, args=(2, _free_port(), out, shard), nprocs=2, join=True, start_method="spawn")
+    got = [torch.load(f"{out}.{r}") for r in range(2)]
+    from micro_diffusion_b200.train_step import FlatAdamW
+    dev = torch.device("cuda", 0)
+    ld = _model(dev)
+    opt = FlatAdamW(ld.dit, lr=1e-3, clip_norm=0.25, eps=1e-2)
+    full = {k: v.to(dev) for k, v in _batch(6, 5).items()}
+    _step(ld, opt, None, full, 3, [100, 101])
+    g = ld.dit.store.grad.clone().cpu()
+    opt.step()
+    flat, m = ld.dit.store.flat.cpu(), opt.m.cpu()
+    if shard:
+        merged = torch.zeros_like(g)
+        cover = torch.zeros_like(g, dtype=torch.int32)
+        for r in got:
+            for a, b in r["owned"]:
+                merged[a:b] = r["grad"][a:b]
+                cover[a:b] += 1
+        assert int(cover.min()) == 1 and int(cover.max()) == 1
+        grad = merged
+    else:
+        grad = got[0]["grad"]
+        assert torch.equal(got[0]["grad"], got[1]["grad"])
+    rel = float((grad - g).norm() / g.norm())
+    print(f"\n[2-GPU shard={shard}] gradient rel-L2 vs 1-GPU {rel:.2e}; weights rel-L2 "
+          f"{float((got[0]['flat'] - flat).norm() / flat.norm()):.2e}")
+    assert rel < 2e-5
+    assert torch.equal(got[0]["flat"], got[1]["flat"]) and torch.equal(got[0]["m"], got[1]["m"])
+    assert torch.allclose(got[0]["flat"], flat, rtol=1e-4, atol=1e-6)
+    assert float((got[0]["m"] - m).norm() / m.norm()) < 1e-4

@@ -165,8 +165,7 @@ def test_attention(B, H, Tq, Tk, hd):
         ops.attn_bwd(do, qkv[:, :hsz], kv[:, :hsz], kv[:, hsz:], o, lse, delta, dq, dkv[:, :hsz], dkv[:, hsz:], B, H, Tq,
                      Tk, hd)
     cpu2, cu2 = both(b, [do, qkv, kv, cpu[2], cpu[3], delta, dq, dkv])
-    if Tk > 80:  # the fused few-key backward kernels derive delta on the fly and leave the scratch alone
-        close(cu2[5], cpu2[5], "delta", 1e-3)
+    # `delta` is scratch: the tcgen05 path and the fused few-key mma.sync kernels derive it on the fly and leave it alone
     close(cu2[6], cpu2[6], "dq", 1e-2, ulps=8.0); close(cu2[7], cpu2[7], "dkv", 1e-2, ulps=8.0)
 
 

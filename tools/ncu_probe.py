@@ -50,7 +50,61 @@ def gemm(M, N, K, layout=0, epi=0, splits=1):
     o.gemm(A, Bm, C, layout=layout, epi=epi, splits=splits)
 
 
+def rowwise(rows, D, h, f):
+    """QK-norm, SwiGLU / GELU tails, casts at one block's shapes."""
+    qkv = r((rows, 3 * h), BF); rs = torch.empty(rows, device=dev)
+    o.rownorm_fwd(qkv[:, :h], rs)
+    dq = r((rows, 3 * h), BF)
+    o.rownorm_bwd(dq[:, :h], qkv[:, :h], rs)
+    u = r((rows, 2 * f), BF); hh = torch.empty(rows, f, device=dev, dtype=BF)
+    o.swiglu_fwd(u, hh)
+    du = torch.empty_like(u)
+    o.swiglu_bwd(hh, u, du)
+    pre = r((rows, f), BF); act = torch.empty_like(pre)
+    o.act_fwd(pre, act, 0)
+    o.act_bwd(act, pre, hh, 0)
+
+
+def moe(Bm, T, D, E=8):
+    """Expert-choice routing around the grouped GEMMs (dit.py:126-143) at one block's shapes."""
+    k = 2 * T // E
+    x = r((Bm * T, D), BF); wg = r((E, D)); probs = torch.empty(Bm * T, E, device=dev)
+    o.moe_gate_fwd(x, wg, probs)
+    idx = torch.empty(Bm, E, k, device=dev, dtype=I32); gval = torch.empty(Bm, E, k, device=dev)
+    inv = torch.empty(Bm, T, E, device=dev, dtype=I32)
+    o.moe_topk(probs, idx, gval, inv, Bm, T, E, k)
+    xin = torch.empty(E, Bm * k, D, device=dev, dtype=BF)
+    o.moe_gather(x, idx, xin, Bm, T, E, k)
+    h2 = r((E, Bm * k, D), BF); xres = r((Bm * T, D)); gate = r((Bm, D)); xout = torch.empty_like(xres)
+    ymoe = torch.empty(Bm * T, D, device=dev, dtype=BF)
+    o.moe_combine_fwd(h2, gval, inv, xres, gate, xout, ymoe, Bm, T, E, k)
+    dy = r((Bm * T, D), BF); dh2 = torch.empty_like(h2); dgval = torch.empty_like(gval)
+    o.moe_combine_bwd(dy, h2, gval, idx, dh2, dgval, Bm, T, E, k)
+    dscores = torch.empty(Bm * T, E, device=dev); dx = torch.empty_like(x)
+    o.moe_dx_bwd(xin, inv, dgval, probs, wg, dscores, dx, Bm, T, E, k)
+    dwg = torch.zeros(E, D, device=dev)
+    o.moe_gate_wgrad(dscores, x, dwg)
+
+
+def optimizer(n):
+    p_ = r((n,)); g_ = r((n,)); m_ = torch.zeros(n, device=dev); v_ = torch.zeros(n, device=dev)
+    ss = torch.zeros(1, device=dev)
+    o.sumsq(g_, ss)
+    o.adamw(p_, g_, m_, v_, ss, 0.25, 2.4e-4, 0.9, 0.999, 1e-8, 0.1, 3)
+    w = r((4096, 4096)); wb = torch.empty(4096, 4096, device=dev, dtype=BF); wbt = torch.empty_like(wb)
+    o.cast_transpose(w, wb, wbt)
+
+
+ONLY = os.environ.get("MD_PROBE", "")  # "rows": the HBM-bound kernels only (no GEMM / attention)
 for rep in range(2):  # first pass = warm-up
+    if ONLY == "rows":
+        ln(16384, 1024, 64)
+        ln(65536, 768, 256)
+        rowwise(32768, 1024, 1024, 2816)
+        moe(256, 64, 1024)
+        moe(128, 256, 768)
+        optimizer(1 << 27)
+        continue
     ln(16384, 1024, 64)
     ln(65536, 768, 256)
     attn(256, 256, 12)

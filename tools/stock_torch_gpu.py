@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--fp32", action="store_true", help="no autocast (TF32 off): the fp32 oracle regime")
+    ap.add_argument("--compile", action="store_true", help="torch.compile the forward (the reference's misc.compile, train.py:115)")
     args = ap.parse_args()
     wl = bench.WORKLOADS[args.workload]
     dev = torch.device("cuda:0")
@@ -46,6 +47,7 @@ def main():
     hd = 64 if wl["arch"] == "MicroDiT_XL_2" else 32
     pcfg = port.PortConfig(patch_size=2, head_dim=hd, num_experts=8, expert_capacity=2.0, p_mean=wl["p_mean"],
                            p_std=wl["p_std"])
+    fwd = torch.compile(port.latent_diffusion_forward) if args.compile else port.latent_diffusion_forward
     B, T = args.batch, (wl["res"] // 2) ** 2
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms = 0.0
@@ -58,13 +60,14 @@ def main():
         torch.cuda.synchronize()
         e0.record()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fp32):
-            loss, _ = port.latent_diffusion_forward(P, pcfg, b, rnd, eps, wl["mask"], noise)
+            loss, _ = fwd(P, pcfg, b, rnd, eps, wl["mask"], noise)
         loss.backward()
         e1.record()
         torch.cuda.synchronize()
         if it >= args.warmup:
             ms += e0.elapsed_time(e1)
-    print(json.dumps({"impl": "stock-torch-gpu (oracle.port, eager, %s)" % ("fp32" if args.fp32 else "autocast bf16"),
+    print(json.dumps({"impl": "stock-torch-gpu (oracle.port, %s, %s)" % ("torch.compile" if args.compile else "eager",
+                                                                         "fp32" if args.fp32 else "autocast bf16"),
                       "workload": wl["name"], "batch": B, "iters": args.iters, "value": B * args.iters / (ms / 1e3),
                       "unit": "img/s (forward+backward, no optimizer)", "ms_per_iter": ms / args.iters,
                       "peak_hbm_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "loss": float(loss)}))
