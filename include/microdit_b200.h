@@ -103,11 +103,14 @@ MD_API int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_t* s
                      const float* scale, int64_t ldmod, int64_t T, const float* mean, const float* rstd,
                      void* dx, int dx_mode, float* dgamma, float* dshift, float* dscale, int64_t rows,
                      int64_t D, int prec, void* stream);
-/* Non-affine LayerNorm over a W-wide column slice, in place on bf16 (QK-norm: ln_q / ln_k utils.py:183-186,
- * 122-125).  fwd: x <- (x-mean)*rstd, rstd out.  bwd: dy <- rstd*(dy - mean(dy) - xhat*mean(dy*xhat)). */
-MD_API int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, float eps, int prec, void* stream);
+/* Non-affine LayerNorm over W-wide column slices, in place on bf16 (QK-norm: ln_q / ln_k utils.py:183-186,
+ * 122-125).  fwd: x <- (x-mean)*rstd, rstd out.  bwd: dy <- rstd*(dy - mean(dy) - xhat*mean(dy*xhat)).
+ * nslice (1..4) adjacent slices [s*W, (s+1)*W) of every row are normalised independently in ONE launch (q and k of
+ * the packed qkv projection); rstd is [nslice][rows]. */
+MD_API int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, int64_t nslice, float eps, int prec,
+                          void* stream);
 MD_API int md_rownorm_bwd(void* dy, int64_t ld_dy, const void* xhat, int64_t ld_x, const float* rstd, int64_t rows,
-                          int64_t W, int prec, void* stream);
+                          int64_t W, int64_t nslice, int prec, void* stream);
 /* Backward of x_new = x + gate[sample] * y (dit.py:236,238): dy(bf16) = gate * dres;
  * dgate[sample] += sum_t dres * y (atomic).  y / gate / dgate may be NULL (plain f32->bf16 cast). */
 MD_API int md_gate_bwd(const float* dres, const void* y, const float* gate, int64_t ldmod, int64_t T, void* dy,

@@ -75,6 +75,10 @@ __device__ __forceinline__ void st4a(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = raw;
 }
 __device__ __forceinline__ void st4a(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float2 ld2a(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ float2 ld2a(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ float ld1a(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ float ld1a(const float* p) { return *p; }
 __device__ __forceinline__ void st1a(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }

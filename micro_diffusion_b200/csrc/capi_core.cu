@@ -13,4 +13,4 @@ int md_set_error(int code, const char* msg) {
 }  // namespace md
 
 extern "C" const char* md_last_error(void) { return md::g_err; }
-extern "C" int md_abi_version(void) { return 3; }
+extern "C" int md_abi_version(void) { return 4; }

@@ -27,9 +27,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------- gate fwd
-// warp per row; gate weights staged in shared memory (E*D fp32 <= 64 KB).
-template <typename AT>
-__global__ void __launch_bounds__(256)
+// A warp owns kRowsPerWarp consecutive rows; gate weights staged in shared memory (E*D fp32 <= 64 KB).  The weights
+// of a column chunk are read from shared memory once and used for all the warp's rows: with one row per warp the
+// kernel was shared-memory-bandwidth bound (16 LDS.128 per 64 FMA), 5x off the HBM time of reading x once.
+constexpr int kRowsPerWarp = 4;
+constexpr int kGChunk = 2;  // 16-byte chunks per row a lane keeps in flight (x 4 rows)
+template <int ME, typename AT>
+__global__ void __launch_bounds__(256, ME <= 8 ? 2 : 1)
 moe_gate_fwd_kernel(const AT* __restrict__ x, const float* __restrict__ wg, float* __restrict__ probs, long long rows,
                     int D, int E) {
   extern __shared__ float swg[];  // [E][D]
@@ -37,55 +41,66 @@ moe_gate_fwd_kernel(const AT* __restrict__ x, const float* __restrict__ wg, floa
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  for (long long row = 1LL * blockIdx.x * 8 + warp; row < rows; row += 1LL * gridDim.x * 8) {
-    float acc[kMaxE];
+  for (long long row0 = (1LL * blockIdx.x * 8 + warp) * kRowsPerWarp; row0 < rows;
+       row0 += 1LL * gridDim.x * 8 * kRowsPerWarp) {
+    float acc[kRowsPerWarp][ME];
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e) acc[e] = 0.f;
-    for (int base = 0; base < nvec; base += 32 * kChunk) {
-      V8<AT> raw[kChunk];
+    for (int r = 0; r < kRowsPerWarp; ++r)
 #pragma unroll
-      for (int j = 0; j < kChunk; ++j) {  // all loads of this slab first
+      for (int e = 0; e < ME; ++e) acc[r][e] = 0.f;
+    for (int base = 0; base < nvec; base += 32 * kGChunk) {
+      V8<AT> raw[kGChunk][kRowsPerWarp];
+#pragma unroll
+      for (int j = 0; j < kGChunk; ++j) {  // all loads of this slab first
         const int i = base + lane + 32 * j;
-        raw[j] = i < nvec ? ldv8(x + row * D + 8 * i) : zerov8<AT>();
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r)
+          raw[j][r] = (i < nvec && row0 + r < rows) ? ldv8(x + (row0 + r) * D + 8 * i) : zerov8<AT>();
       }
 #pragma unroll
-      for (int j = 0; j < kChunk; ++j) {
+      for (int j = 0; j < kGChunk; ++j) {
         const int i = base + lane + 32 * j;
         if (i < nvec) {
-          float xv[8];
-          unpackv8(raw[j], xv);
+          float xv[kRowsPerWarp][8];
 #pragma unroll
-          for (int e = 0; e < kMaxE; ++e) {
+          for (int r = 0; r < kRowsPerWarp; ++r) unpackv8(raw[j][r], xv[r]);
+#pragma unroll
+          for (int e = 0; e < ME; ++e) {
             if (e < E) {
               const float4 w0 = *reinterpret_cast<const float4*>(swg + e * D + 8 * i);
               const float4 w1 = *reinterpret_cast<const float4*>(swg + e * D + 8 * i + 4);
-              acc[e] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x + xv[5] * w1.y +
-                        xv[6] * w1.z + xv[7] * w1.w;
+#pragma unroll
+              for (int r = 0; r < kRowsPerWarp; ++r)
+                acc[r][e] += xv[r][0] * w0.x + xv[r][1] * w0.y + xv[r][2] * w0.z + xv[r][3] * w0.w + xv[r][4] * w1.x +
+                             xv[r][5] * w1.y + xv[r][6] * w1.z + xv[r][7] * w1.w;
             }
           }
         }
       }
     }
-    float mx = -INFINITY;
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e) {
-      if (e < E) {
-        acc[e] = warp_sum(acc[e]);
-        mx = fmaxf(mx, acc[e]);
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < ME; ++e) {
+        if (e < E) {
+          acc[r][e] = warp_sum(acc[r][e]);
+          mx = fmaxf(mx, acc[r][e]);
+        }
       }
-    }
-    float den = 0.f;
+      float den = 0.f;
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e) {
-      if (e < E) {
-        acc[e] = expf(acc[e] - mx);
-        den += acc[e];
+      for (int e = 0; e < ME; ++e) {
+        if (e < E) {
+          acc[r][e] = expf(acc[r][e] - mx);
+          den += acc[r][e];
+        }
       }
-    }
-    if (lane == 0) {
+      if (lane == 0 && row0 + r < rows) {
 #pragma unroll
-      for (int e = 0; e < kMaxE; ++e)
-        if (e < E) probs[row * E + e] = acc[e] / den;
+        for (int e = 0; e < ME; ++e)
+          if (e < E) probs[(row0 + r) * E + e] = acc[r][e] / den;
+      }
     }
   }
 }
@@ -249,8 +264,10 @@ moe_combine_bwd_kernel(const AT* __restrict__ dy, const AT* __restrict__ h2, con
 }
 
 // ------------------------------------------------------------------------------------------ dx bwd
-// warp per token: dscores (softmax backward of the selected gate values) and
-// dx = sum_e dxin[slot] + dscores . Wg
+// Half-warp per token: dscores (softmax backward of the selected gate values) and
+// dx = sum_e dxin[slot] + dscores . Wg.  Lanes l and l + 16 work on the same columns of two consecutive tokens, so
+// their gate-weight reads hit the same shared-memory addresses (one wavefront pair instead of four per LDS.128):
+// with a full warp per token the weight reads, not HBM, set the pace.
 template <int ME, typename AT>
 __global__ void __launch_bounds__(256)
 moe_dx_bwd_kernel(const AT* __restrict__ dxin, const int32_t* __restrict__ inv, const float* __restrict__ dgval,
@@ -260,9 +277,10 @@ moe_dx_bwd_kernel(const AT* __restrict__ dxin, const int32_t* __restrict__ inv, 
   for (int i = threadIdx.x; i < E * D; i += blockDim.x) swg[i] = wg[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hl = lane & 15;
   const long long rows = 1LL * B * T;
   const int nvec = D >> 3;
-  for (long long row = 1LL * blockIdx.x * 8 + warp; row < rows; row += 1LL * gridDim.x * 8) {
+  for (long long row = 2 * (1LL * blockIdx.x * 8 + warp) + (lane >> 4); row < rows; row += 2LL * gridDim.x * 8) {
     const long long b = row / T;
     int slot[ME];
     float ds[ME];
@@ -282,12 +300,12 @@ moe_dx_bwd_kernel(const AT* __restrict__ dxin, const int32_t* __restrict__ inv, 
 #pragma unroll
     for (int e = 0; e < ME; ++e)
       if (e < E) ds[e] = probs[row * E + e] * (ds[e] - dot);
-    if (lane == 0) {
+    if (hl == 0) {
 #pragma unroll
       for (int e = 0; e < ME; ++e)
         if (e < E) dscores[row * E + e] = ds[e];
     }
-    for (int i = lane; i < nvec; i += 32) {
+    for (int i = hl; i < nvec; i += 16) {
       float acc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.f;
@@ -316,36 +334,72 @@ moe_dx_bwd_kernel(const AT* __restrict__ dxin, const int32_t* __restrict__ inv, 
 }
 
 // -------------------------------------------------------------------------------------- gate wgrad
-// block = 256 threads, slab of 128 rows; thread owns columns c, c+256, ... ; dwg[e][c] += sum_r ds[r][e]*x[r][c]
-template <typename AT>
+// dwg[e][c] += sum_r ds[r][e] * x[r][c].  Persistent blocks of 256 threads walk 64-row slabs; a thread owns the
+// column pairs (2t, 2t+1) + 512 j and keeps their E partial sums in registers over ALL its slabs, so the atomics
+// are paid once per block (the first version paid them per 128 rows and read ds with one LDS per FMA).
+constexpr int kWgSlab = 64;
+template <int ME, int NJ, typename AT>
 __global__ void __launch_bounds__(256)
 moe_gate_wgrad_kernel(const float* __restrict__ dscores, const AT* __restrict__ x, float* __restrict__ dwg,
                       long long rows, int D, int E) {
-  __shared__ float sds[128 * kMaxE];
-  const long long r0 = 1LL * blockIdx.x * 128;
-  const int nr = static_cast<int>(min(128LL, rows - r0));
-  for (int i = threadIdx.x; i < nr * E; i += blockDim.x) sds[i] = dscores[r0 * E + i];
-  __syncthreads();
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float acc[kMaxE];
+  __shared__ __align__(16) float sds[kWgSlab * ME];
+  const int c0 = 2 * threadIdx.x;
+  float acc[NJ][2][ME];
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e) acc[e] = 0.f;
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int e = 0; e < ME; ++e) acc[j][0][e] = acc[j][1][e] = 0.f;
+  const long long slabs = (rows + kWgSlab - 1) / kWgSlab;
+  for (long long sl = blockIdx.x; sl < slabs; sl += gridDim.x) {
+    const long long r0 = sl * kWgSlab;
+    const int nr = static_cast<int>(min(static_cast<long long>(kWgSlab), rows - r0));
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWgSlab * ME; i += blockDim.x) {
+      const int r = i / ME, e = i % ME;
+      sds[i] = (r < nr && e < E) ? dscores[(r0 + r) * E + e] : 0.f;
+    }
+    __syncthreads();
     for (int r = 0; r < nr; r += 8) {
-      float xv[8];
+      float xv[8][NJ][2];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) xv[u] = (r + u < nr) ? ld1a(x + (r0 + r + u) * D + c) : 0.f;
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int c = c0 + 512 * j;
+          const bool ok = (r + u < nr) && (c < D);
+          const float2 t = ok ? ld2a(x + (r0 + r + u) * D + c) : make_float2(0.f, 0.f);
+          xv[u][j][0] = t.x;
+          xv[u][j][1] = t.y;
+        }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        if (r + u < nr) {
+        float d[ME];
 #pragma unroll
-          for (int e = 0; e < kMaxE; ++e)
-            if (e < E) acc[e] += sds[(r + u) * E + e] * xv[u];
+        for (int e = 0; e < ME; e += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(sds + (r + u) * ME + e);  // rows >= nr hold zeros
+          d[e] = t.x; d[e + 1] = t.y; d[e + 2] = t.z; d[e + 3] = t.w;
         }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+          for (int e = 0; e < ME; ++e) {
+            acc[j][0][e] += d[e] * xv[u][j][0];
+            acc[j][1][e] += d[e] * xv[u][j][1];
+          }
       }
     }
+  }
 #pragma unroll
-    for (int e = 0; e < kMaxE; ++e)
-      if (e < E) atomicAdd(dwg + e * D + c, acc[e]);
+  for (int j = 0; j < NJ; ++j) {
+    const int c = c0 + 512 * j;
+    if (c < D) {
+#pragma unroll
+      for (int e = 0; e < ME; ++e)
+        if (e < E) {
+          atomicAdd(dwg + e * D + c, acc[j][0][e]);
+          atomicAdd(dwg + e * D + c + 1, acc[j][1][e]);
+        }
+    }
   }
 }
 
@@ -380,11 +434,17 @@ extern "C" int md_moe_gate_fwd(const void* x, const float* wg, float* probs, int
   if (smem > 200 * 1024) return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_gate_fwd: E*D too large for shared memory");
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(moe_gate_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(moe_gate_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_gate_fwd_kernel<8, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_gate_fwd_kernel<8, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_gate_fwd_kernel<16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(moe_gate_fwd_kernel<16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  MD_WITH_ACT(prec, moe_gate_fwd_kernel<AT><<<warp_grid(rows), 256, smem, ST(stream)>>>(CAP(AT, x), wg, probs, rows, (int)D, (int)E));
+  const int grid = warp_grid((rows + kRowsPerWarp - 1) / kRowsPerWarp);
+  if (E <= 8)
+    MD_WITH_ACT(prec, moe_gate_fwd_kernel<8, AT><<<grid, 256, smem, ST(stream)>>>(CAP(AT, x), wg, probs, rows, (int)D, (int)E));
+  else
+    MD_WITH_ACT(prec, moe_gate_fwd_kernel<16, AT><<<grid, 256, smem, ST(stream)>>>(CAP(AT, x), wg, probs, rows, (int)D, (int)E));
   return check_launch("md_moe_gate_fwd");
 }
 
@@ -457,10 +517,10 @@ extern "C" int md_moe_dx_bwd(const void* dxin, const int32_t* inv, const float* 
     attr = true;
   }
   if (E <= 8)
-    MD_WITH_ACT(prec, moe_dx_bwd_kernel<8, AT><<<warp_grid(B * T), 256, smem, ST(stream)>>>(
+    MD_WITH_ACT(prec, moe_dx_bwd_kernel<8, AT><<<warp_grid((B * T + 1) / 2), 256, smem, ST(stream)>>>(
                           CAP(AT, dxin), inv, dgval, probs, wg, dscores, AP(AT, dx), (int)B, (int)T, (int)E, (int)k, (int)D));
   else
-    MD_WITH_ACT(prec, moe_dx_bwd_kernel<16, AT><<<warp_grid(B * T), 256, smem, ST(stream)>>>(
+    MD_WITH_ACT(prec, moe_dx_bwd_kernel<16, AT><<<warp_grid((B * T + 1) / 2), 256, smem, ST(stream)>>>(
                           CAP(AT, dxin), inv, dgval, probs, wg, dscores, AP(AT, dx), (int)B, (int)T, (int)E, (int)k, (int)D));
   return check_launch("md_moe_dx_bwd");
 }
@@ -470,7 +530,20 @@ extern "C" int md_moe_gate_wgrad(const float* dscores, const void* x, float* dwg
   if (int rc = check_moe("md_moe_gate_wgrad", D, E)) return rc;
   if (rows == 0) return 0;
   if (!dscores || !x || !dwg) return md_set_error(MD_ERR_INVALID, "md_moe_gate_wgrad: null pointer");
-  MD_WITH_ACT(prec, moe_gate_wgrad_kernel<AT><<<(unsigned)((rows + 127) / 128), 256, 0, ST(stream)>>>(dscores, CAP(AT, x), dwg,
-                                                                                                     rows, (int)D, (int)E));
+  if (D > 2048) return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_gate_wgrad: D > 2048");
+  const long long slabs = (rows + kWgSlab - 1) / kWgSlab;
+  const unsigned grid = (unsigned)(slabs < 148 * 2 ? slabs : 148 * 2);
+#define WGRAD(ME, NJ) \
+  MD_WITH_ACT(prec, moe_gate_wgrad_kernel<ME, NJ, AT><<<grid, 256, 0, ST(stream)>>>(dscores, CAP(AT, x), dwg, rows, (int)D, (int)E))
+  if (E <= 8) {
+    if (D <= 512) WGRAD(8, 1);
+    else if (D <= 1024) WGRAD(8, 2);
+    else WGRAD(8, 4);
+  } else {
+    if (D <= 512) WGRAD(16, 1);
+    else if (D <= 1024) WGRAD(16, 2);
+    else WGRAD(16, 4);
+  }
+#undef WGRAD
   return check_launch("md_moe_gate_wgrad");
 }

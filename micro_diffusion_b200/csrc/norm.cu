@@ -259,11 +259,15 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // VEC = uint4 groups per lane (8 bf16 each): W <= 256 * VEC
 template <int VEC, typename AT>
 __global__ void __launch_bounds__(128)
-rownorm_fwd_kernel(AT* __restrict__ x, long long ld, float* __restrict__ rstd_out, long long rows, int W, float eps) {
+rownorm_fwd_kernel(AT* __restrict__ x, long long ld, float* __restrict__ rstd_out, long long rows, int W, int nslice,
+                   float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = W >> 3;
-  for (long long row = 1LL * blockIdx.x * 4 + warp; row < rows; row += 1LL * gridDim.x * 4) {
-    AT* p = x + row * ld;
+  // virtual row = (row, slice): the slices of one row are adjacent in memory and go to consecutive warps
+  for (long long vr = 1LL * blockIdx.x * 4 + warp; vr < rows * nslice; vr += 1LL * gridDim.x * 4) {
+    const long long row = vr / nslice;
+    const int sl = static_cast<int>(vr - row * nslice);
+    AT* p = x + row * ld + sl * W;
     V8<AT> raw[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -290,7 +294,7 @@ rownorm_fwd_kernel(AT* __restrict__ x, long long ld, float* __restrict__ rstd_ou
       }
     }
     const float rstd = rsqrtf(warp_sum(ss) / W + eps);
-    if (lane == 0) rstd_out[row] = rstd;
+    if (lane == 0) rstd_out[sl * rows + row] = rstd;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int i = lane + 32 * j;
@@ -308,12 +312,14 @@ rownorm_fwd_kernel(AT* __restrict__ x, long long ld, float* __restrict__ rstd_ou
 template <int VEC, typename AT>
 __global__ void __launch_bounds__(128)
 rownorm_bwd_kernel(AT* __restrict__ dy, long long ld_dy, const AT* __restrict__ xhat, long long ld_x,
-                   const float* __restrict__ rstd, long long rows, int W) {
+                   const float* __restrict__ rstd, long long rows, int W, int nslice) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = W >> 3;
-  for (long long row = 1LL * blockIdx.x * 4 + warp; row < rows; row += 1LL * gridDim.x * 4) {
-    AT* pd = dy + row * ld_dy;
-    const AT* px = xhat + row * ld_x;
+  for (long long vr = 1LL * blockIdx.x * 4 + warp; vr < rows * nslice; vr += 1LL * gridDim.x * 4) {
+    const long long row = vr / nslice;
+    const int sl = static_cast<int>(vr - row * nslice);
+    AT* pd = dy + row * ld_dy + sl * W;
+    const AT* px = xhat + row * ld_x + sl * W;
     V8<AT> rd[VEC], rx[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -321,7 +327,7 @@ rownorm_bwd_kernel(AT* __restrict__ dy, long long ld_dy, const AT* __restrict__ 
       rd[j] = i < nvec ? ldv8(pd + 8 * i) : zerov8<AT>();
       rx[j] = i < nvec ? ldv8(px + 8 * i) : zerov8<AT>();
     }
-    const float rs = rstd[row];
+    const float rs = rstd[sl * rows + row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -496,31 +502,33 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
   return check_launch("md_ln_bwd");
 }
 
-extern "C" int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, float eps, int prec,
-                              void* stream) {
+extern "C" int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, int64_t nslice, float eps,
+                              int prec, void* stream) {
   if (rows == 0) return 0;
+  if (nslice < 1 || nslice > 4) return md_set_error(MD_ERR_INVALID, "md_rownorm_fwd: need 1 <= nslice <= 4");
   if (!x || !rstd) return md_set_error(MD_ERR_INVALID, "md_rownorm_fwd: null pointer");
   if (W % 8 != 0 || W > 2048 || ld % 8 != 0)
     return md_set_error(MD_ERR_UNSUPPORTED, "md_rownorm_fwd: need W % 8 == 0, W <= 2048, ld % 8 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (W <= 1024)
-    MD_WITH_ACT(prec, rownorm_fwd_kernel<4, AT><<<row_grid(rows), 128, 0, st>>>(AP(AT, x), ld, rstd, rows, static_cast<int>(W), eps));
+    MD_WITH_ACT(prec, rownorm_fwd_kernel<4, AT><<<row_grid(rows * nslice), 128, 0, st>>>(AP(AT, x), ld, rstd, rows, static_cast<int>(W), static_cast<int>(nslice), eps));
   else
-    MD_WITH_ACT(prec, rownorm_fwd_kernel<8, AT><<<row_grid(rows), 128, 0, st>>>(AP(AT, x), ld, rstd, rows, static_cast<int>(W), eps));
+    MD_WITH_ACT(prec, rownorm_fwd_kernel<8, AT><<<row_grid(rows * nslice), 128, 0, st>>>(AP(AT, x), ld, rstd, rows, static_cast<int>(W), static_cast<int>(nslice), eps));
   return check_launch("md_rownorm_fwd");
 }
 
 extern "C" int md_rownorm_bwd(void* dy, int64_t ld_dy, const void* xhat, int64_t ld_x, const float* rstd, int64_t rows,
-                              int64_t W, int prec, void* stream) {
+                              int64_t W, int64_t nslice, int prec, void* stream) {
   if (rows == 0) return 0;
+  if (nslice < 1 || nslice > 4) return md_set_error(MD_ERR_INVALID, "md_rownorm_bwd: need 1 <= nslice <= 4");
   if (!dy || !xhat || !rstd) return md_set_error(MD_ERR_INVALID, "md_rownorm_bwd: null pointer");
   if (W % 8 != 0 || W > 2048 || ld_dy % 8 != 0 || ld_x % 8 != 0)
     return md_set_error(MD_ERR_UNSUPPORTED, "md_rownorm_bwd: need W % 8 == 0, W <= 2048, ld % 8 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (W <= 1024)
-    MD_WITH_ACT(prec, rownorm_bwd_kernel<4, AT><<<row_grid(rows), 128, 0, st>>>(AP(AT, dy), ld_dy, CAP(AT, xhat), ld_x, rstd, rows, static_cast<int>(W)));
+    MD_WITH_ACT(prec, rownorm_bwd_kernel<4, AT><<<row_grid(rows * nslice), 128, 0, st>>>(AP(AT, dy), ld_dy, CAP(AT, xhat), ld_x, rstd, rows, static_cast<int>(W), static_cast<int>(nslice)));
   else
-    MD_WITH_ACT(prec, rownorm_bwd_kernel<8, AT><<<row_grid(rows), 128, 0, st>>>(AP(AT, dy), ld_dy, CAP(AT, xhat), ld_x, rstd, rows, static_cast<int>(W)));
+    MD_WITH_ACT(prec, rownorm_bwd_kernel<8, AT><<<row_grid(rows * nslice), 128, 0, st>>>(AP(AT, dy), ld_dy, CAP(AT, xhat), ld_x, rstd, rows, static_cast<int>(W), static_cast<int>(nslice)));
   return check_launch("md_rownorm_bwd");
 }
 

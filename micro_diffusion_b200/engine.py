@@ -91,9 +91,8 @@ class Engine:
         sv.x = self._ln_add(x, pend, sv.xm, sv.mean1, sv.rstd1, gamma=P[n + ".norm1.weight"], shift=sh_a, scale=sc_a, T=T)
         sv.qkv = o.empty((M, 3 * h), BF16)
         o.gemm(sv.xm, st.W(n + ".attn.qkv.weight"), sv.qkv)
-        sv.rq = o.empty((M,), F32); sv.rk = o.empty((M,), F32)
-        o.rownorm_fwd(sv.qkv[:, :h], sv.rq, eps)
-        o.rownorm_fwd(sv.qkv[:, h:2 * h], sv.rk, eps)
+        sv.rqk = o.empty((2, M), F32)  # ln_q and ln_k (utils.py:183-186) in one launch: adjacent slices of qkv
+        o.rownorm_fwd(sv.qkv[:, :2 * h], sv.rqk, eps, nslice=2)
         sv.att = o.empty((M, h), BF16); sv.lse = o.empty((B, bs.heads, T), F32)
         o.attn_fwd(sv.qkv[:, :h], sv.qkv[:, h:2 * h], sv.qkv[:, 2 * h:], sv.att, sv.lse, B, bs.heads, T, T, hd)
         sv.ya = o.empty((M, D), BF16)
@@ -210,8 +209,7 @@ class Engine:
         delta = o.empty((B, bs.heads, T), F32)
         o.attn_bwd(datt, sv.qkv[:, :h], sv.qkv[:, h:2 * h], sv.qkv[:, 2 * h:], sv.att, sv.lse, delta, dqkv[:, :h],
                    dqkv[:, h:2 * h], dqkv[:, 2 * h:], B, bs.heads, T, T, hd)
-        o.rownorm_bwd(dqkv[:, :h], sv.qkv[:, :h], sv.rq)
-        o.rownorm_bwd(dqkv[:, h:2 * h], sv.qkv[:, h:2 * h], sv.rk)
+        o.rownorm_bwd(dqkv[:, :2 * h], sv.qkv[:, :2 * h], sv.rqk, nslice=2)
         dxm1 = o.empty((M, D), BF16)
         o.gemm(dqkv, st.WT(n + ".attn.qkv.weight"), dxm1)
         self._wgrad(dqkv, sv.xm, st.G(n + ".attn.qkv.weight"))
@@ -250,9 +248,8 @@ class Engine:
         o.ln_fwd(s.y0, s.yn1, s.m1, s.r1, gamma=P["y_emb_preprocess.norm1.weight"], T=L, eps=eps)
         s.qkv = o.empty((R, 3 * D), BF16)
         o.gemm(s.yn1, st.W("y_emb_preprocess.attn.qkv.weight"), s.qkv)
-        s.rq = o.empty((R,), F32); s.rk = o.empty((R,), F32)
-        o.rownorm_fwd(s.qkv[:, :D], s.rq, eps)
-        o.rownorm_fwd(s.qkv[:, D:2 * D], s.rk, eps)
+        s.rqk = o.empty((2, R), F32)
+        o.rownorm_fwd(s.qkv[:, :2 * D], s.rqk, eps, nslice=2)
         s.att = o.empty((R, D), BF16); s.lse = o.empty((B, H, L), F32)
         o.attn_fwd(s.qkv[:, :D], s.qkv[:, D:2 * D], s.qkv[:, 2 * D:], s.att, s.lse, B, H, L, L, hd)
         s.y1 = o.empty((R, D), F32)
@@ -365,8 +362,7 @@ class Engine:
         dqkv = o.empty((R, 3 * D), BF16); delta = o.empty((B, H, L), F32)
         o.attn_bwd(datt, s.qkv[:, :D], s.qkv[:, D:2 * D], s.qkv[:, 2 * D:], s.att, s.lse, delta, dqkv[:, :D],
                    dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, H, L, L, hd)
-        o.rownorm_bwd(dqkv[:, :D], s.qkv[:, :D], s.rq)
-        o.rownorm_bwd(dqkv[:, D:2 * D], s.qkv[:, D:2 * D], s.rk)
+        o.rownorm_bwd(dqkv[:, :2 * D], s.qkv[:, :2 * D], s.rqk, nslice=2)
         o.gemm(dqkv, st.WT("y_emb_preprocess.attn.qkv.weight"), dyn)
         self._wgrad(dqkv, s.yn1, st.G("y_emb_preprocess.attn.qkv.weight"))
         o.ln_bwd(dyn, s.y0, s.m1, s.r1, gamma=P["y_emb_preprocess.norm1.weight"], T=L, dx=dy2, dx_mode=0,

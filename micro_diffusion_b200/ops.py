@@ -28,8 +28,8 @@ _I = C.c_int
 _PROTOS = {
     "md_ln_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I64, _F, _I, _P],
     "md_ln_bwd": [_P, _P, _I, _P, _P, _P, _I64, _I64, _P, _P, _P, _I, _P, _P, _P, _I64, _I64, _I, _P],
-    "md_rownorm_fwd": [_P, _I64, _P, _I64, _I64, _F, _I, _P],
-    "md_rownorm_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I, _P],
+    "md_rownorm_fwd": [_P, _I64, _P, _I64, _I64, _I64, _F, _I, _P],
+    "md_rownorm_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I, _P],
     "md_gate_bwd": [_P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _I, _P],
     "md_attn_fwd": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
     "md_attn_fwd_tc": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P],
@@ -260,14 +260,17 @@ class CudaOps:
                    _ptr(gamma), sc, ld or ld2 or ld3, T, mean.data_ptr(), rstd.data_ptr(), _ptr(dx), dx_mode,
                    _ptr(dgamma), dsh, dsc, rows, D)
 
-    def rownorm_fwd(self, x, rstd, eps=1e-6):
-        rows, W = x.shape
-        self._call("md_rownorm_fwd", x.data_ptr(), x.stride(0), rstd.data_ptr(), rows, W, eps)
+    def rownorm_fwd(self, x, rstd, eps=1e-6, nslice=1):
+        """x [rows, nslice*W]: every W-wide slice normalised on its own; rstd [nslice, rows] ([rows] for one slice)."""
+        rows, W = x.shape[0], x.shape[1] // nslice
+        assert rstd.numel() == nslice * rows and x.shape[1] == nslice * W
+        self._call("md_rownorm_fwd", x.data_ptr(), x.stride(0), rstd.data_ptr(), rows, W, nslice, eps)
 
-    def rownorm_bwd(self, dy, xhat, rstd):
-        rows, W = dy.shape
+    def rownorm_bwd(self, dy, xhat, rstd, nslice=1):
+        rows, W = dy.shape[0], dy.shape[1] // nslice
+        assert rstd.numel() == nslice * rows and xhat.shape[1] == dy.shape[1] == nslice * W
         self._call("md_rownorm_bwd", dy.data_ptr(), dy.stride(0), xhat.data_ptr(), xhat.stride(0), rstd.data_ptr(),
-                   rows, W)
+                   rows, W, nslice)
 
     def gate_bwd(self, dres, dy, *, y=None, gate=None, dgate=None, T):
         rows, D = dres.shape

@@ -172,20 +172,28 @@ class EmuOps:
         if dgamma is not None:
             dgamma.add_((Bc * ((1 + scale.float()) if scale is not None else 1.0)).sum(0))
 
-    def rownorm_fwd(self, x, rstd, eps=1e-6):
+    def rownorm_fwd(self, x, rstd, eps=1e-6, nslice=1):
         self.launches += 1
-        xv = _f(x)
-        mu = xv.mean(1, keepdim=True)
-        rs = torch.rsqrt(((xv - mu) ** 2).mean(1, keepdim=True) + eps)
-        x.copy_((xv - mu) * rs)
-        rstd.copy_(rs.flatten())
+        rows, W = x.shape[0], x.shape[1] // nslice
+        rv = rstd.view(nslice, rows)
+        for s in range(nslice):
+            xs = x[:, s * W:(s + 1) * W]
+            xv = _f(xs)
+            mu = xv.mean(1, keepdim=True)
+            rs = torch.rsqrt(((xv - mu) ** 2).mean(1, keepdim=True) + eps)
+            xs.copy_((xv - mu) * rs)
+            rv[s].copy_(rs.flatten())
 
-    def rownorm_bwd(self, dy, xhat, rstd):
+    def rownorm_bwd(self, dy, xhat, rstd, nslice=1):
         self.launches += 1
-        d, xh = _f(dy), _f(xhat)
-        m1 = d.mean(1, keepdim=True)
-        m2 = (d * xh).mean(1, keepdim=True)
-        dy.copy_(rstd[:, None] * (d - m1 - xh * m2))
+        rows, W = dy.shape[0], dy.shape[1] // nslice
+        rv = rstd.view(nslice, rows)
+        for s in range(nslice):
+            ds = dy[:, s * W:(s + 1) * W]
+            d, xh = _f(ds), _f(xhat[:, s * W:(s + 1) * W])
+            m1 = d.mean(1, keepdim=True)
+            m2 = (d * xh).mean(1, keepdim=True)
+            ds.copy_(rv[s][:, None] * (d - m1 - xh * m2))
 
     def gate_bwd(self, dres, dy, *, y=None, gate=None, dgate=None, T):
         self.launches += 1

@@ -63,7 +63,7 @@ def test_c_abi_exports_every_declared_symbol():
         if name in _PROTOS:
             nargs = len([a for a in args.split(",") if a.strip()])
             assert nargs == len(_PROTOS[name]), f"ctypes prototype of {name} is out of date"
-    assert lib.md_abi_version() == 3
+    assert lib.md_abi_version() == 4
     # struct layout of md_gemm_args must match the header field order
     fields = re.search(r"typedef struct md_gemm_args \{(.*?)\} md_gemm_args;", header, flags=re.S).group(1)
     names = re.findall(r"(\w+)\s*(?:,|;)", re.sub(r"\b(const|void|int64_t|int32_t|float)\b|\*", " ", fields))

@@ -110,19 +110,20 @@ def test_ln_gather_scatter_and_bf16_out():
     close(cu3[6], cpu3[6], "bf16 dx")
 
 
-@pytest.mark.parametrize("rows,W,ld,off", [(200, 512, 1536, 512), (77, 1024, 2048, 0), (33, 64, 192, 64)])
-def test_rownorm(rows, W, ld, off):
+@pytest.mark.parametrize("rows,W,ld,off,ns", [(200, 512, 1536, 512, 1), (77, 1024, 2048, 0, 1), (33, 64, 192, 64, 1),
+                                              (201, 512, 1536, 0, 2), (77, 768, 2304, 0, 2), (5, 64, 256, 64, 3)])
+def test_rownorm(rows, W, ld, off, ns):
     buf = rnd((rows, ld), 1, BF16, 3.0)
-    rstd = torch.zeros(rows)
+    rstd = torch.zeros(ns, rows)
 
     def f(o, buf, rstd):
-        o.rownorm_fwd(buf[:, off:off + W], rstd, 1e-6)
+        o.rownorm_fwd(buf[:, off:off + ns * W], rstd, 1e-6, nslice=ns)
     cpu, cu = both(f, [buf, rstd])
     close(cu[0], cpu[0], "rownorm x"); close(cu[1], cpu[1], "rstd", 1e-3)
     dy = rnd((rows, ld), 2, BF16)
 
     def b(o, dy, xh, rstd):
-        o.rownorm_bwd(dy[:, off:off + W], xh[:, off:off + W], rstd)
+        o.rownorm_bwd(dy[:, off:off + ns * W], xh[:, off:off + ns * W], rstd, nslice=ns)
     cpu2, cu2 = both(b, [dy, cpu[0], cpu[1]])
     close(cu2[0], cpu2[0], "rownorm dy")
 
@@ -193,7 +194,8 @@ def test_swiglu_act():
     close(cu[2], cpu[2], "gelu tanh bwd", 1e-4)
 
 
-@pytest.mark.parametrize("B,T,E,cap,D", [(3, 64, 8, 2.0, 256), (2, 256, 8, 2.0, 768), (2, 100, 4, 1.0, 128)])
+@pytest.mark.parametrize("B,T,E,cap,D", [(3, 64, 8, 2.0, 256), (2, 256, 8, 2.0, 768), (2, 100, 4, 1.0, 128), (3, 67, 8, 2.0, 1024),
+                                          (1, 33, 16, 2.0, 512)])
 def test_moe_ops(B, T, E, cap, D):
     k = int(cap * T / E)
     rows = B * T
