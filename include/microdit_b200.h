@@ -53,6 +53,8 @@ MD_API int md_abi_version(void);
                             /*           C2(bf16, optional) = alpha*acc+bias                         */
 #define MD_EPI_ATOMIC_F32 3 /* C(f32) += alpha*acc   (red.global.add; the only mode allowing splits) */
 #define MD_EPI_ACT_DUAL 4   /* C(bf16) = pre = alpha*acc+bias ; C2(bf16) = act(pre); act: 0 gelu-erf, 1 gelu-tanh */
+#define MD_EPI_ACT_GRAD 5   /* C(bf16) = alpha*acc * act'(aux) (no bias): the dgrad GEMM of an activation's output applies the
+                             * activation's derivative at the saved pre-activation aux (bf16, indexed like C) */
 
 typedef struct md_gemm_args {
   const void* A; /* bf16 */
@@ -62,6 +64,7 @@ typedef struct md_gemm_args {
   const void* bias; /* f32 [batch][N] or NULL */
   const void* res;  /* f32, indexed like C (may alias C); row taken modulo res_mod when res_mod > 0 */
   const void* gate; /* f32 [M / rows_per_gate][ldgate] or NULL (=1) */
+  const void* aux;  /* bf16, indexed like C: the saved pre-activation of MD_EPI_ACT_GRAD */
   int64_t M, N, K;
   int64_t lda, ldb, ldc; /* row pitches in elements */
   int64_t batch;         /* >= 1; batch strides in elements */

@@ -22,7 +22,7 @@ class MicroditLibraryError(RuntimeError):
 class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("C2", C.c_void_p),
-        ("bias", C.c_void_p), ("res", C.c_void_p), ("gate", C.c_void_p),
+        ("bias", C.c_void_p), ("res", C.c_void_p), ("gate", C.c_void_p), ("aux", C.c_void_p),
         ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
         ("batch", C.c_int64),

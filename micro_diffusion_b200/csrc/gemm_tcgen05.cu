@@ -10,9 +10,11 @@
 //   kMN=false  "NT":  C[M,N] = sum_k A[M,k] * B[N,k]     A,B row-major with k contiguous (K-major)
 //   kMN=true   "TN":  C[P,Q] = sum_r A[r,P] * B[r,Q]     A,B row-major with the reduction index r
 //                     strided (MN-major UMMA operands) -- the weight-gradient contraction.
-// Roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator, warps4-7 = epilogue
-// (warp w reads TMEM lanes 32*(w%4)..+31; MD_EPI_WARPS=8 adds a second warp per lane quarter, half of the columns each
-// -- measured equal or slightly slower once the epilogue stopped spilling its accumulator chunk to local memory).
+// Roles: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator, warps 4.. = epilogue (warp w reads TMEM
+// lanes 32*(w%4)..+31).  kEpiW = 4 epilogue warps for the store-only tails (8 measured equal or slightly slower once
+// the epilogue stopped spilling its accumulator chunk to local memory); kEpiW = 8 (a second warp per lane quarter,
+// half of the columns each) for the math-heavy tails -- GELU + dual store, activation gradient -- where one warp per
+// scheduler cannot hide the MUFU / FMA latency of 256 activations per row and tile.
 //
 // kCtas = 2 is the Blackwell CTA-pair mode: two CTAs of a cluster (adjacent SMs) run ONE tcgen05.mma.cta_group::2
 // with M = 256 (128 rows of D in each CTA's TMEM); every CTA stages its own 128 rows of A and only HALF of the B
@@ -34,25 +36,21 @@ namespace md {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-#ifndef MD_EPI_WARPS
-#define MD_EPI_WARPS 4
-#endif
-constexpr int kEpiWarps = MD_EPI_WARPS;  // 4 (one per TMEM lane quarter) or 8 (two per quarter, half of the columns each)
-static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps: 4 or 8");
-constexpr int kColSplit = kEpiWarps / 4;
-constexpr int kThreads = 128 + 32 * kEpiWarps;  // 4 control warps + the epilogue warps
 
-template <int BLOCK_N, int kCtas = 1>
+template <int BLOCK_N, int kCtas, int kEpiW>
 struct GemmCfg {
+  static_assert(kEpiW == 4 || kEpiW == 8, "epilogue warps: 4 or 8");
+  static constexpr int kColSplit = kEpiW / 4;
+  static constexpr int kThreads = 128 + 32 * kEpiW;  // 4 control warps + the epilogue warps
   static constexpr int kStageBytesA = kBlockM * kBlockK * 2;
   static constexpr int kStageBytesB = (BLOCK_N / kCtas) * kBlockK * 2;  // a CTA of a pair stages half of B
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = (kStageBytes > 40 * 1024) ? 4 : (kStageBytes > 30 * 1024 ? 6 : 7);
   static constexpr int kAccStages = 2;
   static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 256 or 512 (power of two)
-  // epilogue staging for the TMA store: 8 warps x 2 buffers x (32 rows x 32 bf16 = 2 KB, 64B-swizzled)
+  // epilogue staging for the TMA store: per warp 2 buffers x (32 rows x 32 bf16 = 2 KB, 64B-swizzled)
   static constexpr int kStoreBufBytes = 32 * 32 * 2;
-  static constexpr int kStoreBytes = kEpiWarps * 2 * kStoreBufBytes;
+  static constexpr int kStoreBytes = kEpiW * 2 * kStoreBufBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -73,6 +71,27 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float e = __expf(2.0f * u);                    // tanh(u) = 1 - 2/(e^{2u}+1)
   const float th = 1.0f - __fdividef(2.0f, e + 1.0f);
   return 0.5f * x * (1.0f + th);
+}
+
+// d gelu / dx for the activation-gradient tail; shares exp(-x^2/2) between the erf and the density term.
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float ez = __expf(-z * z);                     // exp(-x^2 / 2)
+  const float e = 1.0f - poly * t * ez;                // erf(|x| / sqrt2)
+  const float cdf = 0.5f * (1.0f + copysignf(e, x));
+  return fmaf(x * 0.3989422804014327f, ez, cdf);
+}
+__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * fmaf(k1 * x, x * x, x);
+  const float e = __expf(2.0f * u);
+  const float th = 1.0f - __fdividef(2.0f, e + 1.0f);
+  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * k0 * fmaf(3.0f * k1 * x, x, 1.0f);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b);
@@ -102,11 +121,16 @@ __device__ __forceinline__ void decode_tile(int r, int m_blocks, int n_blocks, i
   nb = band * kBand + rr % bw;
 }
 
-template <int BLOCK_N, bool kMN, int kCtas>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BLOCK_N, bool kMN, int kCtas, int kEpiW>
+__global__ void __launch_bounds__(128 + 32 * kEpiW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
-  using Cfg = GemmCfg<BLOCK_N, kCtas>;
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                    const GemmDev p) {
+  using Cfg = GemmCfg<BLOCK_N, kCtas, kEpiW>;
+  constexpr int kColSplit = Cfg::kColSplit;
+  // the 8-warp instantiations serve the activation tails only (host dispatch): compiling the residual / atomic / fp32
+  // tails out keeps their prefetch registers from pushing the 384-thread kernel over its 168-register budget
+  constexpr bool kMath = kEpiW == 8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -123,7 +147,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.tma_store) tma_prefetch_desc(&tmC);
+    if (p.tma_store) {
+      tma_prefetch_desc(&tmC);
+      if (p.epi == EPI_ACT_DUAL) tma_prefetch_desc(&tmC2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -132,7 +159,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps * kCtas);  // one arrive per epilogue warp (of both CTAs in pair mode)
+      mbar_init(&tempty_bar[i], kEpiW * kCtas);  // one arrive per epilogue warp (of both CTAs in pair mode)
     }
     mbar_fence_init();
   }
@@ -279,7 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.gate != nullptr && row_ok) gate_row = p.gate + 1LL * (row / p.rows_per_gate) * p.ldgate;
       const int colbase = nb * BLOCK_N + half * (BLOCK_N / kColSplit);
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / kColSplit);
-      const bool want_res = (p.epi == EPI_RESID_F32) && row_ok && has_k;
+      const bool want_res = !kMath && (p.epi == EPI_RESID_F32) && row_ok && has_k;
 
       // residual prefetch for chunk 0 is independent of the accumulator: issue it before waiting on the MMAs
       float4 resn[8];
@@ -300,7 +327,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       };
-      if (p.epi == EPI_RESID_F32) load_res(0);
+      if constexpr (!kMath) { if (p.epi == EPI_RESID_F32) load_res(0); }
+      // saved pre-activation tile of the activation-gradient tail (bf16, indexed like C): same software pipeline
+      uint4 auxn[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+      auto load_aux = [&](int c) {
+        const int col0 = colbase + c * 32;
+        const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux) + crow + col0;
+        const bool live = row_ok && has_k && col0 < p.N;
+        const bool vec = live && (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(ax) & 15) == 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (vec) {
+            auxn[j] = *reinterpret_cast<const uint4*>(ax + 8 * j);
+          } else {
+            uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+            if (live) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                if (col0 + 8 * j + e < p.N) {
+                  const uint32_t b = static_cast<uint32_t>(__bfloat16_as_ushort(ax[8 * j + e])) << (16 * (e & 1));
+                  if ((e >> 1) == 0) w0 |= b;
+                  else if ((e >> 1) == 1) w1 |= b;
+                  else if ((e >> 1) == 2) w2 |= b;
+                  else w3 |= b;
+                }
+              }
+            }
+            auxn[j] = make_uint4(w0, w1, w2, w3);
+          }
+        }
+      };
+      if (p.epi == EPI_ACT_GRAD) load_aux(0);
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
@@ -316,11 +373,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rnext[j]) * p.alpha;
 #pragma unroll
         for (int j = 0; j < 8; ++j) resv[j] = resn[j];
+        uint4 auxv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) auxv[j] = auxn[j];
         if (c + 1 < kChunksPerWarp) {  // software pipeline: next chunk's TMEM + residual loads fly during this chunk
           tmem_ld_32x32(tbase + (c + 1) * 32, rnext);
-          if (p.epi == EPI_RESID_F32) load_res(c + 1);
+          if constexpr (!kMath) { if (p.epi == EPI_RESID_F32) load_res(c + 1); }
+          if (p.epi == EPI_ACT_GRAD) load_aux(c + 1);
         }
         const int col0 = colbase + c * 32;
+        if (p.epi == EPI_ACT_GRAD) {  // C = acc * act'(pre): the dgrad GEMM hands the pre-activation gradient on directly
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t w = e == 0 ? auxv[j].x : e == 1 ? auxv[j].y : e == 2 ? auxv[j].z : auxv[j].w;
+              const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+              v[8 * j + 2 * e] *= p.act ? gelu_tanh_grad_fast(x0) : gelu_erf_grad_fast(x0);
+              v[8 * j + 2 * e + 1] *= p.act ? gelu_tanh_grad_fast(x1) : gelu_erf_grad_fast(x1);
+            }
+          }
+        }
         if (p.debug == 1) {
           if (v[0] == 123.456f && v[31] == -654.321f) reinterpret_cast<float*>(p.C)[0] = v[5];  // keep the loads alive
         } else if (p.tma_store) {
@@ -336,26 +409,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 32; ++j)
                 if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
             }
-            uint8_t* buf = my_stage + (store_it & 1) * Cfg::kStoreBufBytes;
-            if (lane == 0) tma_store_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
-            __syncwarp();
             const int sw = (lane >> 1) & 3;
+            if (p.epi == EPI_ACT_DUAL) {
+              // pre-activation and activation of the chunk leave together: the warp's two staging buffers hold one box each
+              // (the activation is taken on the bf16-rounded pre-activation, see the direct-store path below)
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 a;
-              a.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-              a.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-              a.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-              a.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-              *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ sw) << 4)) = a;
+              for (int j = 0; j < 4; ++j) {
+                float x[8], y[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  x[e] = bf16_round(v[8 * j + e]);
+                  y[e] = p.act ? gelu_tanh_fast(x[e]) : gelu_erf_fast(x[e]);
+                }
+                *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ sw) << 4)) =
+                    pack_bf16x8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+                *reinterpret_cast<uint4*>(my_stage + Cfg::kStoreBufBytes + lane * 64 + ((j ^ sw) << 4)) =
+                    pack_bf16x8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmC, my_stage, col0, row0, bz);
+                tma_store_3d(&tmC2, my_stage + Cfg::kStoreBufBytes, col0, row0, bz);
+                tma_store_commit();
+              }
+            } else {
+              uint8_t* buf = my_stage + (store_it & 1) * Cfg::kStoreBufBytes;
+              if (lane == 0) tma_store_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 a;
+                a.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+                a.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                a.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                a.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ sw) << 4)) = a;
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmC, buf, col0, row0, bz);
+                tma_store_commit();
+              }
+              ++store_it;
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tmC, buf, col0, row0, bz);
-              tma_store_commit();
-            }
-            ++store_it;
           }
         } else
         // No divergent `continue`: every lane must reach the next (warp-aligned) tcgen05 instruction together.
@@ -366,7 +466,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; ++j)
               if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
           }
-          if (p.epi == EPI_ATOMIC_F32) {
+          if (!kMath && p.epi == EPI_ATOMIC_F32) {
             float* dst = reinterpret_cast<float*>(p.C) + crow + col0;
             if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -413,7 +513,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           } else {
-            if (p.epi == EPI_RESID_F32) {
+            if (!kMath && p.epi == EPI_RESID_F32) {
               if (p.C2 != nullptr) {  // bf16 copy of the raw GEMM result (needed by backward for d(gate))
                 __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
                 if (ncols == 32 && ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
@@ -438,7 +538,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v[4 * j] += resv[j].x; v[4 * j + 1] += resv[j].y; v[4 * j + 2] += resv[j].z; v[4 * j + 3] += resv[j].w;
               }
             }
-            if (p.epi == EPI_STORE_BF16) {
+            if (kMath || p.epi == EPI_STORE_BF16 || p.epi == EPI_ACT_GRAD) {
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
               if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -516,10 +616,10 @@ static int make_store_map(CUtensorMap* map, void* ptr, long long cols, long long
   return 0;
 }
 
-template <int BLOCK_N, bool kMN, int kCtas>
+template <int BLOCK_N, bool kMN, int kCtas, int kEpiW = 4>
 static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, kCtas>;
-  CUtensorMap tmA, tmB, tmC;
+  using Cfg = GemmCfg<BLOCK_N, kCtas, kEpiW>;
+  CUtensorMap tmA, tmB, tmC, tmC2;
   int rc;
   if (!kMN) {
     rc = make_map(&tmA, a->A, a->K, a->M, a->batch, a->lda, a->strideA, kBlockM);
@@ -545,15 +645,24 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
   }
   dev.debug = debug_env;
   dev.tma_store = 0;
-  if (tma_store_env && a->epilogue == EPI_STORE_BF16 && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 &&
-      (a->ldc % 8) == 0 && (a->batch == 1 || (a->strideC % 8) == 0)) {
+  const bool bf16_out = a->epilogue == EPI_STORE_BF16 || a->epilogue == EPI_ACT_GRAD || a->epilogue == EPI_ACT_DUAL;
+  const bool dual = a->epilogue == EPI_ACT_DUAL;
+  if (tma_store_env && bf16_out && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (a->ldc % 8) == 0 &&
+      (a->batch == 1 || (a->strideC % 8) == 0) && (!dual || (reinterpret_cast<uintptr_t>(a->C2) & 15) == 0)) {
     rc = make_store_map(&tmC, a->C, a->N, a->M, a->batch, a->ldc, a->strideC);
     if (rc) return rc;
+    if (dual) {
+      rc = make_store_map(&tmC2, a->C2, a->N, a->M, a->batch, a->ldc, a->strideC);
+      if (rc) return rc;
+    } else {
+      tmC2 = tmC;
+    }
     dev.tma_store = 1;
   } else {
     tmC = tmA;  // unused
+    tmC2 = tmA;
   }
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, kMN, kCtas>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, kMN, kCtas, kEpiW>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -567,7 +676,7 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
   const int grid = static_cast<int>((tiles < slots ? tiles : slots) * kCtas);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -577,7 +686,7 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, dev);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, dev);
   if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
   return 0;
 }
@@ -595,6 +704,10 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
     return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: residual epilogue needs res");
   if (a->epilogue == EPI_ACT_DUAL && a->C2 == nullptr)
     return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: activation epilogue needs C2");
+  if (a->epilogue == EPI_ACT_GRAD && a->aux == nullptr)
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: activation-gradient epilogue needs aux (the saved pre-activation)");
+  if (a->epilogue == EPI_ACT_GRAD && a->bias != nullptr)
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: the activation-gradient epilogue takes no bias");
   if (a->gate != nullptr && a->rows_per_gate <= 0)
     return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: gate needs rows_per_gate > 0");
   int splits = a->splits > 0 ? a->splits : 1;
@@ -621,6 +734,7 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   dev.bias = reinterpret_cast<const float*>(a->bias);
   dev.res = reinterpret_cast<const float*>(a->res);
   dev.gate = reinterpret_cast<const float*>(a->gate);
+  dev.aux = a->aux;
   dev.M = static_cast<int>(a->M); dev.N = static_cast<int>(a->N); dev.K = static_cast<int>(a->K);
   dev.batch = static_cast<int>(a->batch); dev.splits = splits;
   dev.ldc = a->ldc; dev.strideC = a->strideC; dev.strideBias = a->strideBias;
@@ -662,10 +776,21 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
     ctas_forced = e ? atoi(e) : 0;
   }
   const bool pair = ctas_forced == 2 || (ctas_forced == 0 && a->M > kBlockM);
+  // eight epilogue warps for the tails that do real math per element (NT only: the weight-gradient layout never has one)
+  static int epi8_env = -1;
+  if (epi8_env == -1) {
+    const char* e = getenv("MD_GEMM_EPI8");
+    epi8_env = e ? atoi(e) : 1;
+  }
+  const bool math_tail = (a->epilogue == EPI_ACT_DUAL || a->epilogue == EPI_ACT_GRAD) && !mn && epi8_env;
   if (pair) {
     if (mn) return use256 ? launch<256, true, 2>(a, dev, sm_count, stream) : launch<128, true, 2>(a, dev, sm_count, stream);
+    if (math_tail)
+      return use256 ? launch<256, false, 2, 8>(a, dev, sm_count, stream) : launch<128, false, 2, 8>(a, dev, sm_count, stream);
     return use256 ? launch<256, false, 2>(a, dev, sm_count, stream) : launch<128, false, 2>(a, dev, sm_count, stream);
   }
   if (mn) return use256 ? launch<256, true, 1>(a, dev, sm_count, stream) : launch<128, true, 1>(a, dev, sm_count, stream);
+  if (math_tail)
+    return use256 ? launch<256, false, 1, 8>(a, dev, sm_count, stream) : launch<128, false, 1, 8>(a, dev, sm_count, stream);
   return use256 ? launch<256, false, 1>(a, dev, sm_count, stream) : launch<128, false, 1>(a, dev, sm_count, stream);
 }

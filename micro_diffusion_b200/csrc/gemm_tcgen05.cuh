@@ -8,6 +8,7 @@ enum {
   EPI_RESID_F32 = MD_EPI_RESID_F32,
   EPI_ATOMIC_F32 = MD_EPI_ATOMIC_F32,
   EPI_ACT_DUAL = MD_EPI_ACT_DUAL,
+  EPI_ACT_GRAD = MD_EPI_ACT_GRAD,
   EPI_COUNT
 };
 // Kernel-side argument block (everything the device needs besides the two tensor maps).
@@ -17,6 +18,7 @@ struct GemmDev {
   const float* bias;
   const float* res;
   const float* gate;
+  const void* aux;
   long long ldc, strideC, strideBias, ldgate;
   int M, N, K, batch, splits, rows_per_gate, epi, res_mod, act;
   int debug;      // diagnostics only (MD_GEMM_DEBUG): 1 = epilogue skips its stores, 2 = also skips the TMEM loads

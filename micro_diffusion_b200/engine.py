@@ -12,6 +12,7 @@ parameter gradients are fp32.  Saved activations are bf16 except the residual st
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace as NS
 from typing import Optional
 
@@ -21,7 +22,7 @@ from .arch import BlockSpec, DiTConfig
 from .params import ParamStore
 
 NT, TN = 0, 1
-EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL = 0, 1, 2, 3, 4
+EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD = 0, 1, 2, 3, 4, 5
 ACT_ERF, ACT_TANH = 0, 1
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 
@@ -30,6 +31,7 @@ class Engine:
     def __init__(self, cfg: DiTConfig, store: ParamStore, ops, sm_count: int = 148):
         self.cfg, self.store, self.ops = cfg, store, ops
         self.sm_count = sm_count
+        self.fuse_act = os.environ.get("MD_FUSE_ACT", "1") != "0"  # expert GELU / GELU' in the GEMM epilogues (A/B knob)
         self.L = None  # caption length, set per call
 
     # ================================================================== helpers
@@ -134,10 +136,13 @@ class Engine:
             sv.xin = o.empty((E, B * k, D), BF16)
             o.moe_gather(sv.xm3, sv.idx, sv.xin, B, T, E, k)
             sv.hpre = o.empty((E, B * k, f), BF16); sv.hact = o.empty((E, B * k, f), BF16)
-            # GELU stays a separate HBM-bound pass: in the GEMM epilogue (EPI_ACT_DUAL) the erf + second store make the
-            # tile epilogue-bound (456 vs 1240 TFLOP/s measured, profiles/r01_per_op_c2_v15_f1.csv)
-            o.gemm(sv.xin, st.WT(n + ".mlp.w1"), sv.hpre)
-            o.act_fwd(sv.hpre, sv.hact, ACT_ERF)
+            # GELU in the epilogue of the first expert GEMM (8 epilogue warps, both outputs through TMA stores): the
+            # [E, B*k, f] hidden tensor is written once as pre-activation and once as activation, never re-read here
+            if self.fuse_act:
+                o.gemm(sv.xin, st.WT(n + ".mlp.w1"), sv.hpre, epi=EPI_ACT_DUAL, C2=sv.hact, act=ACT_ERF)
+            else:
+                o.gemm(sv.xin, st.WT(n + ".mlp.w1"), sv.hpre)
+                o.act_fwd(sv.hpre, sv.hact, ACT_ERF)
             sv.h2 = o.empty((E, B * k, D), BF16)
             o.gemm(sv.hact, st.WT(n + ".mlp.w2"), sv.h2)
             out = o.empty((M, D), F32)
@@ -171,11 +176,14 @@ class Engine:
             E, k = cfg.num_experts, sv.k
             dh2 = o.empty((E, B * k, D), BF16); dgval = o.empty((B, E, k), F32)
             o.moe_combine_bwd(dy, sv.h2, sv.gval, sv.idx, dh2, dgval, B, T, E, k)
-            dhact = o.empty((E, B * k, f), BF16)
-            o.gemm(dh2, st.W(n + ".mlp.w2"), dhact)
-            self._wgrad(sv.hact, dh2, st.G(n + ".mlp.w2"))
             dhpre = o.empty((E, B * k, f), BF16)
-            o.act_bwd(dhact, sv.hpre, dhpre, ACT_ERF)
+            if self.fuse_act:  # d hact -> d hpre inside the dgrad GEMM's epilogue (GELU' at the saved pre-activation)
+                o.gemm(dh2, st.W(n + ".mlp.w2"), dhpre, epi=EPI_ACT_GRAD, aux=sv.hpre, act=ACT_ERF)
+            else:
+                dhact = o.empty((E, B * k, f), BF16)
+                o.gemm(dh2, st.W(n + ".mlp.w2"), dhact)
+                o.act_bwd(dhact, sv.hpre, dhpre, ACT_ERF)
+            self._wgrad(sv.hact, dh2, st.G(n + ".mlp.w2"))
             dxin = o.empty((E, B * k, D), BF16)
             o.gemm(dhpre, st.W(n + ".mlp.w1"), dxin)
             self._wgrad(sv.xin, dhpre, st.G(n + ".mlp.w1"))

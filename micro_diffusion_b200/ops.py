@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import GemmArgs, MicroditLibraryError
 
 NT, TN = 0, 1
-EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL = 0, 1, 2, 3, 4
+EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD = 0, 1, 2, 3, 4, 5
 ACT_GELU_ERF, ACT_GELU_TANH = 0, 1
 
 _I64 = C.c_int64
@@ -172,7 +172,7 @@ class CudaOps:
         return out if x.dim() == 3 else out[0]
 
     def gemm(self, A, B, Cm, *, layout=NT, epi=EPI_BF16, C2=None, bias=None, res=None, gate=None, rows_per_gate=0,
-             res_mod=0, splits=1, act=0, alpha=1.0):
+             res_mod=0, splits=1, act=0, alpha=1.0, aux=None):
         if self.prec:
             # high precision: the same tcgen05 kernel at 3x the contraction depth over bf16 (hi, lo) splits of the fp32
             # operands; outputs stay fp32 (the bf16-store epilogues become fp32 stores, the fused activation a second pass)
@@ -182,16 +182,21 @@ class CudaOps:
                 self._gemm_lowp(A3, B3, Cm, layout=layout, epi=EPI_F32, bias=bias, alpha=alpha)
                 self.act_fwd(Cm, C2, act)
                 return
+            if epi == EPI_ACT_GRAD:
+                tmp = torch.empty_like(Cm)
+                self._gemm_lowp(A3, B3, tmp, layout=layout, epi=EPI_F32, alpha=alpha)
+                self.act_bwd(tmp, aux, Cm, act)
+                return
             if epi == EPI_RESID and C2 is not None:
                 raise MicroditLibraryError("high-precision GEMM: the bf16 side copy of the residual epilogue is not available")
             self._gemm_lowp(A3, B3, Cm, layout=layout, epi=EPI_F32 if epi == EPI_BF16 else epi, bias=bias, res=res,
                             gate=gate, rows_per_gate=rows_per_gate, res_mod=res_mod, splits=splits, alpha=alpha)
             return
         self._gemm_lowp(A, B, Cm, layout=layout, epi=epi, C2=C2, bias=bias, res=res, gate=gate,
-                        rows_per_gate=rows_per_gate, res_mod=res_mod, splits=splits, act=act, alpha=alpha)
+                        rows_per_gate=rows_per_gate, res_mod=res_mod, splits=splits, act=act, alpha=alpha, aux=aux)
 
     def _gemm_lowp(self, A, B, Cm, *, layout=NT, epi=EPI_BF16, C2=None, bias=None, res=None, gate=None, rows_per_gate=0,
-                   res_mod=0, splits=1, act=0, alpha=1.0):
+                   res_mod=0, splits=1, act=0, alpha=1.0, aux=None):
         a = GemmArgs()
         batched = A.dim() == 3
         A3, B3, C3 = (A, B, Cm) if batched else (A.unsqueeze(0), B.unsqueeze(0), Cm.unsqueeze(0))
@@ -207,7 +212,7 @@ class CudaOps:
             assert B3.shape[1] == K
         assert C3.shape[1] == M and C3.shape[2] == N, (C3.shape, M, N)
         a.A, a.B, a.C, a.C2 = A3.data_ptr(), B3.data_ptr(), C3.data_ptr(), _ptr(C2)
-        a.bias, a.res = _ptr(bias), _ptr(res)
+        a.bias, a.res, a.aux = _ptr(bias), _ptr(res), _ptr(aux)
         a.M, a.N, a.K = M, N, K
         a.lda, a.ldb, a.ldc = A3.stride(1), B3.stride(1), C3.stride(1)
         a.batch = A3.shape[0]
@@ -220,9 +225,11 @@ class CudaOps:
         a.sm_limit = self.sm_limit
         if C2 is not None:
             assert C2.is_contiguous() or C2.stride(-2) == C3.stride(1)
+        if aux is not None:
+            assert aux.dtype == torch.bfloat16 and aux.shape == Cm.shape and aux.stride() == Cm.stride()
         if res is not None:
             assert res.dtype == torch.float32 and res.stride(-1) == 1 and res.stride(-2) == C3.stride(1)
-        want = torch.bfloat16 if epi in (EPI_BF16, EPI_ACT_DUAL) else torch.float32
+        want = torch.bfloat16 if epi in (EPI_BF16, EPI_ACT_DUAL, EPI_ACT_GRAD) else torch.float32
         assert Cm.dtype == want, (Cm.dtype, epi)
         flops = 2 * M * N * K * int(a.batch)
         self.gemm_flops += flops

@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 NT, TN = 0, 1
-EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL = 0, 1, 2, 3, 4
+EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD = 0, 1, 2, 3, 4, 5
 
 
 def _f(t):
@@ -60,7 +60,7 @@ class EmuOps:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, Cm, *, layout=NT, epi=EPI_BF16, C2=None, bias=None, res=None, gate=None, rows_per_gate=0,
-             res_mod=0, splits=1, act=0, alpha=1.0):
+             res_mod=0, splits=1, act=0, alpha=1.0, aux=None):
         self.launches += 1
         batched = A.dim() == 3
         A3, B3, C3 = (A, B, Cm) if batched else (A.unsqueeze(0), B.unsqueeze(0), Cm.unsqueeze(0))
@@ -88,6 +88,10 @@ class EmuOps:
             C3.copy_(pre)
             a = F.gelu(pre.float(), approximate="tanh" if act == 1 else "none")
             (C2 if batched else C2.unsqueeze(0)).copy_(a)
+        elif epi == EPI_ACT_GRAD:
+            assert (self.exact or Cm.dtype == torch.bfloat16) and aux is not None and bias is None
+            x3 = aux if batched else aux.unsqueeze(0)
+            C3.copy_(acc * self._gelu_grad(_f(x3), act))
         elif epi == EPI_RESID:
             assert Cm.dtype == torch.float32 and res is not None
             if C2 is not None:

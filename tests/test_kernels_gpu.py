@@ -341,6 +341,42 @@ def test_gemm_via_ops(layout, M, N, K, epi):
             close(cu[2], cpu[2], "gemm act pre"); close(cu[3], cpu[3], "gemm act out")
 
 
+@pytest.mark.parametrize("M,N,K,batch,ld_extra", [
+    (512, 768, 256, 1, 0),       # CTA pair, 256-wide tiles, 8 epilogue warps, TMA stores
+    (1000, 200, 320, 1, 0),      # ragged M and N: both store boxes clipped, aux tail loads guarded
+    (96, 128, 192, 1, 0),        # single 128-row block -> 1-CTA kernel
+    (640, 384, 128, 3, 0),       # batched (the expert banks)
+    (130, 100, 64, 1, 2),        # pitch 102: not TMA-addressable -> direct-store fallback, scalar aux loads
+])
+@pytest.mark.parametrize("act", [0, 1])
+def test_gemm_activation_epilogues(M, N, K, batch, ld_extra, act):
+    """GELU + dual store (MD_EPI_ACT_DUAL) and activation gradient at the saved pre-activation (MD_EPI_ACT_GRAD):
+    the fused tails of the expert GEMMs (dit.py:135-137) against the CPU contract."""
+    A = rnd((batch, M, K), 1, BF16); B = rnd((batch, N, K), 2, BF16)
+    shape = (batch, M, N + ld_extra)
+    pre = torch.full(shape, 3.0, dtype=BF16); out = torch.full(shape, 5.0, dtype=BF16)
+    if batch == 1:
+        A, B, pre, out = A[0], B[0], pre[0], out[0]
+
+    def fwd(o, A, B, pre, out):
+        o.gemm(A, B, pre[..., :N], layout=0, epi=4, C2=out[..., :N], act=act, alpha=0.05)
+    cpu, cu = both(fwd, [A, B, pre, out])
+    close(cu[2][..., :N], cpu[2][..., :N], "act dual pre"); close(cu[3][..., :N], cpu[3][..., :N], "act dual out")
+    if ld_extra:
+        assert torch.equal(cu[2].cpu()[..., N:], cpu[2][..., N:]) and torch.equal(cu[3].cpu()[..., N:], cpu[3][..., N:])
+    aux = (rnd(shape, 3, BF16, 1.5))
+    dpre = torch.full(shape, 9.0, dtype=BF16)
+    if batch == 1:
+        aux, dpre = aux[0], dpre[0]
+
+    def bwd(o, A, B, aux, dpre):
+        o.gemm(A, B, dpre[..., :N], layout=0, epi=5, aux=aux[..., :N], act=act, alpha=0.05)
+    cpu, cu = both(bwd, [A, B, aux, dpre])
+    close(cu[3][..., :N], cpu[3][..., :N], "act grad")
+    if ld_extra:
+        assert torch.equal(cu[3].cpu()[..., N:], cpu[3][..., N:]), "store leaked outside its column slice"
+
+
 @pytest.mark.parametrize("layout,M,N,K,batch,ld_extra,col_off", [
     (0, 1000, 200, 320, 1, 0, 0),      # ragged M and N (N % 32 != 0): the TMA store box is clipped at both edges
     (0, 96, 128, 192, 1, 0, 0),        # single 128-row block -> 1-CTA kernel, 128-wide tile
