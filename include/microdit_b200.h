@@ -101,11 +101,16 @@ MD_API int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, const v
                      int prec, void* stream);
 /* Backward of the above.  dy bf16 [rows, D].  dx_mode: 0 = dx(f32)[r] += , 1 = dx(bf16)[r] = ,
  * 2 = dx(f32)[src_rows[r]] += (scatter).  dgamma f32 [D] += (atomic); dshift / dscale f32 [samples, D]
- * pitched by ldmod, += (atomic; caller zeroes them once per step).  NULL outputs are skipped. */
+ * pitched by ldmod, += (atomic; caller zeroes them once per step).  NULL outputs are skipped.
+ * Fused tail (dy_next != NULL; needs dx_mode 0): the updated dx is the gradient entering the NEXT branch of the backward
+ * chain, so its gated-residual backward (md_gate_bwd below) rides along instead of re-reading dx:
+ * dy_next(bf16) = gate_next[sample] * dx_new, dgate_next[sample] += sum_t dx_new * y_next (atomic); y_next / gate_next /
+ * dgate_next may be NULL (plain cast). */
 MD_API int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_t* src_rows, const float* gamma,
                      const float* scale, int64_t ldmod, int64_t T, const float* mean, const float* rstd,
-                     void* dx, int dx_mode, float* dgamma, float* dshift, float* dscale, int64_t rows,
-                     int64_t D, int prec, void* stream);
+                     void* dx, int dx_mode, float* dgamma, float* dshift, float* dscale, const void* y_next,
+                     const float* gate_next, float* dgate_next, void* dy_next, int64_t rows, int64_t D, int prec,
+                     void* stream);
 /* Non-affine LayerNorm over W-wide column slices, in place on bf16 (QK-norm: ln_q / ln_k utils.py:183-186,
  * 122-125).  fwd: x <- (x-mean)*rstd, rstd out.  bwd: dy <- rstd*(dy - mean(dy) - xhat*mean(dy*xhat)).
  * nslice (1..4) adjacent slices [s*W, (s+1)*W) of every row are normalised independently in ONE launch (q and k of

@@ -332,6 +332,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint4 auxn[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
       auto load_aux = [&](int c) {
         const int col0 = colbase + c * 32;
+        if (p.tma_store == 2) {
+          // coalesced: lane -> (row (lane >> 2) + 8 i, 16-byte piece lane & 3) of the warp's 32 x 32 box, i.e. full 64-byte
+          // row segments per four lanes; the box is transposed to one row per lane through shared memory when it is used
+          const int row0 = (mb * kCtas + cta_rank) * kBlockM + q * 32;
+          const int pc = lane & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = row0 + (lane >> 2) + 8 * i;
+            const bool ok = r < p.M && col0 + pc * 8 < p.N;  // N % 8 == 0 in this mode: whole pieces
+            auxn[i] = ok ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) +
+                                                            1LL * bz * p.strideC + 1LL * r * p.ldc + col0 + pc * 8)
+                         : make_uint4(0u, 0u, 0u, 0u);
+          }
+          return;
+        }
         const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux) + crow + col0;
         const bool live = row_ok && has_k && col0 < p.N;
         const bool vec = live && (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(ax) & 15) == 0);
@@ -383,6 +398,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         const int col0 = colbase + c * 32;
         if (p.epi == EPI_ACT_GRAD) {  // C = acc * act'(pre): the dgrad GEMM hands the pre-activation gradient on directly
+          if (p.tma_store == 2) {
+            uint8_t* ab = my_stage + Cfg::kStoreBufBytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = (lane >> 2) + 8 * i;
+              *reinterpret_cast<uint4*>(ab + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4)) = auxv[i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              auxv[j] = *reinterpret_cast<const uint4*>(ab + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+            __syncwarp();
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -396,6 +424,61 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (p.debug == 1) {
           if (v[0] == 123.456f && v[31] == -654.321f) reinterpret_cast<float*>(p.C)[0] = v[5];  // keep the loads alive
+        } else if (p.tma_store == 2) {
+          // bf16 store staged through shared memory and written by the warp itself: the 32 x 32 box is transposed so that
+          // four lanes write one full 64-byte row segment (fire-and-forget st.global, full sectors).  The math tails use
+          // this instead of the TMA store: their stores queue behind the producer's prefetched operand loads in the TMA
+          // unit, and waiting for a staging buffer to be read cost ~2 us per chunk (the first fused GELU epilogue ran at
+          // 0.45x of the plain GEMM for that reason).
+          const int row0 = (mb * kCtas + cta_rank) * kBlockM + q * 32;
+          if (row0 < p.M && col0 < p.N) {  // warp-uniform
+            if (p.bias != nullptr) {
+              const int ncols = min(32, p.N - col0);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
+            }
+            const int sw = (lane >> 1) & 3;
+            auto write_box = [&](const uint8_t* buf, void* base) {
+              __syncwarp();
+              const int pc = lane & 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = (lane >> 2) + 8 * i;
+                const uint4 val = *reinterpret_cast<const uint4*>(buf + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+                if (row0 + r < p.M && col0 + pc * 8 < p.N)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + 1LL * bz * p.strideC +
+                                            1LL * (row0 + r) * p.ldc + col0 + pc * 8) = val;
+              }
+              __syncwarp();
+            };
+            if (p.epi == EPI_ACT_DUAL) {
+              // the activation is taken on the bf16-rounded pre-activation so that backward (which re-reads C)
+              // differentiates the same function
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float x[8], y[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  x[e] = bf16_round(v[8 * j + e]);
+                  y[e] = p.act ? gelu_tanh_fast(x[e]) : gelu_erf_fast(x[e]);
+                }
+                *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ sw) << 4)) =
+                    pack_bf16x8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+                *reinterpret_cast<uint4*>(my_stage + Cfg::kStoreBufBytes + lane * 64 + ((j ^ sw) << 4)) =
+                    pack_bf16x8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+              }
+              write_box(my_stage, p.C);
+              write_box(my_stage + Cfg::kStoreBufBytes, p.C2);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ sw) << 4)) =
+                    pack_bf16x8(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5],
+                                v[8 * j + 6], v[8 * j + 7]);
+              write_box(my_stage, p.C);
+            }
+          }
         } else if (p.tma_store) {
           // bf16 store through shared memory: each lane (= output row) drops its 64 bytes into a 64B-swizzled 32 x 32
           // box and one lane hands the box to the TMA, which writes full lines and clips at the tensor edge.  Direct
@@ -647,7 +730,16 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
   dev.tma_store = 0;
   const bool bf16_out = a->epilogue == EPI_STORE_BF16 || a->epilogue == EPI_ACT_GRAD || a->epilogue == EPI_ACT_DUAL;
   const bool dual = a->epilogue == EPI_ACT_DUAL;
-  if (tma_store_env && bf16_out && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (a->ldc % 8) == 0 &&
+  const bool aligned_out = (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (a->ldc % 8) == 0 && (a->N % 8) == 0 &&
+                           (a->batch == 1 || (a->strideC % 8) == 0) &&
+                           (!dual || (reinterpret_cast<uintptr_t>(a->C2) & 15) == 0) &&
+                           (a->epilogue != EPI_ACT_GRAD || (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0);
+  // staged + coalesced st.global (tma_store = 2): always for the math tails, MD_GEMM_TMA_STORE=2 forces it for the plain store
+  if (tma_store_env && bf16_out && aligned_out && (kEpiW == 8 || tma_store_env == 2)) {
+    dev.tma_store = 2;
+    tmC = tmA;
+    tmC2 = tmA;
+  } else if (tma_store_env && bf16_out && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (a->ldc % 8) == 0 &&
       (a->batch == 1 || (a->strideC % 8) == 0) && (!dual || (reinterpret_cast<uintptr_t>(a->C2) & 15) == 0)) {
     rc = make_store_map(&tmC, a->C, a->N, a->M, a->batch, a->ldc, a->strideC);
     if (rc) return rc;

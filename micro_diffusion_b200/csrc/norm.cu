@@ -240,6 +240,150 @@ ln_bwd_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const int32
   }
 }
 
+// --------------------------------------------------------------------------------- ln_bwd (teams)
+// The model widths (512 / 768 / 1024): a row is shared by a TEAM of 2 or 4 warps (D = 128 * TEAM * V: V float4 groups per
+// lane), 8 / TEAM teams per 256-thread block.  Cutting the per-lane footprint is what makes room for the fused tail
+// below (one warp per row sat at 245 registers, 8 warps per SM); the partial row sums cross through a double-buffered
+// shared-memory slot and a named barrier over the team.
+//
+// Fused tail (dy_next != NULL): dx_new is the gradient entering the NEXT branch of the backward chain (DiTBlock,
+// dit.py:236-238 read backwards), whose first step used to be a separate pass over dx (md_gate_bwd):
+//   dy_next = bf16(gate_next[sample] * dx_new),   dgate_next[sample] += sum_t dx_new * y_next.
+template <int V, int TEAM, bool XBF, typename AT>
+__global__ void __launch_bounds__(256, 2)
+ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const int32_t* __restrict__ src_rows,
+                   const float* __restrict__ gamma, const float* __restrict__ scale, long long ldmod, long long T,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ dx, int dx_mode,
+                   float* __restrict__ dgamma, float* __restrict__ dshift, float* __restrict__ dscale,
+                   const AT* __restrict__ y_next, const float* __restrict__ gate_next, float* __restrict__ dgate_next,
+                   AT* __restrict__ dy_next, int rpb) {
+  constexpr int D = 128 * TEAM * V;
+  constexpr int NT = 8 / TEAM;  // teams per block
+  extern __shared__ float sm[];
+  float* red = sm;             // [NT][D]
+  float* sw = sm + NT * D;     // [D] gamma * (1 + scale): d xhat / d y, constant over the block (one sample)
+  float* sg = sw + D;          // [D] gate_next
+  float* xch = sg + D;         // [NT][2 parities][TEAM warps][2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = warp / TEAM, wt = warp % TEAM;
+  const long long smp = blockIdx.y;
+  const long long t0 = 1LL * blockIdx.x * rpb;
+  const long long t1 = min(T, t0 + rpb);
+  const float* sc = scale ? scale + smp * ldmod : nullptr;
+  const float* gt = gate_next ? gate_next + smp * ldmod : nullptr;
+  const bool need_cols = (dgamma != nullptr) || (dshift != nullptr) || (dscale != nullptr);
+  const bool need_gate = (dgate_next != nullptr) && (y_next != nullptr);
+  for (int c = threadIdx.x; c < D; c += 256) {
+    sw[c] = (gamma ? gamma[c] : 1.f) * (sc ? 1.f + sc[c] : 1.f);
+    sg[c] = gt ? gt[c] : 1.f;
+  }
+  __syncthreads();
+
+  float4 accA[V], accB[V], accG[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) accA[j] = accB[j] = accG[j] = f4zero();
+  const int i0 = wt * 32 + lane;  // float4 group index of this lane: i0 + 32 * TEAM * j
+  int it = 0;
+  for (long long t = t0 + team; t < t1; t += NT, ++it) {
+    const long long row = smp * T + t;
+    const long long src = src_rows ? src_rows[row] : row;
+    const long long drow = (dx_mode == 2) ? src : row;
+    float4 d[V], xh[V], old[V], yv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int i = i0 + 32 * TEAM * j;
+      d[j] = ld4a(dy + row * D + 4LL * i);
+      xh[j] = ld4<XBF>(x, src * D + 4LL * i);
+    }
+    if (dx != nullptr && dx_mode != 1) {
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        old[j] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dx) + drow * D + 4LL * (i0 + 32 * TEAM * j));
+    }
+    if (need_gate) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) yv[j] = ld4a(y_next + row * D + 4LL * (i0 + 32 * TEAM * j));
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float4 w = *reinterpret_cast<const float4*>(sw + 4 * (i0 + 32 * TEAM * j));
+      xh[j] = make_float4((xh[j].x - mu) * rs, (xh[j].y - mu) * rs, (xh[j].z - mu) * rs, (xh[j].w - mu) * rs);
+      accA[j].x += d[j].x; accA[j].y += d[j].y; accA[j].z += d[j].z; accA[j].w += d[j].w;
+      accB[j].x += d[j].x * xh[j].x; accB[j].y += d[j].y * xh[j].y;
+      accB[j].z += d[j].z * xh[j].z; accB[j].w += d[j].w * xh[j].w;
+      d[j] = make_float4(d[j].x * w.x, d[j].y * w.y, d[j].z * w.z, d[j].w * w.w);  // d loss / d xhat
+      s1 += d[j].x + d[j].y + d[j].z + d[j].w;
+      s2 += d[j].x * xh[j].x + d[j].y * xh[j].y + d[j].z * xh[j].z + d[j].w * xh[j].w;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    float* slot = xch + ((team * 2 + (it & 1)) * TEAM) * 2;
+    if (lane == 0) {
+      slot[wt * 2] = s1;
+      slot[wt * 2 + 1] = s2;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(32 * TEAM) : "memory");
+    s1 = 0.f;
+    s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < TEAM; ++u) {  // fixed order: every warp of the team gets bit-identical sums
+      s1 += slot[u * 2];
+      s2 += slot[u * 2 + 1];
+    }
+    const float m1 = s1 * (1.f / D), m2 = s2 * (1.f / D);
+    if (dx != nullptr) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const int i = i0 + 32 * TEAM * j;
+        float4 o;
+        o.x = rs * (d[j].x - m1 - xh[j].x * m2); o.y = rs * (d[j].y - m1 - xh[j].y * m2);
+        o.z = rs * (d[j].z - m1 - xh[j].z * m2); o.w = rs * (d[j].w - m1 - xh[j].w * m2);
+        if (dx_mode == 1) {
+          st4a(reinterpret_cast<AT*>(dx) + drow * D + 4LL * i, o);
+        } else {
+          o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w;
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(dx) + drow * D + 4LL * i) = o;
+          if (dy_next != nullptr) {
+            const float4 g = *reinterpret_cast<const float4*>(sg + 4 * i);
+            st4a(dy_next + row * D + 4LL * i, make_float4(o.x * g.x, o.y * g.y, o.z * g.z, o.w * g.w));
+            if (need_gate) {
+              accG[j].x += o.x * yv[j].x; accG[j].y += o.y * yv[j].y;
+              accG[j].z += o.z * yv[j].z; accG[j].w += o.w * yv[j].w;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!need_cols && !need_gate) return;
+  // cross-team reduction of the column partials, one quantity at a time through red[NT][D]
+  for (int pass = 0; pass < 3; ++pass) {
+    if (pass < 2 && !need_cols) continue;
+    if (pass == 2 && !need_gate) continue;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      *reinterpret_cast<float4*>(red + team * D + 4 * (i0 + 32 * TEAM * j)) =
+          pass == 0 ? accA[j] : (pass == 1 ? accB[j] : accG[j]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int u = 0; u < NT; ++u) v += red[u * D + c];
+      if (pass == 0) {
+        if (dshift) atomicAdd(dshift + smp * ldmod + c, v);
+      } else if (pass == 1) {
+        if (dscale) atomicAdd(dscale + smp * ldmod + c, v * (gamma ? gamma[c] : 1.f));
+        if (dgamma) atomicAdd(dgamma + c, v * (sc ? 1.f + sc[c] : 1.f));
+      } else {
+        atomicAdd(dgate_next + smp * ldmod + c, v);
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------- rownorm
 __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
@@ -470,7 +614,8 @@ extern "C" int md_ln_fwd(const void* x, int x_bf16, const int32_t* src_rows, con
 
 extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_t* src_rows, const float* gamma,
                          const float* scale, int64_t ldmod, int64_t T, const float* mean, const float* rstd, void* dx,
-                         int dx_mode, float* dgamma, float* dshift, float* dscale, int64_t rows, int64_t D, int prec,
+                         int dx_mode, float* dgamma, float* dshift, float* dscale, const void* y_next,
+                         const float* gate_next, float* dgate_next, void* dy_next, int64_t rows, int64_t D, int prec,
                          void* stream) {
   if (int rc = check_ln_dims("md_ln_bwd", rows, D, T)) return rc;
   if (rows == 0) return 0;
@@ -478,10 +623,35 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
   if (rows % T != 0) return md_set_error(MD_ERR_INVALID, "md_ln_bwd: rows must be a multiple of T");
   if (dx_mode < 0 || dx_mode > 2 || (dx_mode == 2 && !src_rows))
     return md_set_error(MD_ERR_INVALID, "md_ln_bwd: bad dx_mode");
+  if (dy_next != nullptr && (dx == nullptr || dx_mode != 0))
+    return md_set_error(MD_ERR_INVALID, "md_ln_bwd: the fused next-branch tail needs dx with dx_mode 0");
+  if ((y_next != nullptr || gate_next != nullptr || dgate_next != nullptr) && dy_next == nullptr)
+    return md_set_error(MD_ERR_INVALID, "md_ln_bwd: y_next / gate_next / dgate_next come with dy_next");
   const int rpb = rows_per_block(T, rows / T);
   dim3 grid(static_cast<unsigned>((T + rpb - 1) / rpb), static_cast<unsigned>(rows / T));
-  const size_t smem = 4 * D * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (D == 1024 || D == 768 || D == 512) {
+    const size_t smem = (6 * D + 64) * sizeof(float);
+#define LN_BWD_TEAM(V, TEAM)                                                                                               \
+  MD_WITH_ACT(prec, do {                                                                                               \
+    if (x_bf16)                                                                                                        \
+      ln_bwd_team_kernel<V, TEAM, true, AT><<<grid, 256, smem, st>>>(CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T, mean, \
+                                                               rstd, dx, dx_mode, dgamma, dshift, dscale,              \
+                                                               CAP(AT, y_next), gate_next, dgate_next, AP(AT, dy_next), \
+                                                               rpb);                                                   \
+    else                                                                                                               \
+      ln_bwd_team_kernel<V, TEAM, false, AT><<<grid, 256, smem, st>>>(CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T,      \
+                                                                mean, rstd, dx, dx_mode, dgamma, dshift, dscale,       \
+                                                                CAP(AT, y_next), gate_next, dgate_next,                \
+                                                                AP(AT, dy_next), rpb);                                 \
+  } while (0))
+    if (D == 1024) LN_BWD_TEAM(2, 4);
+    else if (D == 768) LN_BWD_TEAM(3, 2);
+    else LN_BWD_TEAM(2, 2);
+#undef LN_BWD_TEAM
+    return check_launch("md_ln_bwd");
+  }
+  const size_t smem = 4 * D * sizeof(float);
 #define LN_BWD(VEC, EXACT)                                                                                             \
   MD_WITH_ACT(prec, do {                                                                                               \
     if (x_bf16)                                                                                                        \
@@ -493,13 +663,15 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
                                                                     mean, rstd, dx, dx_mode, dgamma, dshift, dscale,  \
                                                                     rows, static_cast<int>(D), rpb);                  \
   } while (0))
-  if (D == 1024) LN_BWD(8, true);
-  else if (D == 768) LN_BWD(6, true);
-  else if (D == 512) LN_BWD(4, true);
-  else if (D <= 1024) LN_BWD(8, false);
+  if (D <= 1024) LN_BWD(8, false);
   else LN_BWD(16, false);
 #undef LN_BWD
-  return check_launch("md_ln_bwd");
+  if (int rc = check_launch("md_ln_bwd")) return rc;
+  // other widths: the next branch's gate backward runs as its own pass over the updated dx
+  if (dy_next != nullptr)
+    return md_gate_bwd(reinterpret_cast<const float*>(dx), y_next, gate_next, ldmod, T, dy_next, dgate_next, rows, D, prec,
+                       stream);
+  return 0;
 }
 
 extern "C" int md_rownorm_fwd(void* x, int64_t ld, float* rstd, int64_t rows, int64_t W, int64_t nslice, float eps,

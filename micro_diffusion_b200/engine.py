@@ -32,6 +32,8 @@ class Engine:
         self.cfg, self.store, self.ops = cfg, store, ops
         self.sm_count = sm_count
         self.fuse_act = os.environ.get("MD_FUSE_ACT", "1") != "0"  # expert GELU / GELU' in the GEMM epilogues (A/B knob)
+        # gated-residual backward of the next branch emitted by the preceding LayerNorm backward (A/B knob)
+        self.fuse_ln = os.environ.get("MD_FUSE_LN", "1") != "0"
         self.L = None  # caption length, set per call
 
     # ================================================================== helpers
@@ -151,18 +153,29 @@ class Engine:
         return out, pend_out, (sv if keep else None)
 
     # ================================================================== block backward
-    def _block_bwd(self, bs: BlockSpec, sv, dx, dkv, B, T, L, mod, dmod):
+    def _ffn_gate_args(self, bs: BlockSpec, sv, mod, dmod):
+        """What the backward chain needs to enter a block's feed-forward branch: y, gate and d gate of x + g_m * y."""
+        return dict(y_next=sv.ym, gate_next=self._mods(bs.name, bs.dim, mod)[5], dgate_next=self._mods(bs.name, bs.dim, dmod)[5])
+
+    def _block_bwd(self, bs: BlockSpec, sv, dx, dkv, B, T, L, mod, dmod, dy_in=None, nxt=None):
         """dx (f32 [M,D]): in = grad wrt the block output, out = grad wrt the block input (in place).
-        dkv (bf16 [B*L, 2D] column slice of the stage-wide buffer) receives d loss / d (K, V) of this block."""
+        dkv (bf16 [B*L, 2D] column slice of the stage-wide buffer) receives d loss / d (K, V) of this block.
+        dy_in: gate_m * dx already in bf16 (emitted by the LayerNorm backward that produced dx); nxt: the
+        _ffn_gate_args of the block the chain enters next -- this block's last LayerNorm backward then emits that
+        block's dy_in, which is returned."""
         o, st, cfg = self.ops, self.store, self.cfg
         P, G = st.p, st.g
         n, D, h, f, hd = bs.name, bs.dim, bs.attn_dim, bs.ffn_dim, cfg.head_dim
         M = B * T
+        fuse = self.fuse_ln
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = self._mods(n, D, mod)
         dsh_a, dsc_a, dg_a, dsh_m, dsc_m, dg_m = self._mods(n, D, dmod)
-        dy = o.empty((M, D), BF16)
         # ---- feed-forward branch
-        o.gate_bwd(dx, dy, y=sv.ym, gate=g_m, dgate=dg_m, T=T)
+        if dy_in is None:
+            dy = o.empty((M, D), BF16)
+            o.gate_bwd(dx, dy, y=sv.ym, gate=g_m, dgate=dg_m, T=T)
+        else:
+            dy = dy_in
         dxm = o.empty((M, D), BF16)
         if not bs.moe:
             dh = o.empty((M, f), BF16)
@@ -190,10 +203,12 @@ class Engine:
             dscores = o.empty((M, E), F32)
             o.moe_dx_bwd(dxin, sv.inv, dgval, sv.probs, P[n + ".mlp.gate.weight"], dscores, dxm, B, T, E, k)
             o.moe_gate_wgrad(dscores, sv.xm3, G[n + ".mlp.gate.weight"])
+        dy = o.empty((M, D), BF16)
         o.ln_bwd(dxm, sv.x2, sv.mean3, sv.rstd3, gamma=P[n + ".norm3.weight"], scale=sc_m, T=T, dx=dx, dx_mode=0,
-                 dgamma=G[n + ".norm3.weight"], dshift=dsh_m, dscale=dsc_m)
-        # ---- cross attention branch (no gate, no modulation)
-        o.gate_bwd(dx, dy, T=T)  # f32 -> bf16
+                 dgamma=G[n + ".norm3.weight"], dshift=dsh_m, dscale=dsc_m, dy_next=dy if fuse else None)
+        # ---- cross attention branch (no gate, no modulation): dy = bf16(dx)
+        if not fuse:
+            o.gate_bwd(dx, dy, T=T)
         datt2 = o.empty((M, D), BF16)
         o.gemm(dy, st.WT(n + ".cross_attn.proj.weight"), datt2)
         self._wgrad(dy, sv.att2, st.G(n + ".cross_attn.proj.weight"))
@@ -206,10 +221,15 @@ class Engine:
         dxn2 = o.empty((M, D), BF16)
         o.gemm(dqx, st.WT(n + ".cross_attn.q_linear.weight"), dxn2)
         self._wgrad(dqx, sv.xn2, st.G(n + ".cross_attn.q_linear.weight"))
-        o.ln_bwd(dxn2, sv.x1, sv.mean2, sv.rstd2, gamma=P[n + ".norm2.weight"], T=T, dx=dx, dx_mode=0,
-                 dgamma=G[n + ".norm2.weight"])
+        dy = o.empty((M, D), BF16)
+        if fuse:
+            o.ln_bwd(dxn2, sv.x1, sv.mean2, sv.rstd2, gamma=P[n + ".norm2.weight"], T=T, dx=dx, dx_mode=0,
+                     dgamma=G[n + ".norm2.weight"], dy_next=dy, y_next=sv.ya, gate_next=g_a, dgate_next=dg_a)
+        else:
+            o.ln_bwd(dxn2, sv.x1, sv.mean2, sv.rstd2, gamma=P[n + ".norm2.weight"], T=T, dx=dx, dx_mode=0,
+                     dgamma=G[n + ".norm2.weight"])
+            o.gate_bwd(dx, dy, y=sv.ya, gate=g_a, dgate=dg_a, T=T)
         # ---- self attention branch
-        o.gate_bwd(dx, dy, y=sv.ya, gate=g_a, dgate=dg_a, T=T)
         datt = o.empty((M, h), BF16)
         o.gemm(dy, st.WT(n + ".attn.proj.weight"), datt)
         self._wgrad(dy, sv.att, st.G(n + ".attn.proj.weight"))
@@ -221,8 +241,11 @@ class Engine:
         dxm1 = o.empty((M, D), BF16)
         o.gemm(dqkv, st.WT(n + ".attn.qkv.weight"), dxm1)
         self._wgrad(dqkv, sv.xm, st.G(n + ".attn.qkv.weight"))
+        dy_out = o.empty((M, D), BF16) if (fuse and nxt is not None) else None
         o.ln_bwd(dxm1, sv.x, sv.mean1, sv.rstd1, gamma=P[n + ".norm1.weight"], scale=sc_a, T=T, dx=dx, dx_mode=0,
-                 dgamma=G[n + ".norm1.weight"], dshift=dsh_a, dscale=dsc_a)
+                 dgamma=G[n + ".norm1.weight"], dshift=dsh_a, dscale=dsc_a, dy_next=dy_out,
+                 **(nxt if dy_out is not None else {}))
+        return dy_out
 
     # ================================================================== conditioning stem
     def _stem_fwd(self, cap, drop, cnoise, B, keep: bool, cap_out=None):
@@ -579,14 +602,19 @@ class Engine:
         fo = st.layout.ada_offset["final_layer"]
         sc_f = mod[:, fo + D:fo + 2 * D]
         dx = o.zeros((B * Tk, D), F32)
+        nb = len(cfg.blocks)
+        fuse = self.fuse_ln and nb > 0 and cfg.blocks[-1].dim == D
+        dy = o.empty((B * Tk, D), BF16) if fuse else None
         o.ln_bwd(dxf, c.xlast, c.m_f, c.r_f, gamma=P["final_layer.norm_final.weight"], scale=sc_f, T=Tk, dx=dx,
                  dx_mode=0, dgamma=G["final_layer.norm_final.weight"], dshift=dmod[:, fo:fo + D],
-                 dscale=dmod[:, fo + D:fo + 2 * D])
+                 dscale=dmod[:, fo + D:fo + 2 * D], dy_next=dy,
+                 **(self._ffn_gate_args(cfg.blocks[-1], c.block_sv[-1], mod, dmod) if fuse else {}))
         # ---- backbone
-        nb = len(cfg.blocks)
         dkv_b = o.empty((B * L, nb * 2 * D), BF16)
         for i in range(nb - 1, -1, -1):
-            self._block_bwd(cfg.blocks[i], c.block_sv[i], dx, dkv_b[:, i * 2 * D:(i + 1) * 2 * D], B, Tk, L, mod, dmod)
+            nxt = self._ffn_gate_args(cfg.blocks[i - 1], c.block_sv[i - 1], mod, dmod) if i > 0 else None
+            dy = self._block_bwd(cfg.blocks[i], c.block_sv[i], dx, dkv_b[:, i * 2 * D:(i + 1) * 2 * D], B, Tk, L, mod, dmod,
+                                 dy_in=dy, nxt=nxt)
             c.block_sv[i] = None  # release this block's saved activations
         self._kv_bwd("kv.blocks", dkv_b, s.ybf, dy2)
         del dkv_b
@@ -615,9 +643,11 @@ class Engine:
             dymix = o.zeros((B * L, Dm), F32) if cfg.has_mixer_maps else dy2
             nm = len(cfg.mixer_blocks)
             dkv_m = o.empty((B * L, nm * 2 * Dm), BF16)
+            dy = None
             for i in range(nm - 1, -1, -1):
-                self._block_bwd(cfg.mixer_blocks[i], c.mixer_sv[i], dxm, dkv_m[:, i * 2 * Dm:(i + 1) * 2 * Dm], B, T, L,
-                                mod, dmod)
+                nxt = self._ffn_gate_args(cfg.mixer_blocks[i - 1], c.mixer_sv[i - 1], mod, dmod) if i > 0 else None
+                dy = self._block_bwd(cfg.mixer_blocks[i], c.mixer_sv[i], dxm, dkv_m[:, i * 2 * Dm:(i + 1) * 2 * Dm], B, T, L,
+                                     mod, dmod, dy_in=dy, nxt=nxt)
                 c.mixer_sv[i] = None
             self._kv_bwd("kv.patch_mixer", dkv_m, c.ymix, dymix)
             del dkv_m

@@ -27,7 +27,7 @@ _I = C.c_int
 
 _PROTOS = {
     "md_ln_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _I64, _I64, _F, _I, _P],
-    "md_ln_bwd": [_P, _P, _I, _P, _P, _P, _I64, _I64, _P, _P, _P, _I, _P, _P, _P, _I64, _I64, _I, _P],
+    "md_ln_bwd": [_P, _P, _I, _P, _P, _P, _I64, _I64, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _P],
     "md_rownorm_fwd": [_P, _I64, _P, _I64, _I64, _I64, _F, _I, _P],
     "md_rownorm_bwd": [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I, _P],
     "md_gate_bwd": [_P, _P, _P, _I64, _I64, _P, _P, _I64, _I64, _I, _P],
@@ -258,14 +258,20 @@ class CudaOps:
                    D, eps)
 
     def ln_bwd(self, dy, x, mean, rstd, *, gamma=None, scale=None, T, src_rows=None, dx=None, dx_mode=0,
-               dgamma=None, dshift=None, dscale=None):
+               dgamma=None, dshift=None, dscale=None, dy_next=None, y_next=None, gate_next=None, dgate_next=None):
+        """dy_next (bf16 [rows, D]): also emit the next branch's gated-residual backward from the updated dx
+        (dy_next = gate_next * dx, dgate_next += sum_t dx * y_next) -- what a separate gate_bwd pass would compute."""
         rows, D = dy.shape
         sc, ld = _mod(scale)
         dsh, ld2 = _mod(dshift)
         dsc, ld3 = _mod(dscale)
+        gn, ld4 = _mod(gate_next)
+        dgn, ld5 = _mod(dgate_next)
+        lds = {v for v in (ld, ld2, ld3, ld4, ld5) if v}
+        assert len(lds) <= 1, "all per-sample vectors of one call are views of the same modulation buffer"
         self._call("md_ln_bwd", dy.data_ptr(), x.data_ptr(), int(x.dtype == torch.bfloat16), _ptr(src_rows),
-                   _ptr(gamma), sc, ld or ld2 or ld3, T, mean.data_ptr(), rstd.data_ptr(), _ptr(dx), dx_mode,
-                   _ptr(dgamma), dsh, dsc, rows, D)
+                   _ptr(gamma), sc, lds.pop() if lds else 0, T, mean.data_ptr(), rstd.data_ptr(), _ptr(dx), dx_mode,
+                   _ptr(dgamma), dsh, dsc, _ptr(y_next), gn, dgn, _ptr(dy_next), rows, D)
 
     def rownorm_fwd(self, x, rstd, eps=1e-6, nslice=1):
         """x [rows, nslice*W]: every W-wide slice normalised on its own; rstd [nslice, rows] ([rows] for one slice)."""

@@ -142,7 +142,16 @@ class EmuOps:
             rstd.copy_(rs.flatten())
 
     def ln_bwd(self, dy, x, mean, rstd, *, gamma=None, scale=None, T, src_rows=None, dx=None, dx_mode=0,
-               dgamma=None, dshift=None, dscale=None):
+               dgamma=None, dshift=None, dscale=None, dy_next=None, y_next=None, gate_next=None, dgate_next=None):
+        self._ln_bwd(dy, x, mean, rstd, gamma=gamma, scale=scale, T=T, src_rows=src_rows, dx=dx, dx_mode=dx_mode,
+                     dgamma=dgamma, dshift=dshift, dscale=dscale)
+        if dy_next is not None:  # fused tail == gate_bwd on the updated dx
+            assert dx is not None and dx_mode == 0
+            self.launches -= 1
+            self.gate_bwd(dx, dy_next, y=y_next, gate=gate_next, dgate=dgate_next, T=T)
+
+    def _ln_bwd(self, dy, x, mean, rstd, *, gamma=None, scale=None, T, src_rows=None, dx=None, dx_mode=0,
+                dgamma=None, dshift=None, dscale=None):
         self.launches += 1
         rows, D = dy.shape
         xv = _f(x).reshape(-1, D)

@@ -61,7 +61,8 @@ def both(fn, tensors):
     return cpu, cu
 
 
-@pytest.mark.parametrize("rows,D,T,xbf", [(256, 1024, 64, False), (154, 768, 77, False), (96, 128, 32, True), (40, 192, 8, False)])
+@pytest.mark.parametrize("rows,D,T,xbf", [(256, 1024, 64, False), (154, 768, 77, False), (96, 128, 32, True), (40, 192, 8, False),
+                                          (1024, 768, 256, False), (210, 512, 35, True)])
 def test_ln_fwd_bwd(rows, D, T, xbf):
     ns = rows // T
     x = rnd((rows, D), 1, BF16 if xbf else F32, 2.0) + 0.5
@@ -82,6 +83,18 @@ def test_ln_fwd_bwd(rows, D, T, xbf):
                  dshift=dmod[:, :D], dscale=dmod[:, 2 * D:3 * D])
     cpu2, cu2 = both(b, [dy, x, gamma, mod, cpu[4], cpu[5], dx, dgamma, dmod])
     close(cu2[6], cpu2[6], "ln dx", 1e-4); close(cu2[7], cpu2[7], "dgamma", 1e-4); close(cu2[8], cpu2[8], "dshift/dscale", 1e-4)
+    # fused tail: the next branch's gated-residual backward (dy_next, d gate) from the updated dx, gated and plain
+    yn = rnd((rows, D), 6, BF16)
+    for gated in (True, False):
+        dyn = torch.zeros(rows, D, dtype=BF16)
+
+        def b2(o, dy, x, gamma, mod, mean, rstd, dx, dgamma, dmod, yn, dyn):
+            o.ln_bwd(dy, x, mean, rstd, gamma=gamma, scale=mod[:, 3 * D:4 * D], T=T, dx=dx, dx_mode=0, dgamma=dgamma,
+                     dshift=dmod[:, :D], dscale=dmod[:, 2 * D:3 * D], dy_next=dyn,
+                     **(dict(y_next=yn, gate_next=mod[:, 5 * D:], dgate_next=dmod[:, 4 * D:5 * D]) if gated else {}))
+        cpu3, cu3 = both(b2, [dy, x, gamma, mod, cpu[4], cpu[5], dx, dgamma, dmod, yn, dyn])
+        close(cu3[6], cpu3[6], "fused ln dx", 1e-4); close(cu3[7], cpu3[7], "fused dgamma", 1e-4)
+        close(cu3[8], cpu3[8], "fused dshift/dscale/dgate", 1e-4); close(cu3[10], cpu3[10], "dy_next")
 
 
 def test_ln_gather_scatter_and_bf16_out():

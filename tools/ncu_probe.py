@@ -23,8 +23,9 @@ def ln(rows, D, T):
     mean = torch.empty(rows, device=dev); rstd = torch.empty(rows, device=dev)
     o.ln_fwd(x, y, mean, rstd, gamma=g, shift=mod[:, :D], scale=mod[:, D:2 * D], T=T)
     dy = r((rows, D), BF); dx = r((rows, D)); dg = torch.zeros(D, device=dev); dmod = torch.zeros_like(mod)
+    yb2 = r((rows, D), BF); dyn = torch.empty(rows, D, device=dev, dtype=BF)
     o.ln_bwd(dy, x, mean, rstd, gamma=g, scale=mod[:, D:2 * D], T=T, dx=dx, dx_mode=0, dgamma=dg, dshift=dmod[:, :D],
-             dscale=dmod[:, D:2 * D])
+             dscale=dmod[:, D:2 * D], dy_next=dyn, y_next=yb2, gate_next=mod[:, 2 * D:3 * D], dgate_next=dmod[:, 3 * D:4 * D])
     res = r((rows, D)); yb = r((rows, D), BF); dyb = torch.empty(rows, D, device=dev, dtype=BF)
     o.gate_bwd(res, dyb, y=yb, gate=mod[:, :D], dgate=dmod[:, 2 * D:3 * D], T=T)
 
