@@ -28,6 +28,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 #include "tensormap.cuh"
 
@@ -94,6 +96,17 @@ __device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
   return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * k0 * fmaf(3.0f * k1 * x, x, 1.0f);
 }
 
+// The activation kind is a compile-time parameter of the chunk loops: with a runtime `act ? tanh : erf` per element the
+// compiler evaluated BOTH activations and selected (the first fused epilogues spent twice the issue slots they needed).
+template <bool kTanh> __device__ __forceinline__ float gelu_fast(float x) {
+  if constexpr (kTanh) return gelu_tanh_fast(x);
+  else return gelu_erf_fast(x);
+}
+template <bool kTanh> __device__ __forceinline__ float gelu_grad_fast(float x) {
+  if constexpr (kTanh) return gelu_tanh_grad_fast(x);
+  else return gelu_erf_grad_fast(x);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b);
 __device__ __forceinline__ uint4 pack_bf16x8(float a0, float a1, float a2, float a3, float a4, float a5, float a6,
                                              float a7);
@@ -124,8 +137,7 @@ __device__ __forceinline__ void decode_tile(int r, int m_blocks, int n_blocks, i
 template <int BLOCK_N, bool kMN, int kCtas, int kEpiW>
 __global__ void __launch_bounds__(128 + 32 * kEpiW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
-                    const GemmDev p) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
   using Cfg = GemmCfg<BLOCK_N, kCtas, kEpiW>;
   constexpr int kColSplit = Cfg::kColSplit;
   // the 8-warp instantiations serve the activation tails only (host dispatch): compiling the residual / atomic / fp32
@@ -147,10 +159,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.tma_store) {
-      tma_prefetch_desc(&tmC);
-      if (p.epi == EPI_ACT_DUAL) tma_prefetch_desc(&tmC2);
-    }
+    if (p.tma_store == 1) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -411,16 +420,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               auxv[j] = *reinterpret_cast<const uint4*>(ab + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
             __syncwarp();
           }
+          auto apply_grad = [&](auto tanh_tag) {
+            constexpr bool kTanh = decltype(tanh_tag)::value;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t w = e == 0 ? auxv[j].x : e == 1 ? auxv[j].y : e == 2 ? auxv[j].z : auxv[j].w;
-              const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
-              v[8 * j + 2 * e] *= p.act ? gelu_tanh_grad_fast(x0) : gelu_erf_grad_fast(x0);
-              v[8 * j + 2 * e + 1] *= p.act ? gelu_tanh_grad_fast(x1) : gelu_erf_grad_fast(x1);
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t w = e == 0 ? auxv[j].x : e == 1 ? auxv[j].y : e == 2 ? auxv[j].z : auxv[j].w;
+                const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+                v[8 * j + 2 * e] *= gelu_grad_fast<kTanh>(x0);
+                v[8 * j + 2 * e + 1] *= gelu_grad_fast<kTanh>(x1);
+              }
             }
-          }
+          };
+          if (p.act) apply_grad(std::true_type{});
+          else apply_grad(std::false_type{});
         }
         if (p.debug == 1) {
           if (v[0] == 123.456f && v[31] == -654.321f) reinterpret_cast<float*>(p.C)[0] = v[5];  // keep the loads alive
@@ -455,19 +469,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.epi == EPI_ACT_DUAL) {
               // the activation is taken on the bf16-rounded pre-activation so that backward (which re-reads C)
               // differentiates the same function
+              auto stage_dual = [&](auto tanh_tag) {
+                constexpr bool kTanh = decltype(tanh_tag)::value;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float x[8], y[8];
+                for (int j = 0; j < 4; ++j) {
+                  float x[8], y[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  x[e] = bf16_round(v[8 * j + e]);
-                  y[e] = p.act ? gelu_tanh_fast(x[e]) : gelu_erf_fast(x[e]);
+                  for (int e = 0; e < 8; ++e) {
+                    x[e] = bf16_round(v[8 * j + e]);
+                    y[e] = gelu_fast<kTanh>(x[e]);
+                  }
+                  *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ sw) << 4)) =
+                      pack_bf16x8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+                  *reinterpret_cast<uint4*>(my_stage + Cfg::kStoreBufBytes + lane * 64 + ((j ^ sw) << 4)) =
+                      pack_bf16x8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
                 }
-                *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ sw) << 4)) =
-                    pack_bf16x8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-                *reinterpret_cast<uint4*>(my_stage + Cfg::kStoreBufBytes + lane * 64 + ((j ^ sw) << 4)) =
-                    pack_bf16x8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
-              }
+              };
+              if (p.act) stage_dual(std::true_type{});
+              else stage_dual(std::false_type{});
               write_box(my_stage, p.C);
               write_box(my_stage + Cfg::kStoreBufBytes, p.C2);
             } else {
@@ -493,32 +512,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
             }
             const int sw = (lane >> 1) & 3;
-            if (p.epi == EPI_ACT_DUAL) {
-              // pre-activation and activation of the chunk leave together: the warp's two staging buffers hold one box each
-              // (the activation is taken on the bf16-rounded pre-activation, see the direct-store path below)
-              if (lane == 0) tma_store_wait_read<0>();
-              __syncwarp();
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float x[8], y[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  x[e] = bf16_round(v[8 * j + e]);
-                  y[e] = p.act ? gelu_tanh_fast(x[e]) : gelu_erf_fast(x[e]);
-                }
-                *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ sw) << 4)) =
-                    pack_bf16x8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-                *reinterpret_cast<uint4*>(my_stage + Cfg::kStoreBufBytes + lane * 64 + ((j ^ sw) << 4)) =
-                    pack_bf16x8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
-              }
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_3d(&tmC, my_stage, col0, row0, bz);
-                tma_store_3d(&tmC2, my_stage + Cfg::kStoreBufBytes, col0, row0, bz);
-                tma_store_commit();
-              }
-            } else {
+            {
               uint8_t* buf = my_stage + (store_it & 1) * Cfg::kStoreBufBytes;
               if (lane == 0) tma_store_wait_read<1>();  // the store issued from this buffer two chunks ago has read it
               __syncwarp();
@@ -573,9 +567,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; j += 8) {
               float x[8], y[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                x[e] = bf16_round(v[j + e]);
-                y[e] = p.act ? gelu_tanh_fast(x[e]) : gelu_erf_fast(x[e]);
+              for (int e = 0; e < 8; ++e) x[e] = bf16_round(v[j + e]);
+              if (p.act) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = gelu_tanh_fast(x[e]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = gelu_erf_fast(x[e]);
               }
               const uint4 a = pack_bf16x8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
               const uint4 g = pack_bf16x8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
@@ -702,7 +700,7 @@ static int make_store_map(CUtensorMap* map, void* ptr, long long cols, long long
 template <int BLOCK_N, bool kMN, int kCtas, int kEpiW = 4>
 static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, kCtas, kEpiW>;
-  CUtensorMap tmA, tmB, tmC, tmC2;
+  CUtensorMap tmA, tmB, tmC;
   int rc;
   if (!kMN) {
     rc = make_map(&tmA, a->A, a->K, a->M, a->batch, a->lda, a->strideA, kBlockM);
@@ -735,24 +733,17 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
                            (!dual || (reinterpret_cast<uintptr_t>(a->C2) & 15) == 0) &&
                            (a->epilogue != EPI_ACT_GRAD || (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0);
   // staged + coalesced st.global (tma_store = 2): always for the math tails, MD_GEMM_TMA_STORE=2 forces it for the plain store
-  if (tma_store_env && bf16_out && aligned_out && (kEpiW == 8 || tma_store_env == 2)) {
+  const bool math = a->epilogue == EPI_ACT_DUAL || a->epilogue == EPI_ACT_GRAD;
+  if (tma_store_env && bf16_out && aligned_out && (math || tma_store_env == 2)) {
     dev.tma_store = 2;
     tmC = tmA;
-    tmC2 = tmA;
-  } else if (tma_store_env && bf16_out && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (a->ldc % 8) == 0 &&
-      (a->batch == 1 || (a->strideC % 8) == 0) && (!dual || (reinterpret_cast<uintptr_t>(a->C2) & 15) == 0)) {
+  } else if (tma_store_env && a->epilogue == EPI_STORE_BF16 && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 &&
+             (a->ldc % 8) == 0 && (a->batch == 1 || (a->strideC % 8) == 0)) {
     rc = make_store_map(&tmC, a->C, a->N, a->M, a->batch, a->ldc, a->strideC);
     if (rc) return rc;
-    if (dual) {
-      rc = make_store_map(&tmC2, a->C2, a->N, a->M, a->batch, a->ldc, a->strideC);
-      if (rc) return rc;
-    } else {
-      tmC2 = tmC;
-    }
     dev.tma_store = 1;
   } else {
     tmC = tmA;  // unused
-    tmC2 = tmA;
   }
   auto kern = gemm_tcgen05_kernel<BLOCK_N, kMN, kCtas, kEpiW>;
   static bool attr_set = false;
@@ -778,7 +769,7 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, dev);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, dev);
   if (e != cudaSuccess) return md_set_error(MD_ERR_CUDA, cudaGetErrorString(e));
   return 0;
 }

@@ -242,15 +242,15 @@ ln_bwd_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const int32
 
 // --------------------------------------------------------------------------------- ln_bwd (teams)
 // The model widths (512 / 768 / 1024): a row is shared by a TEAM of 2 or 4 warps (D = 128 * TEAM * V: V float4 groups per
-// lane), 8 / TEAM teams per 256-thread block.  Cutting the per-lane footprint is what makes room for the fused tail
+// lane), NT teams per block.  Cutting the per-lane footprint is what makes room for the fused tail
 // below (one warp per row sat at 245 registers, 8 warps per SM); the partial row sums cross through a double-buffered
 // shared-memory slot and a named barrier over the team.
 //
 // Fused tail (dy_next != NULL): dx_new is the gradient entering the NEXT branch of the backward chain (DiTBlock,
 // dit.py:236-238 read backwards), whose first step used to be a separate pass over dx (md_gate_bwd):
 //   dy_next = bf16(gate_next[sample] * dx_new),   dgate_next[sample] += sum_t dx_new * y_next.
-template <int V, int TEAM, bool XBF, typename AT>
-__global__ void __launch_bounds__(256, 2)
+template <int V, int TEAM, int NT, int kMinBlocks, bool kPrefetch, bool XBF, typename AT>
+__global__ void __launch_bounds__(32 * TEAM * NT, kMinBlocks)
 ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const int32_t* __restrict__ src_rows,
                    const float* __restrict__ gamma, const float* __restrict__ scale, long long ldmod, long long T,
                    const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ dx, int dx_mode,
@@ -258,7 +258,7 @@ ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const 
                    const AT* __restrict__ y_next, const float* __restrict__ gate_next, float* __restrict__ dgate_next,
                    AT* __restrict__ dy_next, int rpb) {
   constexpr int D = 128 * TEAM * V;
-  constexpr int NT = 8 / TEAM;  // teams per block
+  constexpr int kThreads = 32 * TEAM * NT;  // NT teams per block
   extern __shared__ float sm[];
   float* red = sm;             // [NT][D]
   float* sw = sm + NT * D;     // [D] gamma * (1 + scale): d xhat / d y, constant over the block (one sample)
@@ -273,7 +273,7 @@ ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const 
   const float* gt = gate_next ? gate_next + smp * ldmod : nullptr;
   const bool need_cols = (dgamma != nullptr) || (dshift != nullptr) || (dscale != nullptr);
   const bool need_gate = (dgate_next != nullptr) && (y_next != nullptr);
-  for (int c = threadIdx.x; c < D; c += 256) {
+  for (int c = threadIdx.x; c < D; c += kThreads) {
     sw[c] = (gamma ? gamma[c] : 1.f) * (sc ? 1.f + sc[c] : 1.f);
     sg[c] = gt ? gt[c] : 1.f;
   }
@@ -283,28 +283,50 @@ ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const 
 #pragma unroll
   for (int j = 0; j < V; ++j) accA[j] = accB[j] = accG[j] = f4zero();
   const int i0 = wt * 32 + lane;  // float4 group index of this lane: i0 + 32 * TEAM * j
-  int it = 0;
-  for (long long t = t0 + team; t < t1; t += NT, ++it) {
+  const bool want_old = dx != nullptr && dx_mode != 1;
+  // One row ahead: the loads of the team's next row are issued before this row's reductions and barrier, so a team
+  // keeps two rows in flight (with four warps per row only four rows per SM were in flight otherwise, half of what
+  // the one-warp-per-row kernel had, and the fused kernel ran at 0.65 of the HBM roofline).
+  float4 nd[V], nx[V], nold[V], ny[V];
+  float nmu = 0.f, nrs = 0.f;
+  long long ndrow = 0;
+  auto prefetch = [&](long long t) {
     const long long row = smp * T + t;
     const long long src = src_rows ? src_rows[row] : row;
-    const long long drow = (dx_mode == 2) ? src : row;
-    float4 d[V], xh[V], old[V], yv[V];
+    ndrow = (dx_mode == 2) ? src : row;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int i = i0 + 32 * TEAM * j;
-      d[j] = ld4a(dy + row * D + 4LL * i);
-      xh[j] = ld4<XBF>(x, src * D + 4LL * i);
+      nd[j] = ld4a(dy + row * D + 4LL * i);
+      nx[j] = ld4<XBF>(x, src * D + 4LL * i);
     }
-    if (dx != nullptr && dx_mode != 1) {
+    if (want_old) {
 #pragma unroll
       for (int j = 0; j < V; ++j)
-        old[j] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dx) + drow * D + 4LL * (i0 + 32 * TEAM * j));
+        nold[j] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dx) + ndrow * D + 4LL * (i0 + 32 * TEAM * j));
     }
     if (need_gate) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) yv[j] = ld4a(y_next + row * D + 4LL * (i0 + 32 * TEAM * j));
+      for (int j = 0; j < V; ++j) ny[j] = ld4a(y_next + row * D + 4LL * (i0 + 32 * TEAM * j));
     }
-    const float mu = mean[row], rs = rstd[row];
+    nmu = mean[row];
+    nrs = rstd[row];
+  };
+  if (t0 + team < t1) prefetch(t0 + team);
+  int it = 0;
+  for (long long t = t0 + team; t < t1; t += NT, ++it) {
+    const long long row = smp * T + t;
+    const long long drow = ndrow;
+    float4 d[V], xh[V], old[V], yv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      d[j] = nd[j];
+      xh[j] = nx[j];
+      old[j] = nold[j];
+      yv[j] = ny[j];
+    }
+    const float mu = nmu, rs = nrs;
+    if (kPrefetch && t + NT < t1) prefetch(t + NT);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -356,6 +378,7 @@ ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const 
         }
       }
     }
+    if (!kPrefetch && t + NT < t1) prefetch(t + NT);
   }
   if (!need_cols && !need_gate) return;
   // cross-team reduction of the column partials, one quantity at a time through red[NT][D]
@@ -368,7 +391,7 @@ ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const 
       *reinterpret_cast<float4*>(red + team * D + 4 * (i0 + 32 * TEAM * j)) =
           pass == 0 ? accA[j] : (pass == 1 ? accB[j] : accG[j]);
     __syncthreads();
-    for (int c = threadIdx.x; c < D; c += 256) {
+    for (int c = threadIdx.x; c < D; c += kThreads) {
       float v = 0.f;
 #pragma unroll
       for (int u = 0; u < NT; ++u) v += red[u * D + c];
@@ -631,23 +654,22 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
   dim3 grid(static_cast<unsigned>((T + rpb - 1) / rpb), static_cast<unsigned>(rows / T));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (D == 1024 || D == 768 || D == 512) {
-    const size_t smem = (6 * D + 64) * sizeof(float);
-#define LN_BWD_TEAM(V, TEAM)                                                                                               \
+    // width -> (float4 groups per lane, warps per row, rows in flight per block, blocks per SM, one-row-ahead loads)
+#define LN_BWD_TEAM(V, TEAM, NT, MINB, PF)                                                                              \
   MD_WITH_ACT(prec, do {                                                                                               \
+    const size_t smem = ((NT + 2) * D + 64) * sizeof(float);                                                          \
     if (x_bf16)                                                                                                        \
-      ln_bwd_team_kernel<V, TEAM, true, AT><<<grid, 256, smem, st>>>(CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T, mean, \
-                                                               rstd, dx, dx_mode, dgamma, dshift, dscale,              \
-                                                               CAP(AT, y_next), gate_next, dgate_next, AP(AT, dy_next), \
-                                                               rpb);                                                   \
+      ln_bwd_team_kernel<V, TEAM, NT, MINB, PF, true, AT><<<grid, 32 * TEAM * NT, smem, st>>>(                          \
+          CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T, mean, rstd, dx, dx_mode, dgamma, dshift, dscale,           \
+          CAP(AT, y_next), gate_next, dgate_next, AP(AT, dy_next), rpb);                                               \
     else                                                                                                               \
-      ln_bwd_team_kernel<V, TEAM, false, AT><<<grid, 256, smem, st>>>(CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T,      \
-                                                                mean, rstd, dx, dx_mode, dgamma, dshift, dscale,       \
-                                                                CAP(AT, y_next), gate_next, dgate_next,                \
-                                                                AP(AT, dy_next), rpb);                                 \
+      ln_bwd_team_kernel<V, TEAM, NT, MINB, PF, false, AT><<<grid, 32 * TEAM * NT, smem, st>>>(                         \
+          CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T, mean, rstd, dx, dx_mode, dgamma, dshift, dscale,           \
+          CAP(AT, y_next), gate_next, dgate_next, AP(AT, dy_next), rpb);                                               \
   } while (0))
-    if (D == 1024) LN_BWD_TEAM(2, 4);
-    else if (D == 768) LN_BWD_TEAM(3, 2);
-    else LN_BWD_TEAM(2, 2);
+    if (D == 1024) LN_BWD_TEAM(2, 4, 2, 2, true);
+    else if (D == 768) LN_BWD_TEAM(2, 3, 2, 2, true);
+    else LN_BWD_TEAM(2, 2, 4, 2, true);
 #undef LN_BWD_TEAM
     return check_launch("md_ln_bwd");
   }
