@@ -357,6 +357,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           return;
         }
         const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux) + crow + col0;
+        if (p.tma_store == 3) {  // one row per lane, two full 32-byte sectors per chunk (N % 16 == 0: whole pieces)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (row_ok && col0 + 16 * k < p.N) ld_global_256(ax + 16 * k, auxn[2 * k], auxn[2 * k + 1]);
+            else auxn[2 * k] = auxn[2 * k + 1] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          return;
+        }
         const bool live = row_ok && has_k && col0 < p.N;
         const bool vec = live && (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(ax) & 15) == 0);
 #pragma unroll
@@ -438,6 +446,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (p.debug == 1) {
           if (v[0] == 123.456f && v[31] == -654.321f) reinterpret_cast<float*>(p.C)[0] = v[5];  // keep the loads alive
+        } else if (p.tma_store == 3) {
+          // bf16 store straight from the accumulator registers: every lane owns one output row and writes its 64 bytes of the
+          // chunk as two 256-bit stores = two full 32-byte sectors, no shared-memory staging at all.  (The staged variants
+          // -- TMA store or coalesced st.global -- cost 4-8 KB of shared-memory traffic per chunk and warp, in a mainloop that
+          // is itself shared-memory-bandwidth bound.)
+          if (row_ok && col0 < p.N) {
+            if (p.bias != nullptr) {
+              const int ncols = min(32, p.N - col0);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += p.bias[1LL * bz * p.strideBias + col0 + j];
+            }
+            __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
+            auto put = [&](__nv_bfloat16* dst, const float (&f)[32]) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (col0 + 16 * k < p.N)
+                  st_global_256(dst + 16 * k,
+                                pack_bf16x8(f[16 * k], f[16 * k + 1], f[16 * k + 2], f[16 * k + 3], f[16 * k + 4],
+                                            f[16 * k + 5], f[16 * k + 6], f[16 * k + 7]),
+                                pack_bf16x8(f[16 * k + 8], f[16 * k + 9], f[16 * k + 10], f[16 * k + 11], f[16 * k + 12],
+                                            f[16 * k + 13], f[16 * k + 14], f[16 * k + 15]));
+              }
+            };
+            if (p.epi == EPI_ACT_DUAL) {
+              __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+              put(d1, v);
+              if (p.act) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+              }
+              put(d2, v);
+            } else {
+              put(d1, v);
+            }
+          }
         } else if (p.tma_store == 2) {
           // bf16 store staged through shared memory and written by the warp itself: the 32 x 32 box is transposed so that
           // four lanes write one full 64-byte row segment (fire-and-forget st.global, full sectors).  The math tails use
@@ -734,7 +783,20 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
                            (a->epilogue != EPI_ACT_GRAD || (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0);
   // staged + coalesced st.global (tma_store = 2): always for the math tails, MD_GEMM_TMA_STORE=2 forces it for the plain store
   const bool math = a->epilogue == EPI_ACT_DUAL || a->epilogue == EPI_ACT_GRAD;
-  if (tma_store_env && bf16_out && aligned_out && (math || tma_store_env == 2)) {
+  // 32-byte pieces for the register-direct 256-bit path
+  const bool aligned32 = aligned_out && (reinterpret_cast<uintptr_t>(a->C) & 31) == 0 && (a->ldc % 16) == 0 &&
+                         (a->N % 16) == 0 && (a->batch == 1 || (a->strideC % 16) == 0) &&
+                         (!dual || (reinterpret_cast<uintptr_t>(a->C2) & 31) == 0) &&
+                         (a->epilogue != EPI_ACT_GRAD || (reinterpret_cast<uintptr_t>(a->aux) & 31) == 0);
+  static int math_store_env = -1;  // MD_GEMM_MATH_STORE: 3 = 256-bit direct (default), 2 = staged + coalesced
+  if (math_store_env == -1) {
+    const char* e = getenv("MD_GEMM_MATH_STORE");
+    math_store_env = e ? atoi(e) : 3;
+  }
+  if (tma_store_env && bf16_out && aligned32 && ((math && math_store_env == 3) || tma_store_env == 3)) {
+    dev.tma_store = 3;
+    tmC = tmA;
+  } else if (tma_store_env && bf16_out && aligned_out && (math || tma_store_env == 2)) {
     dev.tma_store = 2;
     tmC = tmA;
   } else if (tma_store_env && a->epilogue == EPI_STORE_BF16 && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 &&
