@@ -51,7 +51,7 @@ __device__ long long g_dbg[8 * 512];
   do { if (p.dbg && blockIdx.x == 0 && (idx) < 512) g_dbg[(slot) * 512 + (idx)] = clock64(); } while (0)
 
 struct FwdParams {
-  int dbg;
+  int dbg, o256;
   __nv_bfloat16* o;
   long long ldo;
   float* lse;
@@ -338,14 +338,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (q_ok) {
         const float inv = __fdividef(1.f, l);
         __nv_bfloat16* dst = p.o + (static_cast<long long>(b) * p.Tq + qrow) * p.ldo + h * kHd + half * 32;
+        uint4 w[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 w;
-          w.x = pack2(__uint_as_float(r0[8 * g + 0]) * inv, __uint_as_float(r0[8 * g + 1]) * inv);
-          w.y = pack2(__uint_as_float(r0[8 * g + 2]) * inv, __uint_as_float(r0[8 * g + 3]) * inv);
-          w.z = pack2(__uint_as_float(r0[8 * g + 4]) * inv, __uint_as_float(r0[8 * g + 5]) * inv);
-          w.w = pack2(__uint_as_float(r0[8 * g + 6]) * inv, __uint_as_float(r0[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + g * 8) = w;
+          w[g].x = pack2(__uint_as_float(r0[8 * g + 0]) * inv, __uint_as_float(r0[8 * g + 1]) * inv);
+          w[g].y = pack2(__uint_as_float(r0[8 * g + 2]) * inv, __uint_as_float(r0[8 * g + 3]) * inv);
+          w[g].z = pack2(__uint_as_float(r0[8 * g + 4]) * inv, __uint_as_float(r0[8 * g + 5]) * inv);
+          w[g].w = pack2(__uint_as_float(r0[8 * g + 6]) * inv, __uint_as_float(r0[8 * g + 7]) * inv);
+        }
+        if (p.o256) {  // this thread's 64 bytes of the row as two full 32-byte sectors
+          st_global_256(dst, w[0], w[1]);
+          st_global_256(dst + 16, w[2], w[3]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + g * 8) = w[g];
         }
         if (half == 0) p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + qrow] = m2 + __log2f(l);
       }
@@ -410,6 +416,7 @@ extern "C" int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t
   p.dbg = dbg_env;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.ldo = ldo;
+  p.o256 = ((reinterpret_cast<uintptr_t>(o) & 31) == 0 && (ldo % 16) == 0) ? 1 : 0;
   p.lse = lse;
   p.H = static_cast<int>(H); p.Tq = static_cast<int>(Tq); p.Tk = static_cast<int>(Tk);
   p.n_pad = (p.Tk + 15) & ~15;
@@ -772,12 +779,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     // read back dQ of iteration `it` (this thread: 32 columns of its row) and, after the last query block of a phase,
     // dK (group 0) or dV (group 1) of the key row this thread owns
+    const int dr_log = (quarter == 0 && lane == 0), dr_slot = c ? 3 : 7;
     auto drain = [&](uint32_t g, const BwdPos& it) {
+      if (dr_log) DBG(dr_slot, 8 * g);
       mbar_wait_sleep(&mma_done[g & 1], (g >> 1) & 1);
+      if (dr_log) DBG(dr_slot, 8 * g + 1);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32(trow + kColdQ + c * 32, r);
       tmem_ld_wait();
+      if (dr_log) DBG(dr_slot, 8 * g + 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
@@ -808,12 +819,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           store_bf16x8(dst + 8 * e, f);
         }
       }
+      if (dr_log) DBG(dr_slot, 8 * g + 3);
       if (it.last) {
         uint32_t r2[32];
         const uint32_t col = c == 0 ? kColdK : kColdV;
         tmem_ld_32x32(trow + col, r);
         tmem_ld_32x32(trow + col + 32, r2);
         tmem_ld_wait();
+        if (dr_log) DBG(dr_slot, 8 * g + 4);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_free);
@@ -835,6 +848,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
+      if (dr_log) DBG(dr_slot, 8 * g + 5);
     };
 
     // the dQ partial that drain() of iteration `pv` adds to (written by this very thread one key block earlier) is fetched

@@ -766,7 +766,7 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
   static int tma_store_env = -1;
   if (tma_store_env == -1) {
     const char* e = getenv("MD_GEMM_TMA_STORE");
-    tma_store_env = e ? atoi(e) : 1;
+    tma_store_env = e ? atoi(e) : 3;  // 3 = 256-bit register-direct stores (default), 1 = TMA store, 2 = staged st.global, 0 = 16-byte direct
   }
   static int debug_env = -1;
   if (debug_env == -1) {

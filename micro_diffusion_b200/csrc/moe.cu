@@ -37,7 +37,12 @@ __global__ void __launch_bounds__(256, ME <= 8 ? 2 : 1)
 moe_gate_fwd_kernel(const AT* __restrict__ x, const float* __restrict__ wg, float* __restrict__ probs, long long rows,
                     int D, int E) {
   extern __shared__ float swg[];  // [E][D]
-  for (int i = threadIdx.x; i < E * D; i += blockDim.x) swg[i] = wg[i];
+  {  // 16-byte loads, several in flight per thread: a scalar copy loop exposed one L2 round trip per element
+    const int n4 = (E * D) >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+      reinterpret_cast<float4*>(swg)[i] = reinterpret_cast<const float4*>(wg)[i];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
@@ -274,7 +279,12 @@ moe_dx_bwd_kernel(const AT* __restrict__ dxin, const int32_t* __restrict__ inv, 
                   const float* __restrict__ probs, const float* __restrict__ wg, float* __restrict__ dscores,
                   AT* __restrict__ dx, int B, int T, int E, int k, int D) {
   extern __shared__ float swg[];  // [E][D]
-  for (int i = threadIdx.x; i < E * D; i += blockDim.x) swg[i] = wg[i];
+  {  // 16-byte loads, several in flight per thread: a scalar copy loop exposed one L2 round trip per element
+    const int n4 = (E * D) >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+      reinterpret_cast<float4*>(swg)[i] = reinterpret_cast<const float4*>(wg)[i];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hl = lane & 15;
@@ -403,6 +413,14 @@ moe_gate_wgrad_kernel(const float* __restrict__ dscores, const AT* __restrict__ 
   }
 }
 
+// kernels that stage the gate weights in shared memory: at most two resident blocks per SM (register budget), so a grid of
+// 2 x SMs pays the fill once per block
+static int staged_grid(long long warps_needed) {
+  long long blocks = (warps_needed + 7) / 8;
+  if (blocks > 148LL * 2) blocks = 148LL * 2;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
 static int warp_grid(long long warps_needed) {
   long long blocks = (warps_needed + 7) / 8;
   if (blocks > 148LL * 8) blocks = 148LL * 8;
@@ -440,7 +458,7 @@ extern "C" int md_moe_gate_fwd(const void* x, const float* wg, float* probs, int
     cudaFuncSetAttribute(moe_gate_fwd_kernel<16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  const int grid = warp_grid((rows + kRowsPerWarp - 1) / kRowsPerWarp);
+  const int grid = staged_grid((rows + kRowsPerWarp - 1) / kRowsPerWarp);
   if (E <= 8)
     MD_WITH_ACT(prec, moe_gate_fwd_kernel<8, AT><<<grid, 256, smem, ST(stream)>>>(CAP(AT, x), wg, probs, rows, (int)D, (int)E));
   else
@@ -517,10 +535,10 @@ extern "C" int md_moe_dx_bwd(const void* dxin, const int32_t* inv, const float* 
     attr = true;
   }
   if (E <= 8)
-    MD_WITH_ACT(prec, moe_dx_bwd_kernel<8, AT><<<warp_grid((B * T + 1) / 2), 256, smem, ST(stream)>>>(
+    MD_WITH_ACT(prec, moe_dx_bwd_kernel<8, AT><<<staged_grid((B * T + 1) / 2), 256, smem, ST(stream)>>>(
                           CAP(AT, dxin), inv, dgval, probs, wg, dscores, AP(AT, dx), (int)B, (int)T, (int)E, (int)k, (int)D));
   else
-    MD_WITH_ACT(prec, moe_dx_bwd_kernel<16, AT><<<warp_grid((B * T + 1) / 2), 256, smem, ST(stream)>>>(
+    MD_WITH_ACT(prec, moe_dx_bwd_kernel<16, AT><<<staged_grid((B * T + 1) / 2), 256, smem, ST(stream)>>>(
                           CAP(AT, dxin), inv, dgval, probs, wg, dscores, AP(AT, dx), (int)B, (int)T, (int)E, (int)k, (int)D));
   return check_launch("md_moe_dx_bwd");
 }

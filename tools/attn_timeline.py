@@ -55,6 +55,16 @@ if args.bwd:
             rows.append([e[k + 1] - e[k] for k in range(6)] + [r[8 * (i + 1)] - e[0]])
         print(f"--- {name}: {n} iterations; mean [wait stats, wait S/dP, compute, wait grad GEMMs (g-1), P/dS -> smem, "
               f"drain dQ(g-1)] and period:", np.array(rows).mean(0).round().tolist())
+    for slot, name in ((7, "drain, chunk 0"), (3, "drain, chunk 1")):
+        r = log[slot]
+        rows = []
+        for i in range(1, 40):
+            e = r[8 * i: 8 * i + 6]
+            if (e[:4] > 0).all():
+                rows.append([e[1] - e[0], e[2] - e[1], e[3] - e[2], (e[4] - e[3]) if e[4] > 0 else 0, (e[5] - e[4]) if e[4] > 0 else e[5] - e[3]])
+        if rows:
+            print(f"--- {name}: mean [wait grad GEMMs, dQ tmem->regs, dQ (+partial) store, dK/dV tmem->regs, dK/dV store]:",
+                  np.array(rows).mean(0).round().tolist())
     r = log[4]
     n = int((r > 0).sum()) // 8
     rows = []
