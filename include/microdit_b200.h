@@ -56,6 +56,11 @@ MD_API int md_abi_version(void);
 #define MD_EPI_ACT_GRAD 5   /* C(bf16) = alpha*acc * act'(aux) (no bias): the dgrad GEMM of an activation's output applies the
                              * activation's derivative at the saved pre-activation aux (bf16, indexed like C) */
 
+#define MD_EPI_SWIGLU 6     /* N = 2f columns in the 32-interleaved order (w1 block j, w2 block j, ...): C(bf16) = u = alpha*acc,
+                             * C2(bf16 [M, f], pitch ldc2) = silu(u1) * u2 (FeedForward, dit.py:88-89) */
+#define MD_EPI_SWIGLU_GRAD 7 /* N = f: acc = d h; C(bf16 [M, 2f] interleaved) = (d h * u2 * silu'(u1) | d h * silu(u1)) with
+                              * u = aux (bf16 [M, 2f] interleaved, indexed like C) */
+
 typedef struct md_gemm_args {
   const void* A; /* bf16 */
   const void* B; /* bf16 */
@@ -77,6 +82,10 @@ typedef struct md_gemm_args {
   int32_t act;      /* activation of MD_EPI_ACT_DUAL */
   float alpha;      /* 0 is treated as 1 */
   int32_t sm_limit; /* > 0: use at most this many SMs (persistent grid) -- leaves room for a concurrent collective */
+  int64_t ldc2, strideC2;   /* pitch / batch stride of C2 for MD_EPI_SWIGLU (0: N / 2, unbatched) */
+  int64_t row_interleave;   /* f > 0 (atomic epilogue, M == 2f): output row p is the gradient of row
+                             * (p % 64 < 32 ? 0 : f) + 32 * (p / 64) + p % 32 -- the weight gradient of a 32-row-interleaved
+                             * w1 | w2 stack lands in the parameters' own order */
 } md_gemm_args;
 
 /* Dense / batched bf16 GEMM, fp32 accumulation, tcgen05 tensor cores fed by TMA.
@@ -273,9 +282,11 @@ MD_API int md_cast_f32_bf16(const float* x, void* y, int64_t n, int prec, void* 
 /* out(f32 [N]) += column sums of x [rows, N] (bf16 if x_bf16 else f32), pitch ld (bias gradients) */
 MD_API int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int64_t rows, int64_t N, void* stream);
 /* W f32 [batch, rows, cols] -> wb bf16 same layout (optional) and wbt bf16 [batch, cols, rows] (optional):
- * the per-step bf16 operand copies of the fp32 master weights (what autocast does per call in the reference). */
+ * the per-step bf16 operand copies of the fp32 master weights (what autocast does per call in the reference).
+ * interleave_half = f > 0 (rows == 2f, f % 32 == 0): both copies hold the rows in the 32-interleaved order of the fused
+ * SwiGLU GEMMs (w1 rows 0-31, w2 rows 0-31, w1 rows 32-63, ...; MD_EPI_SWIGLU). */
 MD_API int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch, int64_t rows, int64_t cols,
-                             int prec, void* stream);
+                             int64_t interleave_half, int prec, void* stream);
 /* sumsq(f32 [1]) += sum x^2  (gradient-norm clipping, train.py:85-86) */
 MD_API int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream);
 /* fused (clip-scaled) AdamW on flat fp32 buffers (train.py:39, configs/res_256_pretrain.yaml:50-57):

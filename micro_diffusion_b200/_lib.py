@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("ldgate", C.c_int64), ("rows_per_gate", C.c_int64), ("res_mod", C.c_int64),
         ("layout", C.c_int32), ("epilogue", C.c_int32), ("splits", C.c_int32), ("act", C.c_int32),
         ("alpha", C.c_float), ("sm_limit", C.c_int32),
+        ("ldc2", C.c_int64), ("strideC2", C.c_int64), ("row_interleave", C.c_int64),
     ]
 
 

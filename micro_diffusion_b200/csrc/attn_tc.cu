@@ -478,7 +478,7 @@ constexpr int kTile = 16 * 1024;
 constexpr uint32_t kColS = 0, kColdP = 64, kColBuf = 128, kColdQ = 256, kColdK = 320, kColdV = 384;
 
 struct BwdParams {
-  int dbg;
+  int dbg, st256;
   const __nv_bfloat16* dout; long long lddo;
   const __nv_bfloat16* o; long long ldo;
   const float* lse;
@@ -802,6 +802,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 4; ++e) old[e] = *reinterpret_cast<const uint4*>(old_slot + 16 * e);
         }
+        uint4 w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float f[8];
@@ -816,7 +817,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               f[2 * j + 1] += of.y;
             }
           }
-          store_bf16x8(dst + 8 * e, f);
+          w[e] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+        }
+        // 16-byte stores from this one-row-per-lane layout touch 32 half-used sectors per instruction and took ~1500 cycles
+        // of every iteration (timeline); 256-bit stores write whole sectors with half the instructions
+        if (p.st256) {
+          st_global_256(dst, w[0], w[1]);
+          st_global_256(dst + 16, w[2], w[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) *reinterpret_cast<uint4*>(dst + 8 * e) = w[e];
         }
       }
       if (dr_log) DBG(dr_slot, 8 * g + 3);
@@ -838,13 +848,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           __nv_bfloat16* base = c == 0 ? p.dk + (static_cast<long long>(it.b) * Tk + key) * p.lddk
                                        : p.dv + (static_cast<long long>(it.b) * Tk + key) * p.lddv;
           __nv_bfloat16* dst = base + (it.h0 + kh) * kHd;
+          uint4 w[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const uint32_t* rr = e < 4 ? r : r2;
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(rr[8 * (e & 3) + j]) * mul;
-            store_bf16x8(dst + 8 * e, f);
+            w[e] = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+          }
+          if (p.st256) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) st_global_256(dst + 16 * e, w[2 * e], w[2 * e + 1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) *reinterpret_cast<uint4*>(dst + 8 * e) = w[e];
           }
         }
       }
@@ -995,6 +1013,8 @@ extern "C" int md_attn_bwd_tc(const void* dout, int64_t lddo, const void* q, int
   p.dq = reinterpret_cast<__nv_bfloat16*>(dq); p.lddq = lddq;
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.lddk = lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.lddv = lddv;
+  p.st256 = (((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) & 31) == 0 &&
+             ((lddq | lddk | lddv) % 16) == 0) ? 1 : 0;
   p.H = static_cast<int>(H); p.Tq = static_cast<int>(Tq); p.Tk = static_cast<int>(Tk);
   p.n_pad = (p.Tk + 15) & ~15;
   p.packed = (Tq <= 64 && (H % 2) == 0 && 2 * p.n_pad <= 128) ? 1 : 0;

@@ -173,7 +173,14 @@ __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long 
 template <typename AT>
 __global__ void __launch_bounds__(256)
 cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __restrict__ wbt, long long rows,
-                      long long cols) {
+                      long long cols, long long half) {
+  // half > 0 (rows == 2 * half, half % 32 == 0): the copies hold the rows in the 32-interleaved order of the fused SwiGLU
+  // GEMMs -- input row r (< half: w1, else w2) becomes row 64 * (r' / 32) + (w2 ? 32 : 0) + r' % 32, r' = r mod half
+  auto prow = [&](long long r) -> long long {
+    if (half <= 0) return r;
+    const long long rr = r < half ? r : r - half;
+    return 64 * (rr >> 5) + (r < half ? 0 : 32) + (rr & 31);
+  };
   __shared__ float tile[64][65];
   const long long bz = blockIdx.z;
   const float* wsrc = w + bz * rows * cols;
@@ -188,12 +195,12 @@ cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __re
       if (vec && c + 3 < cols) {
         const float4 f = *reinterpret_cast<const float4*>(wsrc + r * cols + c);
         v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-        if (wb) st4a(wb + bz * rows * cols + r * cols + c, f);
+        if (wb) st4a(wb + bz * rows * cols + prow(r) * cols + c, f);
       } else {
         for (int e = 0; e < 4; ++e)
           if (c + e < cols) {
             v[e] = wsrc[r * cols + c + e];
-            if (wb) st1a(wb + bz * rows * cols + r * cols + c + e, v[e]);
+            if (wb) st1a(wb + bz * rows * cols + prow(r) * cols + c + e, v[e]);
           }
       }
     }
@@ -210,12 +217,12 @@ cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __re
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[e] = tile[4 * tx + e][ty + 16 * pass];
-    AT* dst = wbt + bz * rows * cols + c * rows + r;
-    if (vec && r + 3 < rows) {
-      st4a(dst, make_float4(v[0], v[1], v[2], v[3]));
+    AT* dst = wbt + bz * rows * cols + c * rows;
+    if (vec && r + 3 < rows) {   // r % 4 == 0: the four rows stay adjacent under the 32-row interleave
+      st4a(dst + prow(r), make_float4(v[0], v[1], v[2], v[3]));
     } else {
       for (int e = 0; e < 4; ++e)
-        if (r + e < rows) st1a(dst + e, v[e]);
+        if (r + e < rows) st1a(dst + prow(r + e), v[e]);
     }
   }
 }
@@ -404,11 +411,13 @@ extern "C" int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int6
   return check_launch("md_colsum");
 }
 extern "C" int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch, int64_t rows, int64_t cols,
-                                 int prec, void* stream) {
+                                 int64_t interleave_half, int prec, void* stream) {
   if (batch * rows * cols == 0) return 0;
   if (!w) return md_set_error(MD_ERR_INVALID, "md_cast_transpose: null pointer");
+  if (interleave_half != 0 && (interleave_half % 32 != 0 || rows != 2 * interleave_half))
+    return md_set_error(MD_ERR_INVALID, "md_cast_transpose: interleave_half = f needs f % 32 == 0 and rows == 2 f");
   dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64), (unsigned)batch);
-  MD_WITH_ACT(prec, cast_transpose_kernel<AT><<<grid, 256, 0, ST(stream)>>>(w, AP(AT, wb), AP(AT, wbt), rows, cols));
+  MD_WITH_ACT(prec, cast_transpose_kernel<AT><<<grid, 256, 0, ST(stream)>>>(w, AP(AT, wb), AP(AT, wbt), rows, cols, interleave_half));
   return check_launch("md_cast_transpose");
 }
 extern "C" int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, int prec, void* stream) {

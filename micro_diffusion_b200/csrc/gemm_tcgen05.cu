@@ -309,7 +309,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       const int row = (mb * kCtas + cta_rank) * kBlockM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const long long crow = 1LL * bz * p.strideC + 1LL * row * p.ldc;
+      // weight gradient of a 32-row-interleaved stack (the fused-SwiGLU w1 | w2 layout): tile row -> parameter row
+      int row_out = row;
+      if (p.row_interleave > 0) {
+        const int blk = row >> 6, in = row & 63;
+        row_out = (in < 32 ? 0 : p.row_interleave) + 32 * blk + (in & 31);
+      }
+      const long long crow = 1LL * bz * p.strideC + 1LL * row_out * p.ldc;
       const long long rrow = 1LL * bz * p.strideC + 1LL * (p.res_mod > 0 ? row % p.res_mod : row) * p.ldc;
       const float* gate_row = nullptr;
       if (p.gate != nullptr && row_ok) gate_row = p.gate + 1LL * (row / p.rows_per_gate) * p.ldgate;
@@ -389,15 +395,109 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       };
-      if (p.epi == EPI_ACT_GRAD) load_aux(0);
+      if constexpr (kMath) { if (p.epi == EPI_ACT_GRAD) load_aux(0); }
 
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
+      bool swiglu_done = false;
+      if constexpr (kMath) {
+        if (p.epi == EPI_SWIGLU) {
+          // SwiGLU (dit.py:88-89) in the epilogue of the stacked w1 | w2 GEMM.  The weight stack is interleaved in blocks
+          // of 32 rows (w1 block j, w2 block j, ...), so chunk 2c holds u1 and chunk 2c + 1 the matching u2 columns of the
+          // same lane: C = u (bf16, the interleaved layout backward reads again), C2 = silu(u1) * u2 (bf16, natural).
+          swiglu_done = true;
+#pragma unroll 1
+          for (int cp = 0; cp < kChunksPerWarp / 2; ++cp) {
+            uint32_t r1[32], r2[32];
+            tmem_ld_32x32(tbase + (2 * cp) * 32, r1);
+            tmem_ld_32x32(tbase + (2 * cp + 1) * 32, r2);
+            tmem_ld_wait();
+            const int col0 = colbase + 2 * cp * 32;
+            if (row_ok && col0 < p.N) {
+              __nv_bfloat16* du = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
+              __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(p.C2) + 1LL * bz * p.strideC2 + 1LL * row * p.ldc2 + (col0 >> 1);
+              float a[32], b[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                a[j] = bf16_round(__uint_as_float(r1[j]) * p.alpha);
+                b[j] = bf16_round(__uint_as_float(r2[j]) * p.alpha);
+              }
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                st_global_256(du + 16 * k, pack_bf16x8(a[16 * k], a[16 * k + 1], a[16 * k + 2], a[16 * k + 3], a[16 * k + 4], a[16 * k + 5], a[16 * k + 6], a[16 * k + 7]),
+                              pack_bf16x8(a[16 * k + 8], a[16 * k + 9], a[16 * k + 10], a[16 * k + 11], a[16 * k + 12], a[16 * k + 13], a[16 * k + 14], a[16 * k + 15]));
+                st_global_256(du + 32 + 16 * k, pack_bf16x8(b[16 * k], b[16 * k + 1], b[16 * k + 2], b[16 * k + 3], b[16 * k + 4], b[16 * k + 5], b[16 * k + 6], b[16 * k + 7]),
+                              pack_bf16x8(b[16 * k + 8], b[16 * k + 9], b[16 * k + 10], b[16 * k + 11], b[16 * k + 12], b[16 * k + 13], b[16 * k + 14], b[16 * k + 15]));
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = a[j] * __fdividef(1.0f, 1.0f + __expf(-a[j])) * b[j];
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                st_global_256(dh + 16 * k, pack_bf16x8(a[16 * k], a[16 * k + 1], a[16 * k + 2], a[16 * k + 3], a[16 * k + 4], a[16 * k + 5], a[16 * k + 6], a[16 * k + 7]),
+                              pack_bf16x8(a[16 * k + 8], a[16 * k + 9], a[16 * k + 10], a[16 * k + 11], a[16 * k + 12], a[16 * k + 13], a[16 * k + 14], a[16 * k + 15]));
+            }
+            __syncwarp();
+          }
+        } else if (p.epi == EPI_SWIGLU_GRAD) {
+          // backward of the above inside the w3 dgrad GEMM: acc = d h (never stored); with the saved u1 | u2 of the same 32
+          // columns (aux, interleaved layout, 128 contiguous bytes per lane and chunk) the chunk leaves as
+          // d u1 = d h * u2 * silu'(u1), d u2 = d h * silu(u1) -- again 128 contiguous bytes of the interleaved d u.
+          swiglu_done = true;
+          uint4 ua[8];
+          auto load_u = [&](int c) {
+            const int col0 = colbase + c * 32;
+            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(p.aux) + crow + 2 * col0;
+            if (row_ok && col0 < p.N) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ld_global_256(src + 16 * k, ua[2 * k], ua[2 * k + 1]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) ua[k] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          };
+          load_u(0);
+#pragma unroll 1
+          for (int c = 0; c < kChunksPerWarp; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tbase + c * 32, r);
+            tmem_ld_wait();
+            const int col0 = colbase + c * 32;
+            const bool live = row_ok && col0 < p.N;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + 2 * col0;
+            uint4 o1[4], o2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // 8 columns per k: u1 words ua[k], u2 words ua[4 + k]
+              uint32_t w1[4] = {ua[k].x, ua[k].y, ua[k].z, ua[k].w};
+              uint32_t w2[4] = {ua[4 + k].x, ua[4 + k].y, ua[4 + k].z, ua[4 + k].w};
+              float d1[8], d2[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float u1 = __uint_as_float((e & 1) ? (w1[e >> 1] & 0xffff0000u) : (w1[e >> 1] << 16));
+                const float u2 = __uint_as_float((e & 1) ? (w2[e >> 1] & 0xffff0000u) : (w2[e >> 1] << 16));
+                const float d = __uint_as_float(r[8 * k + e]) * p.alpha;
+                const float sg = __fdividef(1.0f, 1.0f + __expf(-u1));
+                d1[e] = d * u2 * (sg * fmaf(u1, 1.0f - sg, 1.0f));
+                d2[e] = d * u1 * sg;
+              }
+              o1[k] = pack_bf16x8(d1[0], d1[1], d1[2], d1[3], d1[4], d1[5], d1[6], d1[7]);
+              o2[k] = pack_bf16x8(d2[0], d2[1], d2[2], d2[3], d2[4], d2[5], d2[6], d2[7]);
+            }
+            if (c + 1 < kChunksPerWarp) load_u(c + 1);   // flies under the next chunk's TMEM wait and the other warp's math
+            if (live) {
+              st_global_256(dst, o1[0], o1[1]);
+              st_global_256(dst + 16, o1[2], o1[3]);
+              st_global_256(dst + 32, o2[0], o2[1]);
+              st_global_256(dst + 48, o2[2], o2[3]);
+            }
+            __syncwarp();
+          }
+        }
+      }
       uint32_t rnext[32];
-      if (p.debug != 2) tmem_ld_32x32(tbase, rnext);
+      if (p.debug != 2 && !swiglu_done) tmem_ld_32x32(tbase, rnext);
 
 #pragma unroll 1
-      for (int c = 0; c < (p.debug == 2 ? 0 : kChunksPerWarp); ++c) {
+      for (int c = 0; c < ((p.debug == 2 || swiglu_done) ? 0 : kChunksPerWarp); ++c) {
         tmem_ld_wait();
         float v[32];
         float4 resv[8];
@@ -411,10 +511,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (c + 1 < kChunksPerWarp) {  // software pipeline: next chunk's TMEM + residual loads fly during this chunk
           tmem_ld_32x32(tbase + (c + 1) * 32, rnext);
           if constexpr (!kMath) { if (p.epi == EPI_RESID_F32) load_res(c + 1); }
-          if (p.epi == EPI_ACT_GRAD) load_aux(c + 1);
+          if constexpr (kMath) { if (p.epi == EPI_ACT_GRAD) load_aux(c + 1); }
         }
         const int col0 = colbase + c * 32;
-        if (p.epi == EPI_ACT_GRAD) {  // C = acc * act'(pre): the dgrad GEMM hands the pre-activation gradient on directly
+        if (kMath && p.epi == EPI_ACT_GRAD) {  // C = acc * act'(pre): the dgrad GEMM hands the pre-activation gradient on directly
           if (p.tma_store == 2) {
             uint8_t* ab = my_stage + Cfg::kStoreBufBytes;
 #pragma unroll
@@ -470,7 +570,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                             f[16 * k + 13], f[16 * k + 14], f[16 * k + 15]));
               }
             };
-            if (p.epi == EPI_ACT_DUAL) {
+            if (kMath && p.epi == EPI_ACT_DUAL) {
               __nv_bfloat16* d2 = reinterpret_cast<__nv_bfloat16*>(p.C2) + crow + col0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
@@ -487,7 +587,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               put(d1, v);
             }
           }
-        } else if (p.tma_store == 2) {
+        } else if (kMath && p.tma_store == 2) {
           // bf16 store staged through shared memory and written by the warp itself: the 32 x 32 box is transposed so that
           // four lanes write one full 64-byte row segment (fire-and-forget st.global, full sectors).  The math tails use
           // this instead of the TMA store: their stores queue behind the producer's prefetched operand loads in the TMA
@@ -547,7 +647,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               write_box(my_stage, p.C);
             }
           }
-        } else if (p.tma_store) {
+        } else if (!kMath && p.tma_store) {
           // bf16 store through shared memory: each lane (= output row) drops its 64 bytes into a 64B-swizzled 32 x 32
           // box and one lane hands the box to the TMA, which writes full lines and clips at the tensor edge.  Direct
           // st.global from this layout is one half-sector request per lane per store and kept the L1->XBAR port ~70 %
@@ -605,7 +705,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 32; ++j)  // static indices only: a runtime index would push v[] into local memory
                 if (j < ncols) atomicAdd(dst + j, v[j]);
             }
-          } else if (p.epi == EPI_ACT_DUAL) {
+          } else if (kMath && p.epi == EPI_ACT_DUAL) {
             // C = pre-activation (bf16), C2 = act(pre) (bf16); the activation is taken on the bf16-rounded
             // pre-activation so that backward (which re-reads C) differentiates the same function.
             __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(p.C) + crow + col0;
@@ -796,7 +896,7 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
   if (tma_store_env && bf16_out && aligned32 && ((math && math_store_env == 3) || tma_store_env == 3)) {
     dev.tma_store = 3;
     tmC = tmA;
-  } else if (tma_store_env && bf16_out && aligned_out && (math || tma_store_env == 2)) {
+  } else if (tma_store_env && math && aligned_out) {
     dev.tma_store = 2;
     tmC = tmA;
   } else if (tma_store_env && a->epilogue == EPI_STORE_BF16 && (reinterpret_cast<uintptr_t>(a->C) & 15) == 0 &&
@@ -853,6 +953,20 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
     return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: activation-gradient epilogue needs aux (the saved pre-activation)");
   if (a->epilogue == EPI_ACT_GRAD && a->bias != nullptr)
     return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: the activation-gradient epilogue takes no bias");
+  if (a->epilogue == EPI_SWIGLU || a->epilogue == EPI_SWIGLU_GRAD) {
+    const bool fwd = a->epilogue == EPI_SWIGLU;
+    const void* second = fwd ? a->C2 : a->aux;
+    const int64_t ld2 = fwd ? (a->ldc2 > 0 ? a->ldc2 : a->N / 2) : a->ldc;
+    if (second == nullptr || a->bias != nullptr || a->layout != MD_GEMM_NT || a->splits > 1)
+      return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: SwiGLU epilogues need C2 (forward) / aux (backward), NT layout, no bias");
+    if (a->N % (fwd ? 64 : 32) != 0 || (a->ldc % 16) != 0 || (ld2 % 16) != 0 ||
+        ((reinterpret_cast<uintptr_t>(a->C) | reinterpret_cast<uintptr_t>(second)) & 31) != 0 ||
+        (a->batch > 1 && ((a->strideC % 16) != 0 || (fwd && (a->strideC2 % 16) != 0))))
+      return md_set_error(MD_ERR_UNSUPPORTED,
+                          "md_gemm_bf16: SwiGLU epilogues need 32-byte aligned outputs, pitches % 16 == 0 and whole 32-column blocks");
+  }
+  if (a->row_interleave != 0 && (a->epilogue != EPI_ATOMIC_F32 || a->row_interleave % 32 != 0 || a->M != 2 * a->row_interleave))
+    return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: row_interleave = f needs the atomic epilogue, f % 32 == 0 and M == 2 f");
   if (a->gate != nullptr && a->rows_per_gate <= 0)
     return md_set_error(MD_ERR_INVALID, "md_gemm_bf16: gate needs rows_per_gate > 0");
   int splits = a->splits > 0 ? a->splits : 1;
@@ -880,6 +994,9 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   dev.res = reinterpret_cast<const float*>(a->res);
   dev.gate = reinterpret_cast<const float*>(a->gate);
   dev.aux = a->aux;
+  dev.ldc2 = a->ldc2 > 0 ? a->ldc2 : a->N / 2;
+  dev.strideC2 = a->strideC2;
+  dev.row_interleave = static_cast<int>(a->row_interleave);
   dev.M = static_cast<int>(a->M); dev.N = static_cast<int>(a->N); dev.K = static_cast<int>(a->K);
   dev.batch = static_cast<int>(a->batch); dev.splits = splits;
   dev.ldc = a->ldc; dev.strideC = a->strideC; dev.strideBias = a->strideBias;
@@ -921,13 +1038,10 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
     ctas_forced = e ? atoi(e) : 0;
   }
   const bool pair = ctas_forced == 2 || (ctas_forced == 0 && a->M > kBlockM);
-  // eight epilogue warps for the tails that do real math per element (NT only: the weight-gradient layout never has one)
-  static int epi8_env = -1;
-  if (epi8_env == -1) {
-    const char* e = getenv("MD_GEMM_EPI8");
-    epi8_env = e ? atoi(e) : 1;
-  }
-  const bool math_tail = (a->epilogue == EPI_ACT_DUAL || a->epilogue == EPI_ACT_GRAD) && !mn && epi8_env;
+  // eight epilogue warps for the tails that do real math per element (NT only; the 4-warp kernels do not carry them)
+  const bool swiglu = a->epilogue == EPI_SWIGLU || a->epilogue == EPI_SWIGLU_GRAD;  // only the 8-warp kernels carry them
+  const bool math_tail = swiglu || a->epilogue == EPI_ACT_DUAL || a->epilogue == EPI_ACT_GRAD;
+  if (math_tail && mn) return md_set_error(MD_ERR_UNSUPPORTED, "md_gemm_bf16: the activation / SwiGLU epilogues need the NT layout");
   if (pair) {
     if (mn) return use256 ? launch<256, true, 2>(a, dev, sm_count, stream) : launch<128, true, 2>(a, dev, sm_count, stream);
     if (math_tail)

@@ -9,6 +9,8 @@ enum {
   EPI_ATOMIC_F32 = MD_EPI_ATOMIC_F32,
   EPI_ACT_DUAL = MD_EPI_ACT_DUAL,
   EPI_ACT_GRAD = MD_EPI_ACT_GRAD,
+  EPI_SWIGLU = MD_EPI_SWIGLU,
+  EPI_SWIGLU_GRAD = MD_EPI_SWIGLU_GRAD,
   EPI_COUNT
 };
 // Kernel-side argument block (everything the device needs besides the two tensor maps).
@@ -19,8 +21,9 @@ struct GemmDev {
   const float* res;
   const float* gate;
   const void* aux;
-  long long ldc, strideC, strideBias, ldgate;
+  long long ldc, strideC, strideBias, ldgate, ldc2, strideC2;
   int M, N, K, batch, splits, rows_per_gate, epi, res_mod, act;
+  int row_interleave;  // > 0: output row p of the atomic epilogue goes to the parameter row of the 32-row-interleaved stack
   int debug;      // diagnostics only (MD_GEMM_DEBUG): 1 = epilogue skips its stores, 2 = also skips the TMEM loads
   int tma_store;  // bf16 store epilogue goes through smem staging + cp.async.bulk.tensor (tmC valid)
   float alpha;

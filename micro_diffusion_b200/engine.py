@@ -22,7 +22,7 @@ from .arch import BlockSpec, DiTConfig
 from .params import ParamStore
 
 NT, TN = 0, 1
-EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD = 0, 1, 2, 3, 4, 5
+EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD, EPI_SWIGLU, EPI_SWIGLU_GRAD = 0, 1, 2, 3, 4, 5, 6, 7
 ACT_ERF, ACT_TANH = 0, 1
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 
@@ -41,6 +41,31 @@ class Engine:
         """G[P,Q] (+)= dY[r,P]^T X[r,Q]  (reduction over the rows r); the library picks the split of the
         reduction that fills the SMs (splits=0)."""
         self.ops.gemm(dY, X, G, layout=TN, epi=EPI_ATOMIC, splits=0)
+
+    def _wgrad_w12(self, name, dU, X):
+        """Weight gradient of a w1 | w2 stack; with the fused SwiGLU layout the rows of d u arrive interleaved."""
+        self.ops.gemm(dU, X, self.store.G(name), layout=TN, epi=EPI_ATOMIC, splits=0,
+                      row_interleave=self.store.interleave.get(name, 0))
+
+    def _swiglu_fwd(self, name_w12, x, u, hact):
+        """u = x W12^T, hact = silu(u1) * u2 (dit.py:88-89): one GEMM when the stack is interleaved, GEMM + pass otherwise."""
+        o, st = self.ops, self.store
+        if st.interleave.get(name_w12, 0):
+            o.gemm(x, st.W(name_w12), u, epi=EPI_SWIGLU, C2=hact)
+        else:
+            o.gemm(x, st.W(name_w12), u)
+            o.swiglu_fwd(u, hact)
+
+    def _swiglu_bwd(self, name_w12, name_w3, dy, u, du):
+        """du = d(silu(u1) * u2) for d hact = dy W3: inside the w3 dgrad GEMM when the stack is interleaved."""
+        o, st = self.ops, self.store
+        f = u.shape[1] // 2
+        if st.interleave.get(name_w12, 0):
+            o.gemm(dy, st.WT(name_w3), du, epi=EPI_SWIGLU_GRAD, aux=u)
+        else:
+            dh = o.empty((dy.shape[0], f), BF16)
+            o.gemm(dy, st.WT(name_w3), dh)
+            o.swiglu_bwd(dh, u, du)
 
     def _mods(self, key, D, mod):
         o = self.store.layout.ada_offset[key]
@@ -122,9 +147,8 @@ class Engine:
         sv.ym = o.empty((M, D), BF16)
         if not bs.moe:  # SwiGLU (dit.py:88-89); its gated residual is left pending for the next LayerNorm
             sv.u = o.empty((M, 2 * f), BF16)
-            o.gemm(sv.xm3, st.W(n + ".mlp.w12"), sv.u)
             sv.hact = o.empty((M, f), BF16)
-            o.swiglu_fwd(sv.u, sv.hact)
+            self._swiglu_fwd(n + ".mlp.w12", sv.xm3, sv.u, sv.hact)
             o.gemm(sv.hact, st.W(n + ".mlp.w3.weight"), sv.ym)
             out, pend_out = sv.x2, (sv.ym, g_m)
         else:  # expert-choice MoE (dit.py:126-143): the combine kernel applies the gated residual itself
@@ -178,13 +202,11 @@ class Engine:
             dy = dy_in
         dxm = o.empty((M, D), BF16)
         if not bs.moe:
-            dh = o.empty((M, f), BF16)
-            o.gemm(dy, st.WT(n + ".mlp.w3.weight"), dh)
-            self._wgrad(dy, sv.hact, st.G(n + ".mlp.w3.weight"))
             du = o.empty((M, 2 * f), BF16)
-            o.swiglu_bwd(dh, sv.u, du)
+            self._swiglu_bwd(n + ".mlp.w12", n + ".mlp.w3.weight", dy, sv.u, du)
+            self._wgrad(dy, sv.hact, st.G(n + ".mlp.w3.weight"))
             o.gemm(du, st.WT(n + ".mlp.w12"), dxm)
-            self._wgrad(du, sv.xm3, st.G(n + ".mlp.w12"))
+            self._wgrad_w12(n + ".mlp.w12", du, sv.xm3)
         else:
             E, k = cfg.num_experts, sv.k
             dh2 = o.empty((E, B * k, D), BF16); dgval = o.empty((B, E, k), F32)
@@ -289,9 +311,8 @@ class Engine:
         s.yn2 = o.empty((R, D), BF16); s.m2 = o.empty((R,), F32); s.r2 = o.empty((R,), F32)
         o.ln_fwd(s.y1, s.yn2, s.m2, s.r2, gamma=P["y_emb_preprocess.norm2.weight"], T=L, eps=eps)
         s.u = o.empty((R, 2 * fp), BF16)
-        o.gemm(s.yn2, st.W("y_emb_preprocess.mlp.w12"), s.u)
         s.hact = o.empty((R, fp), BF16)
-        o.swiglu_fwd(s.u, s.hact)
+        self._swiglu_fwd("y_emb_preprocess.mlp.w12", s.yn2, s.u, s.hact)
         s.y2 = o.empty((R, D), F32)
         o.gemm(s.hact, st.W("y_emb_preprocess.mlp.w3.weight"), s.y2, epi=EPI_RESID, res=s.y1)
         s.ybf = o.empty((R, D), BF16)
@@ -375,14 +396,12 @@ class Engine:
         fp = cfg.prompt_ffn_dim
         dyb = o.empty((R, D), BF16)
         o.gate_bwd(dy2, dyb, T=L)
-        dh = o.empty((R, fp), BF16)
-        o.gemm(dyb, st.WT("y_emb_preprocess.mlp.w3.weight"), dh)
-        self._wgrad(dyb, s.hact, st.G("y_emb_preprocess.mlp.w3.weight"))
         du = o.empty((R, 2 * fp), BF16)
-        o.swiglu_bwd(dh, s.u, du)
+        self._swiglu_bwd("y_emb_preprocess.mlp.w12", "y_emb_preprocess.mlp.w3.weight", dyb, s.u, du)
+        self._wgrad(dyb, s.hact, st.G("y_emb_preprocess.mlp.w3.weight"))
         dyn = o.empty((R, D), BF16)
         o.gemm(du, st.WT("y_emb_preprocess.mlp.w12"), dyn)
-        self._wgrad(du, s.yn2, st.G("y_emb_preprocess.mlp.w12"))
+        self._wgrad_w12("y_emb_preprocess.mlp.w12", du, s.yn2)
         o.ln_bwd(dyn, s.y1, s.m2, s.r2, gamma=P["y_emb_preprocess.norm2.weight"], T=L, dx=dy2, dx_mode=0,
                  dgamma=G["y_emb_preprocess.norm2.weight"])
         # ---- prompt block: self attention

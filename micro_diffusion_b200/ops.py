@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import GemmArgs, MicroditLibraryError
 
 NT, TN = 0, 1
-EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD = 0, 1, 2, 3, 4, 5
+EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD, EPI_SWIGLU, EPI_SWIGLU_GRAD = 0, 1, 2, 3, 4, 5, 6, 7
 ACT_GELU_ERF, ACT_GELU_TANH = 0, 1
 
 _I64 = C.c_int64
@@ -71,7 +71,7 @@ _PROTOS = {
     "md_mean_tokens_bwd": [_P, _P, _I64, _I64, _I64, _P],
     "md_cast_f32_bf16": [_P, _P, _I64, _I, _P],
     "md_colsum": [_P, _I, _I64, _P, _I64, _I64, _P],
-    "md_cast_transpose": [_P, _P, _P, _I64, _I64, _I64, _I, _P],
+    "md_cast_transpose": [_P, _P, _P, _I64, _I64, _I64, _I64, _I, _P],
     "md_sumsq": [_P, _P, _I64, _P],
     "md_adamw": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I64, _P, _I64, _P],
 }
@@ -172,8 +172,9 @@ class CudaOps:
         return out if x.dim() == 3 else out[0]
 
     def gemm(self, A, B, Cm, *, layout=NT, epi=EPI_BF16, C2=None, bias=None, res=None, gate=None, rows_per_gate=0,
-             res_mod=0, splits=1, act=0, alpha=1.0, aux=None):
+             res_mod=0, splits=1, act=0, alpha=1.0, aux=None, row_interleave=0):
         if self.prec:
+            assert epi not in (EPI_SWIGLU, EPI_SWIGLU_GRAD) and not row_interleave, "fused SwiGLU is a bf16-mode layout"
             # high precision: the same tcgen05 kernel at 3x the contraction depth over bf16 (hi, lo) splits of the fp32
             # operands; outputs stay fp32 (the bf16-store epilogues become fp32 stores, the fused activation a second pass)
             along = 0 if layout == NT else 1
@@ -193,10 +194,11 @@ class CudaOps:
                             gate=gate, rows_per_gate=rows_per_gate, res_mod=res_mod, splits=splits, alpha=alpha)
             return
         self._gemm_lowp(A, B, Cm, layout=layout, epi=epi, C2=C2, bias=bias, res=res, gate=gate,
-                        rows_per_gate=rows_per_gate, res_mod=res_mod, splits=splits, act=act, alpha=alpha, aux=aux)
+                        rows_per_gate=rows_per_gate, res_mod=res_mod, splits=splits, act=act, alpha=alpha, aux=aux,
+                        row_interleave=row_interleave)
 
     def _gemm_lowp(self, A, B, Cm, *, layout=NT, epi=EPI_BF16, C2=None, bias=None, res=None, gate=None, rows_per_gate=0,
-                   res_mod=0, splits=1, act=0, alpha=1.0, aux=None):
+                   res_mod=0, splits=1, act=0, alpha=1.0, aux=None, row_interleave=0):
         a = GemmArgs()
         batched = A.dim() == 3
         A3, B3, C3 = (A, B, Cm) if batched else (A.unsqueeze(0), B.unsqueeze(0), Cm.unsqueeze(0))
@@ -210,7 +212,8 @@ class CudaOps:
             K, M = A3.shape[1], A3.shape[2]
             N = B3.shape[2]
             assert B3.shape[1] == K
-        assert C3.shape[1] == M and C3.shape[2] == N, (C3.shape, M, N)
+        # the SwiGLU backward epilogue turns the N = f columns of d h into the 2f interleaved columns of d u
+        assert C3.shape[1] == M and C3.shape[2] == (2 * N if epi == EPI_SWIGLU_GRAD else N), (C3.shape, M, N)
         a.A, a.B, a.C, a.C2 = A3.data_ptr(), B3.data_ptr(), C3.data_ptr(), _ptr(C2)
         a.bias, a.res, a.aux = _ptr(bias), _ptr(res), _ptr(aux)
         a.M, a.N, a.K = M, N, K
@@ -223,13 +226,19 @@ class CudaOps:
         a.res_mod = res_mod
         a.layout, a.epilogue, a.splits, a.act, a.alpha = layout, epi, splits, act, alpha
         a.sm_limit = self.sm_limit
-        if C2 is not None:
+        a.row_interleave = row_interleave
+        a.ldc2 = a.strideC2 = 0
+        if epi == EPI_SWIGLU:
+            assert C2 is not None and C2.dtype == torch.bfloat16 and C2.shape[-1] == N // 2 and C2.stride(-1) == 1
+            a.ldc2 = C2.stride(-2)
+            a.strideC2 = C2.stride(0) if C2.dim() == 3 else 0
+        elif C2 is not None:
             assert C2.is_contiguous() or C2.stride(-2) == C3.stride(1)
         if aux is not None:
             assert aux.dtype == torch.bfloat16 and aux.shape == Cm.shape and aux.stride() == Cm.stride()
         if res is not None:
             assert res.dtype == torch.float32 and res.stride(-1) == 1 and res.stride(-2) == C3.stride(1)
-        want = torch.bfloat16 if epi in (EPI_BF16, EPI_ACT_DUAL, EPI_ACT_GRAD) else torch.float32
+        want = torch.bfloat16 if epi in (EPI_BF16, EPI_ACT_DUAL, EPI_ACT_GRAD, EPI_SWIGLU, EPI_SWIGLU_GRAD) else torch.float32
         assert Cm.dtype == want, (Cm.dtype, epi)
         flops = 2 * M * N * K * int(a.batch)
         self.gemm_flops += flops
@@ -436,12 +445,12 @@ class CudaOps:
         rows, N = x.shape
         self._call("md_colsum", x.data_ptr(), int(x.dtype == torch.bfloat16), x.stride(0), out.data_ptr(), rows, N)
 
-    def cast_transpose(self, w, wb, wbt):
+    def cast_transpose(self, w, wb, wbt, interleave_half=0):
         if w.dim() == 2:
             batch, (rows, cols) = 1, w.shape
         else:
             batch, rows, cols = w.shape
-        self._call("md_cast_transpose", w.data_ptr(), _ptr(wb), _ptr(wbt), batch, rows, cols)
+        self._call("md_cast_transpose", w.data_ptr(), _ptr(wb), _ptr(wbt), batch, rows, cols, interleave_half)
 
     def sumsq(self, x, out):
         self._call("md_sumsq", x.data_ptr(), out.data_ptr(), x.numel())

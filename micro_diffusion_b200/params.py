@@ -13,6 +13,8 @@ views into it.  That gives
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
@@ -152,6 +154,14 @@ class ParamStore:
         self.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.wb = torch.zeros(n, dtype=lowp_dtype, device=self.device)
         self.wbt = torch.zeros(n, dtype=lowp_dtype, device=self.device)
+        # fused SwiGLU (MD_EPI_SWIGLU, bf16 mode): the bf16 copies of every w1 | w2 stack interleave the two halves in blocks
+        # of 32 rows, so that the GEMM epilogue finds u1 and u2 of a column in the same lane; the fp32 master weights and
+        # gradients keep the parameters' own order.  group name -> f (0 / absent: plain order)
+        self.interleave: Dict[str, int] = {}
+        if lowp_dtype == torch.bfloat16 and os.environ.get("MD_FUSE_SWIGLU", "1") != "0":
+            for g in layout.groups.values():
+                if g.name.endswith(".w12") and g.batch == 1 and (g.rows // 2) % 32 == 0 and g.cols % 16 == 0:
+                    self.interleave[g.name] = g.rows // 2
         self._copies_version: Dict[str, object] = {}
         self.param_ready: Dict[str, object] = {}  # part -> CUDA event of a pending parameter all-gather
         self.p: Dict[str, torch.Tensor] = {}  # fp32 views (reference shapes)
@@ -211,7 +221,7 @@ class ParamStore:
                 src = self.flat[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
                 wb = self.wb[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
                 wbt = self.wbt[g.offset: g.offset + g.numel].view(g.batch, g.cols, g.rows) if g.need_t else None
-                ops.cast_transpose(src, wb, wbt)
+                ops.cast_transpose(src, wb, wbt, interleave_half=self.interleave.get(g.name, 0))
             self._copies_version[pt] = v
             done = True
         return done

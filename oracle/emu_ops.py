@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 NT, TN = 0, 1
-EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD = 0, 1, 2, 3, 4, 5
+EPI_BF16, EPI_F32, EPI_RESID, EPI_ATOMIC, EPI_ACT_DUAL, EPI_ACT_GRAD, EPI_SWIGLU, EPI_SWIGLU_GRAD = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 def _f(t):
@@ -25,6 +25,13 @@ def _f(t):
 def _expand_mod(m, T, rows):
     """[samples, D] -> [rows, D]"""
     return m.float().repeat_interleave(T, dim=0)[:rows]
+
+
+def interleave_perm(f: int) -> torch.Tensor:
+    """perm[p] = row of the natural w1 | w2 stack ([2f, D]) that sits at row p of the 32-interleaved stack."""
+    p = torch.arange(2 * f)
+    blk, inn = p // 64, p % 64
+    return torch.where(inn < 32, 32 * blk + inn, f + 32 * blk + (inn - 32))
 
 
 class EmuOps:
@@ -60,7 +67,7 @@ class EmuOps:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, Cm, *, layout=NT, epi=EPI_BF16, C2=None, bias=None, res=None, gate=None, rows_per_gate=0,
-             res_mod=0, splits=1, act=0, alpha=1.0, aux=None):
+             res_mod=0, splits=1, act=0, alpha=1.0, aux=None, row_interleave=0):
         self.launches += 1
         batched = A.dim() == 3
         A3, B3, C3 = (A, B, Cm) if batched else (A.unsqueeze(0), B.unsqueeze(0), Cm.unsqueeze(0))
@@ -81,7 +88,27 @@ class EmuOps:
             C3.copy_(acc)
         elif epi == EPI_ATOMIC:
             assert Cm.dtype == torch.float32
-            C3.add_(acc)
+            if row_interleave:  # rows arrive in the 32-interleaved order of a w1 | w2 stack, the gradient is in parameter order
+                C3.index_add_(1, interleave_perm(row_interleave), acc)
+            else:
+                C3.add_(acc)
+        elif epi == EPI_SWIGLU:
+            # columns in the interleaved order: [64j, 64j+32) = u1 block j, [64j+32, 64j+64) = u2 block j
+            u = self._r(acc)
+            C3.copy_(u)
+            nb = u.shape[-1] // 64
+            ub = u.float().reshape(u.shape[0], u.shape[1], nb, 2, 32)
+            h = F.silu(ub[:, :, :, 0]) * ub[:, :, :, 1]
+            (C2 if batched else C2.unsqueeze(0)).copy_(h.reshape(u.shape[0], u.shape[1], nb * 32))
+        elif epi == EPI_SWIGLU_GRAD:
+            x3 = aux if batched else aux.unsqueeze(0)
+            nb = acc.shape[-1] // 32
+            ub = _f(x3).reshape(acc.shape[0], acc.shape[1], nb, 2, 32)
+            a, b = ub[:, :, :, 0], ub[:, :, :, 1]
+            d = acc.reshape(acc.shape[0], acc.shape[1], nb, 32)
+            sg = torch.sigmoid(a)
+            du = torch.stack([d * b * (sg * (1 + a * (1 - sg))), d * a * sg], dim=3)
+            C3.copy_(du.reshape(acc.shape[0], acc.shape[1], nb * 64))
         elif epi == EPI_ACT_DUAL:
             assert (self.exact or Cm.dtype == torch.bfloat16) and C2 is not None
             pre = self._r(acc)
@@ -503,8 +530,10 @@ class EmuOps:
         self.launches += 1
         out.add_(_f(x).sum(0))
 
-    def cast_transpose(self, w, wb, wbt):
+    def cast_transpose(self, w, wb, wbt, interleave_half=0):
         self.launches += 1
+        if interleave_half:  # output row p holds parameter row perm[p]
+            w = w.index_select(-2, interleave_perm(interleave_half))
         if wb is not None:
             wb.copy_(w)
         if wbt is not None:

@@ -44,6 +44,10 @@ def close(a, b, what, rtol=None, atol=None, ulps=4.0):
     assert worst <= 1.0, f"{what}: element error {worst:.2f}x the {ulps}-ulp bound (rel-L2 {l2:.3e})"
 
 
+def rel_l2(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
 def both(fn, tensors):
     """run fn(ops, *tensors) on CPU-emulation and CUDA copies; returns (cpu tensors, cuda tensors)."""
     emu = EmuOps("cpu")
@@ -388,6 +392,32 @@ def test_gemm_activation_epilogues(M, N, K, batch, ld_extra, act):
     close(cu[3][..., :N], cpu[3][..., :N], "act grad")
     if ld_extra:
         assert torch.equal(cu[3].cpu()[..., N:], cpu[3][..., N:]), "store leaked outside its column slice"
+
+
+@pytest.mark.parametrize("M,f,K", [(512, 256, 128), (1000, 96, 192), (96, 64, 64), (300, 2816, 64)])
+def test_gemm_swiglu_epilogues(M, f, K):
+    """Fused SwiGLU (dit.py:88-89): interleaved bf16 weight copies (md_cast_transpose), u = x W12^T with
+    hact = silu(u1) * u2 in the epilogue (MD_EPI_SWIGLU), d u inside the w3 dgrad GEMM (MD_EPI_SWIGLU_GRAD) and the
+    weight gradient of the interleaved stack landing in parameter order (row_interleave)."""
+    from oracle.emu_ops import interleave_perm
+    w12 = rnd((2 * f, K), 1, scale=K ** -0.5)
+    wb = torch.zeros(2 * f, K, dtype=BF16); wbt = torch.zeros(K, 2 * f, dtype=BF16)
+    cpu, cu = both(lambda o, w, wb, wbt: o.cast_transpose(w, wb, wbt, interleave_half=f), [w12, wb, wbt])
+    assert torch.equal(cu[1].cpu(), cpu[1]) and torch.equal(cu[2].cpu(), cpu[2])
+    assert torch.equal(cpu[1].float(), w12[interleave_perm(f)].to(BF16).float())
+    x = rnd((M, K), 2, BF16); u = torch.zeros(M, 2 * f, dtype=BF16); h = torch.zeros(M, f, dtype=BF16)
+    cpu2, cu2 = both(lambda o, x, wb, u, h: o.gemm(x, wb, u, epi=6, C2=h), [x, cpu[1], u, h])
+    close(cu2[2], cpu2[2], "swiglu u"); close(cu2[3], cpu2[3], "swiglu hact")
+    # same function as the un-fused pair on the natural layout
+    un = (x.float() @ w12.to(BF16).float().t()).to(BF16).float()
+    ref_h = torch.nn.functional.silu(un[:, :f]) * un[:, f:]
+    assert rel_l2(cpu2[3].float(), ref_h) < 1e-2
+    w3t = rnd((f, K), 3, BF16, scale=K ** -0.5); dy = rnd((M, K), 4, BF16); du = torch.zeros(M, 2 * f, dtype=BF16)
+    cpu3, cu3 = both(lambda o, dy, w3t, uu, du: o.gemm(dy, w3t, du, epi=7, aux=uu), [dy, w3t, cpu2[2], du])
+    close(cu3[3], cpu3[3], "swiglu du")
+    g = rnd((2 * f, K), 5)
+    cpu4, cu4 = both(lambda o, du, x, g: o.gemm(du, x, g, layout=1, epi=3, splits=0, row_interleave=f), [cpu3[3], x, g])
+    close(cu4[2], cpu4[2], "interleaved wgrad", 1e-4)
 
 
 @pytest.mark.parametrize("layout,M,N,K,batch,ld_extra,col_off", [
