@@ -42,13 +42,26 @@ def attn(Tq, Tk, H, hd=64):
     o.rownorm_bwd(dq, q[:, :hs], rs)
 
 
-def gemm(M, N, K, layout=0, epi=0, splits=1):
-    if layout == 0:
-        A = r((M, K), BF); Bm = r((N, K), BF)
+def gemm(M, N, K, layout=0, epi=0, splits=1, batch=1):
+    sa, sb = ((M, K), (N, K)) if layout == 0 else ((K, M), (K, N))
+    if batch > 1:
+        sa, sb = (batch,) + sa, (batch,) + sb
+    A = r(sa, BF); Bm = r(sb, BF)
+    cs = (batch, M, N) if batch > 1 else (M, N)
+    if epi in (0, 4, 5):
+        C = torch.zeros(cs, device=dev, dtype=BF)
+        extra = {}
+        if epi == 4:
+            extra = dict(C2=torch.zeros(cs, device=dev, dtype=BF), act=0)
+        if epi == 5:
+            extra = dict(aux=r(cs, BF), act=0)
+        o.gemm(A, Bm, C, layout=layout, epi=epi, **extra)
+    elif epi == 6:   # fused SwiGLU forward: N = 2f interleaved columns
+        o.gemm(A, Bm, torch.zeros(M, N, device=dev, dtype=BF), epi=6, C2=torch.zeros(M, N // 2, device=dev, dtype=BF))
+    elif epi == 7:   # fused SwiGLU backward: N = f, output 2f
+        o.gemm(A, Bm, torch.zeros(M, 2 * N, device=dev, dtype=BF), epi=7, aux=r((M, 2 * N), BF))
     else:
-        A = r((K, M), BF); Bm = r((K, N), BF)
-    C = torch.zeros(M, N, device=dev, dtype=BF if epi == 0 else F32)
-    o.gemm(A, Bm, C, layout=layout, epi=epi, splits=splits)
+        o.gemm(A, Bm, torch.zeros(cs, device=dev, dtype=F32), layout=layout, epi=epi, splits=splits)
 
 
 def rowwise(rows, D, h, f):
@@ -97,7 +110,7 @@ def optimizer(n):
 
 
 ONLY = os.environ.get("MD_PROBE", "")  # "rows": the HBM-bound kernels only (no GEMM / attention)
-for rep in range(2):  # first pass = warm-up
+for rep in range(int(os.environ.get("MD_PROBE_REPS", "2"))):  # first pass = warm-up (ncu: MD_PROBE_REPS=1)
     if ONLY == "rows":
         ln(16384, 1024, 64)
         ln(65536, 768, 256)
@@ -112,8 +125,14 @@ for rep in range(2):  # first pass = warm-up
     attn(64, 64, 12)
     attn(64, 77, 16)
     gemm(16384, 3072, 1024)
+    gemm(32768, 1024, 1024)
     gemm(16384, 640, 1024)
     gemm(65536, 768, 2048)
+    gemm(131072, 768, 768)
     gemm(1024, 3072, 16384, layout=1, epi=3, splits=3)
+    gemm(16384, 3072, 768, epi=4, batch=8)   # expert GEMM 1 + GELU (dual store)
+    gemm(16384, 3072, 768, epi=5, batch=8)   # expert dgrad + GELU'
+    gemm(32768, 5632, 1024, epi=6)           # w12 GEMM + SwiGLU
+    gemm(32768, 2816, 1024, epi=7)           # w3 dgrad + SwiGLU backward
     torch.cuda.synchronize()
 print("probe done")
