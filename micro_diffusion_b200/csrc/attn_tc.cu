@@ -37,11 +37,13 @@ constexpr int kThreads = 384;            // backward: 4 control warps + 2 groups
 constexpr int kFwdThreads = 640;         // forward: 4 control warps + 2 groups of 8 (two threads per query row)
 constexpr int kTmemCols = 512;
 constexpr int kBytesQ = kQ * kHd * 2;            // 16 KB
-constexpr int kStageQKP = 64 * 1024;             // Q (16 KB) + K (<= 32 KB); later P (<= 64 KB = 4 atoms of 64 keys)
-constexpr int kStageV = 32 * 1024;
-constexpr int kStage = kStageQKP + kStageV;      // 96 KB
 constexpr int kBytesPAtom = kQ * 64 * 2;         // 16 KB: 128 rows x 64 keys
-constexpr int kOffBar = 2 * kStage;
+// A shared-memory stage = [Q (16 KB) | K (keys x 128 B)] -- later overwritten by P (one 16 KB atom per 64 keys) -- and V
+// (keys x 128 B), sized at launch from the sequence lengths: 96 KB for 256 keys (two stages), 43-68 KB for the 64 / 77-key
+// shapes (three stages: the TMA load of tile i+1 then no longer waits for the PV MMA of tile i-1 to free a stage, which had
+// put the whole load latency on every tile's critical path).  TMEM stays double-buffered (tile parity).
+constexpr int kMaxStages = 3;
+constexpr int kOffBar = 208 * 1024;               // >= stages x stage bytes for every shape (host checks)
 constexpr int kOffXch = kOffBar + 256;            // 2 groups x [max | sum] x 2 halves x 128 rows of fp32 = 4 KB
 constexpr int kSmemBytes = kOffXch + 4096 + 1024;
 
@@ -52,6 +54,7 @@ __device__ long long g_dbg[8 * 512];
 
 struct FwdParams {
   int dbg, o256;
+  int ns, stage_bytes, v_off;   // shared-memory ring: stages, bytes per stage, offset of V inside a stage
   __nv_bfloat16* o;
   long long ldo;
   float* lse;
@@ -85,13 +88,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* qk_full = bars;        // [2] TMA bytes of Q + K
-  uint64_t* v_full = bars + 2;     // [2] TMA bytes of V
-  uint64_t* s_full = bars + 4;     // [2] S in TMEM (tcgen05.commit)
-  uint64_t* p_full = bars + 6;     // [2] P in shared memory, S consumed (4 warps)
-  uint64_t* o_full = bars + 8;     // [2] O in TMEM, stage's shared memory free again (tcgen05.commit)
-  uint64_t* o_free = bars + 10;    // [2] O read back: the TMEM buffer is free (4 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* qk_full = bars;        // [3] TMA bytes of Q + K             (indexed by shared-memory stage)
+  uint64_t* v_full = bars + 3;     // [3] TMA bytes of V
+  uint64_t* st_free = bars + 6;    // [3] PV of the tile retired: the stage's shared memory is free (tcgen05.commit)
+  uint64_t* s_full = bars + 9;     // [2] S in TMEM (tcgen05.commit)     (indexed by tile parity = TMEM buffer = group)
+  uint64_t* p_full = bars + 11;    // [2] P in shared memory, S consumed (8 warps)
+  uint64_t* o_full = bars + 13;    // [2] O in TMEM (tcgen05.commit)
+  uint64_t* o_free = bars + 15;    // [2] O read back: the TMEM buffer is free (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  const int ns = p.ns;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pad = p.n_pad;                          // keys of one head, padded to 16
@@ -105,9 +110,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmV);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&qk_full[i], 1);
       mbar_init(&v_full[i], 1);
+      mbar_init(&st_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 8);
       mbar_init(&o_full[i], 1);
@@ -124,31 +132,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, st = 0, round = 0;   // st = it % ns, round = it / ns
       for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
-        const int s = it & 1;
-        const uint32_t n = it >> 1;
         DBG(0, 2 * it);
-        if (it >= 2) mbar_wait_sleep(&o_full[s], (n - 1) & 1);  // PV of the tile two back has read P and V of this stage
+        if (round > 0) mbar_wait_sleep(&st_free[st], (round - 1) & 1);  // PV of the tile that last used this stage has retired
         DBG(0, 2 * it + 1);
         int b, h0, qb;
         decode_tile(t, p, b, h0, qb);
-        uint8_t* sQ = smem + s * kStage;
+        uint8_t* sQ = smem + st * p.stage_bytes;
         uint8_t* sK = sQ + kBytesQ;
-        uint8_t* sV = sQ + kStageQKP;
-        mbar_expect_tx(&qk_full[s], kBytesQ + n_s * 128);
+        uint8_t* sV = sQ + p.v_off;
+        mbar_expect_tx(&qk_full[st], kBytesQ + n_s * 128);
         if (!p.packed) {
-          tma_load_3d(&tmQ, &qk_full[s], sQ, h0 * kHd, qb * kQ, b);
-          tma_load_3d(&tmK, &qk_full[s], sK, h0 * kHd, 0, b);
+          tma_load_3d(&tmQ, &qk_full[st], sQ, h0 * kHd, qb * kQ, b);
+          tma_load_3d(&tmK, &qk_full[st], sK, h0 * kHd, 0, b);
         } else {
-          tma_load_3d(&tmQ, &qk_full[s], sQ, h0 * kHd, 0, b);
-          tma_load_3d(&tmQ, &qk_full[s], sQ + kBytesQ / 2, (h0 + 1) * kHd, 0, b);
-          tma_load_3d(&tmK, &qk_full[s], sK, h0 * kHd, 0, b);
-          tma_load_3d(&tmK, &qk_full[s], sK + n_pad * 128, (h0 + 1) * kHd, 0, b);
+          tma_load_3d(&tmQ, &qk_full[st], sQ, h0 * kHd, 0, b);
+          tma_load_3d(&tmQ, &qk_full[st], sQ + kBytesQ / 2, (h0 + 1) * kHd, 0, b);
+          tma_load_3d(&tmK, &qk_full[st], sK, h0 * kHd, 0, b);
+          tma_load_3d(&tmK, &qk_full[st], sK + n_pad * 128, (h0 + 1) * kHd, 0, b);
         }
-        mbar_expect_tx(&v_full[s], n_s * 128);
-        tma_load_3d(&tmV, &v_full[s], sV, h0 * kHd, 0, b);
-        if (p.packed) tma_load_3d(&tmV, &v_full[s], sV + n_pad * 128, (h0 + 1) * kHd, 0, b);
+        mbar_expect_tx(&v_full[st], n_s * 128);
+        tma_load_3d(&tmV, &v_full[st], sV, h0 * kHd, 0, b);
+        if (p.packed) tma_load_3d(&tmV, &v_full[st], sV + n_pad * 128, (h0 + 1) * kHd, 0, b);
+        if (++st == static_cast<uint32_t>(ns)) { st = 0; ++round; }
       }
     }
   } else if (warp == 1) {
@@ -160,16 +167,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t idesc_s = umma_idesc_bf16(kQ, n_s, false, false);   // Q, K both K-major (head_dim contiguous)
       const uint32_t idesc_o = umma_idesc_bf16(kQ, kHd, false, true);    // P K-major, V MN-major (head_dim contiguous)
       const int ksteps = n_s / 16;
-      auto issue_pv = [&](uint32_t j) {
-        const int s = j & 1;
-        const uint32_t n = j >> 1;
-        DBG(1, 6 * j + 3);
-        mbar_wait_sleep(&p_full[s], n & 1);
-        mbar_wait_sleep(&v_full[s], n & 1);
+      // S of tile i and PV of tile i-1 are both outstanding most of the time; the issuer takes whichever has its inputs
+      // ready instead of a fixed order (with S first, PV(i-1) sat behind the TMA load of tile i, whose stage had just been
+      // freed by PV(i-2): the whole load latency ended up between P and O of every tile).
+      uint32_t n_s_issued = 0, n_pv_issued = 0;       // tiles whose S / PV have been issued
+      uint32_t st_s = 0, rd_s = 0, st_pv = 0, rd_pv = 0;  // shared-memory stage / round of the next S and the next PV tile
+      const uint32_t my_tiles = blockIdx.x < p.tiles ? static_cast<uint32_t>((p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+      auto s_ready = [&]() {
+        const uint32_t it = n_s_issued;
+        if (!mbar_test(&qk_full[st_s], rd_s & 1)) return false;
+        return it < 2 || mbar_test(&o_free[it & 1], ((it >> 1) - 1) & 1);  // O of the tile two back has left this TMEM buffer
+      };
+      auto pv_ready = [&]() {
+        const uint32_t j = n_pv_issued;
+        return mbar_test(&p_full[j & 1], (j >> 1) & 1) && mbar_test(&v_full[st_pv], rd_pv & 1);
+      };
+      auto issue_s = [&]() {
+        const uint32_t it = n_s_issued;
+        DBG(1, 6 * it + 1);
+        tc_fence_after();
+        const uint32_t aq = smem_u32(smem + st_s * p.stage_bytes);
+        const uint64_t dq0 = umma_smem_desc(aq, 16, 1024), dk0 = umma_smem_desc(aq + kBytesQ, 16, 1024);
+#pragma unroll
+        for (int ks = 0; ks < kHd / 16; ++ks)
+          if (elect_one()) umma_bf16(tmem_base + (it & 1) * kMaxCols, dq0 + 2 * ks, dk0 + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
+        if (elect_one()) umma_commit(&s_full[it & 1]);
+        DBG(1, 6 * it + 2);
+        ++n_s_issued;
+        if (++st_s == static_cast<uint32_t>(ns)) { st_s = 0; ++rd_s; }
+      };
+      auto issue_pv = [&]() {
+        const uint32_t j = n_pv_issued;
         DBG(1, 6 * j + 4);
         tc_fence_after();
-        const uint32_t ap = smem_u32(smem + s * kStage);
-        const uint32_t av = ap + kStageQKP;
+        const uint32_t ap = smem_u32(smem + st_pv * p.stage_bytes);
+        const uint32_t av = ap + p.v_off;
         // descriptors advance by plain adds on the 14-bit (address >> 4) field: one UTCHMMA costs the issuing thread a few
         // instructions instead of a full descriptor rebuild (which made the issue loop, not the tensor pipe, the limit)
         const uint64_t da0 = umma_smem_desc(ap, 16, 1024);
@@ -177,7 +209,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // Consecutive MMAs into the SAME accumulator serialise on the accumulator's read-modify-write latency (~100 cycles,
         // three times what a 128x64x16 MMA takes to execute): the reduction over the keys is therefore spread over four
         // accumulators (k-step mod 4 -> columns 64 * j of the dead S buffer) that the epilogue adds up.
-        const uint32_t d = tmem_base + s * kMaxCols;
+        const uint32_t d = tmem_base + (j & 1) * kMaxCols;
         for (int at = 0; at * 4 < ksteps; ++at) {
           const uint64_t da = da0 + static_cast<uint64_t>(at) * (kBytesPAtom >> 4);
           const uint64_t db = db0 + static_cast<uint64_t>(at) * (4 * 16 * 128 >> 4);
@@ -187,28 +219,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (at * 4 + 2 < ksteps) { if (elect_one()) umma_bf16(d + 128, da + 4, db + 256, idesc_o, acc); }
           if (at * 4 + 3 < ksteps) { if (elect_one()) umma_bf16(d + 192, da + 6, db + 384, idesc_o, acc); }
         }
-        if (elect_one()) umma_commit(&o_full[s]);
+        if (elect_one()) umma_commit(&o_full[j & 1]);
+        if (elect_one()) umma_commit(&st_free[st_pv]);   // the stage's shared memory (P, V) is free again
         DBG(1, 6 * j + 5);
+        ++n_pv_issued;
+        if (++st_pv == static_cast<uint32_t>(ns)) { st_pv = 0; ++rd_pv; }
       };
-      uint32_t it = 0;
-      for (long long t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
-        const int s = it & 1;
-        const uint32_t n = it >> 1;
-        DBG(1, 6 * it);
-        mbar_wait_sleep(&qk_full[s], n & 1);
-        if (it >= 2) mbar_wait_sleep(&o_free[s], (n - 1) & 1);  // O of the tile two back has left this TMEM buffer
-        DBG(1, 6 * it + 1);
-        tc_fence_after();
-        const uint32_t aq = smem_u32(smem + s * kStage);
-        const uint64_t dq0 = umma_smem_desc(aq, 16, 1024), dk0 = umma_smem_desc(aq + kBytesQ, 16, 1024);
-#pragma unroll
-        for (int ks = 0; ks < kHd / 16; ++ks)
-          if (elect_one()) umma_bf16(tmem_base + s * kMaxCols, dq0 + 2 * ks, dk0 + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
-        if (elect_one()) umma_commit(&s_full[s]);
-        DBG(1, 6 * it + 2);
-        if (it >= 1) issue_pv(it - 1);
+      uint32_t spins = 0;
+      while (n_pv_issued < my_tiles) {
+        // all lanes evaluate the same barrier states (warp-uniform control flow)
+        const bool can_s = n_s_issued < my_tiles && n_s_issued < n_pv_issued + 2;   // TMEM: at most two tiles past PV
+        if (can_s && s_ready()) { issue_s(); spins = 0; continue; }
+        if (n_pv_issued < n_s_issued && pv_ready()) { issue_pv(); spins = 0; continue; }
+        if (++spins > 400000000u) {
+          if (lane == 0) printf("md: attention forward issuer stalled (block %d, S %u PV %u of %u)\n", blockIdx.x, n_s_issued, n_pv_issued, my_tiles);
+          __trap();
+        }
+        __nanosleep(20);
       }
-      if (it >= 1) issue_pv(it - 1);
     }
   } else if (warp >= 4) {
     // ================================ softmax / epilogue groups ================================
@@ -228,14 +256,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int col0 = (hi ? n_pad : 0) + my0;      // first S column of this thread
     const int chunks = (my1 - my0 + 31) / 32;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + grp * kMaxCols;
-    const uint32_t prow = smem_u32(smem + grp * kStage) + row * 128;   // this row of P (shared-window address)
+    const uint32_t prow0 = smem_u32(smem) + row * 128;   // this row of P inside stage 0 (shared-window address)
     const int sw = row & 7;
     float* xch = reinterpret_cast<float*>(smem + kOffXch) + grp * 512;   // [max | sum][half][128 rows]
     const int s = grp;
     const int nacc = min(4, n_s / 16);            // PV accumulators in use
     const uint32_t bar_id = 1 + grp;
     uint32_t n = 0;
+    uint32_t st = grp % ns;   // shared-memory stage of this group's next tile: (2 n + grp) % ns
     for (long long t = blockIdx.x + 1LL * grp * gridDim.x; t < p.tiles; t += 2LL * gridDim.x, ++n) {
+      const uint32_t prow = prow0 + st * p.stage_bytes;
+      st = (st + 2) % ns;
       int b, h0, qb;
       decode_tile(t, p, b, h0, qb);
       const int h = h0 + hi;
@@ -425,6 +456,18 @@ extern "C" int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t
   p.head_tiles = p.packed ? p.H / 2 : p.H;
   p.tiles = static_cast<long long>(B) * p.head_tiles * p.q_blocks;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
+  {  // shared-memory ring: stage = max(Q + K, P) + V for this shape's key count; as many stages (<= 3) as fit
+    const int n_s = p.packed ? 2 * p.n_pad : p.n_pad;
+    const int qk = kBytesQ + n_s * 128, pb = ((n_s + 63) / 64) * kBytesPAtom;
+    p.v_off = ((qk > pb ? qk : pb) + 1023) & ~1023;
+    p.stage_bytes = p.v_off + ((n_s * 128 + 1023) & ~1023);
+    p.ns = kOffBar / p.stage_bytes;
+    if (p.ns > kMaxStages) p.ns = kMaxStages;
+    static int ns_env = -1;   // MD_ATTN_STAGES=2 restores the two-stage ring (A/B)
+    if (ns_env < 0) { const char* e = getenv("MD_ATTN_STAGES"); ns_env = e ? atoi(e) : 0; }
+    if (ns_env >= 2 && ns_env < p.ns) p.ns = ns_env;
+    if (p.ns < 2) return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_fwd_tc: shared-memory stage too large");
+  }
   CUtensorMap tmQ, tmK, tmV;
   if (int rc = make_map(&tmQ, q, H * hd, Tq, B, ldq, p.packed ? 64 : kQ)) return rc;
   if (int rc = make_map(&tmK, k, H * hd, Tk, B, ldk, p.n_pad)) return rc;

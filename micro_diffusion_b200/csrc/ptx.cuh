@@ -65,6 +65,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Non-blocking probe of a phase (used where a role can choose between two pieces of work)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // Same contract, for waits inside hot loops: the hardware suspends the thread until the phase completes or ~`ns` elapse
 // (so the loop body runs a handful of times, not thousands), and the protocol-bug trap is a bare iteration count.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
