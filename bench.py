@@ -358,8 +358,14 @@ def main():
             gemm = {k: v for k, v in prof.items() if k.startswith("md_gemm_bf16")}
             gemm_ms = sum(v[1] for v in gemm.values())
             attn_ms = sum(v[1] for k, v in prof.items() if k.startswith("md_attn"))
+            # launches whose epilogue only stores (epi 0-3) vs the fused tails (GELU / GELU' / SwiGLU: epi 4-7), which do the
+            # work of a former element-wise pass inside the GEMM and are epilogue- rather than tensor-bound
+            plain = {k: v for k, v in gemm.items() if " epi=" in k and int(k.split(" epi=")[1].split(" ")[0]) < 4}
+            plain_ms, plain_fl = sum(v[1] for v in plain.values()), sum(v[2] for v in plain.values())
             r.update(prof=prof, tot_ms=tot_ms, gemm_ms=gemm_ms, gemm_n=sum(v[0] for v in gemm.values()), attn_ms=attn_ms,
-                     gemm_tflops=probe_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None)
+                     gemm_tflops=probe_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+                     plain_tflops=plain_fl / (plain_ms * 1e-3) / 1e12 if plain_ms > 0 else None,
+                     fused_share=(gemm_ms - plain_ms) / gemm_ms if gemm_ms > 0 else None)
         r["grad_exchange"] = None
         if reducer is not None:
             r["grad_exchange"] = (
@@ -449,6 +455,9 @@ def main():
                          # committed summary of an `ncu --set full` capture (profiles/ncu_gemm_traffic.json, written by
                          # tools/summarize_ncu_raw.py); null when no capture of the current kernel is committed
                          **read_gemm_traffic(),
+                         "achieved_store_only_launches": m.get("plain_tflops"),
+                         "frac_store_only_launches": (m["plain_tflops"] / peaks["bf16_sustained"]) if m.get("plain_tflops") else None,
+                         "fused_tail_share_of_kernel_time": m.get("fused_share"),
                          "peak_source": peaks["source"] + " sustained", "launches_per_step": gemm_n,
                          "share_of_step_kernel_time": gemm_ms / tot_ms if tot_ms else None,
                          "step_algorithmic_tflops_per_gpu": step_tflops,

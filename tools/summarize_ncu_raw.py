@@ -40,7 +40,14 @@ def main(path):
             v, u = r[idx[k]], units[idx[k]]
             try:
                 f = float(v.replace(",", ""))
-                cells.append(f"{f:.1f} {u}".strip() if u not in ("", "%") else (f"{f:.1f}" if u == "%" else f"{f:.0f}"))
+                if k == "gpu__time_duration.sum":
+                    f *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1e-3)
+                    cells.append(f"{f:.1f} us")
+                elif u.endswith("byte"):
+                    f *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6)
+                    cells.append(f"{f:.1f} MB")
+                else:
+                    cells.append(f"{f:.1f} {u}".strip() if u not in ("", "%") else (f"{f:.1f}" if u == "%" else f"{f:.0f}"))
             except ValueError:
                 cells.append(v)
         st = []
@@ -55,5 +62,22 @@ def main(path):
         print(f"| {li} | `{name}` | " + " | ".join(cells) + f" | {top} |")
 
 
+def write_traffic(path, launch, out):
+    """profiles/ncu_gemm_traffic.json for bench.py's roofline.traffic: DRAM bytes (read + write) of launch #`launch`."""
+    import json
+    rows = list(csv.reader(open(path, newline="")))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    r = data[launch]
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        tot += float(r[idx[k]].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[idx[k]]]
+    name = re.sub(r"^void ", "", r[idx["Kernel Name"]]).split("(")[0]
+    json.dump({"dram_bytes": tot, "launch": f"#{launch} {name}", "source": path}, open(out, "w"), indent=1)
+    print(f"wrote {out}: {tot / 1e6:.1f} MB for launch #{launch} {name}", file=sys.stderr)
+
+
 if __name__ == "__main__":
     main(sys.argv[1])
+    if len(sys.argv) >= 5 and sys.argv[2] == "--traffic":
+        write_traffic(sys.argv[1], int(sys.argv[3]), sys.argv[4])
