@@ -50,6 +50,11 @@ class FlatAdamW:
             o.sumsq(st.grad[a:b], self.sumsq)
         if sharded:
             dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM, group=reducer.group)
+        elif reducer is not None and reducer.world > 1:
+            # replicated form: every rank holds the same gradient, but md_sumsq adds its block partials atomically, so the
+            # norm can differ in the last bit from rank to rank -- and with it the clip factor and every updated weight.
+            # Rank 0's value is the value: replicas stay bit-identical (there is no parameter broadcast to repair drift).
+            dist.broadcast(self.sumsq, src=0, group=reducer.group)
         for a, b in segs:
             o.adamw(st.flat[a:b], st.grad[a:b], self.m[a:b], self.v[a:b], self.sumsq, float(self.clip or 0.0),
                     float(lr if lr is not None else self.lr), self.betas[0], self.betas[1], self.eps, self.wd, self.t,

@@ -331,6 +331,34 @@ def test_small_utilities():
     close(cu[0], cpu[0], "adamw p", 1e-5); close(cu[2], cpu[2], "adamw m", 1e-5); close(cu[3], cpu[3], "adamw v", 1e-5)
 
 
+def test_fused_clip_adamw_matches_torch_optim():
+    """md_sumsq + md_adamw (row f-1) against the reference's optimizer stack: GradientClipping(norm, 0.25) +
+    torch.optim.AdamW (train.py:39,86; configs/res_256_pretrain.yaml:6-8,50-57), three steps on the same gradients."""
+    if os.environ.get("MD_TEST_DRYRUN"):
+        pytest.skip("needs the CUDA kernels")
+    from micro_diffusion_b200.ops import CudaOps
+    o = CudaOps(DEV)
+    n = 300007
+    p0 = rnd((n,), 1); grads = [rnd((n,), 10 + i, scale=s_) for i, s_ in enumerate((0.02, 3e-4, 1.0))]
+    lr, betas, eps, wd, clip = 2.4e-4, (0.9, 0.999), 1e-8, 0.1, 0.25
+    ref = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.AdamW([ref], lr=lr, betas=betas, eps=eps, weight_decay=wd)
+    p = p0.clone().to(DEV); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV); ss = torch.zeros(1, device=DEV)
+    for t, g in enumerate(grads, start=1):
+        ref.grad = g.clone().double()
+        torch.nn.utils.clip_grad_norm_([ref], clip)
+        opt.step()
+        gd = g.to(DEV)
+        ss.zero_()
+        o.sumsq(gd, ss)
+        o.adamw(p, gd, m, v, ss, clip, lr, betas[0], betas[1], eps, wd, t)
+        torch.cuda.synchronize()
+        err = float((p.cpu().double() - ref.data).norm() / ref.data.norm())
+        upd = float((p.cpu().double() - p0.double()).norm())
+        uerr = float(((p.cpu().double() - p0.double()) - (ref.data - p0.double())).norm()) / max(upd, 1e-30)
+        assert err < 1e-6 and uerr < 1e-3, (t, err, uerr)   # fp32 vs float64 reference of the same update
+
+
 @pytest.mark.parametrize("layout,M,N,K,epi", [(0, 300, 640, 1024, 0), (0, 512, 768, 256, 2), (0, 256, 16, 128, 1), (0, 4096, 2048, 768, 4),
                                               (1, 768, 1024, 4000, 3), (0, 64, 1024, 16, 2), (1, 256, 16, 4096, 3)])
 def test_gemm_via_ops(layout, M, N, K, epi):
