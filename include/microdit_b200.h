@@ -287,6 +287,17 @@ MD_API int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int64_t 
  * SwiGLU GEMMs (w1 rows 0-31, w2 rows 0-31, w1 rows 32-63, ...; MD_EPI_SWIGLU). */
 MD_API int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch, int64_t rows, int64_t cols,
                              int64_t interleave_half, int prec, void* stream);
+/* The same for many matrices of one flat buffer in a single launch: desc (device memory) has one row per matrix, sorted by
+ * tile_start; matrix i lives at element `offset` of flat / wb / wbt and owns the 64 x 64 tiles
+ * [tile_start, tile_start + tiles_x * ceil(rows / 64)), tiles_x = ceil(cols / 64). */
+typedef struct md_cast_desc {
+  int64_t offset, rows, cols, half; /* half = interleave_half of md_cast_transpose */
+  int64_t need_t;                   /* 0: no transposed copy for this matrix */
+  int64_t tile_start, tiles_x;
+  int64_t reserved;
+} md_cast_desc;
+MD_API int md_cast_transpose_multi(const float* flat, void* wb, void* wbt, const md_cast_desc* desc, int64_t n_desc,
+                                   int64_t total_tiles, int prec, void* stream);
 /* sumsq(f32 [1]) += sum x^2  (gradient-norm clipping, train.py:85-86) */
 MD_API int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream);
 /* fused (clip-scaled) AdamW on flat fp32 buffers (train.py:39, configs/res_256_pretrain.yaml:50-57):

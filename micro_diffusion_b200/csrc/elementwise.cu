@@ -171,9 +171,9 @@ __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long 
 // 64x64 tiles, 256 threads: 16-byte fp32 loads, 8-byte bf16 stores in both orientations (the transposed one through
 // a padded smem tile).  HBM-bound: 4 B read + 2 x 2 B written per element.
 template <typename AT>
-__global__ void __launch_bounds__(256)
-cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __restrict__ wbt, long long rows,
-                      long long cols, long long half) {
+__device__ __forceinline__ void cast_transpose_tile(const float* __restrict__ wsrc, AT* __restrict__ wb_, AT* __restrict__ wbt_,
+                                                    long long rows, long long cols, long long half, long long c0,
+                                                    long long r0, float (&tile)[64][65]) {
   // half > 0 (rows == 2 * half, half % 32 == 0): the copies hold the rows in the 32-interleaved order of the fused SwiGLU
   // GEMMs -- input row r (< half: w1, else w2) becomes row 64 * (r' / 32) + (w2 ? 32 : 0) + r' % 32, r' = r mod half
   auto prow = [&](long long r) -> long long {
@@ -181,10 +181,6 @@ cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __re
     const long long rr = r < half ? r : r - half;
     return 64 * (rr >> 5) + (r < half ? 0 : 32) + (rr & 31);
   };
-  __shared__ float tile[64][65];
-  const long long bz = blockIdx.z;
-  const float* wsrc = w + bz * rows * cols;
-  const long long c0 = 1LL * blockIdx.x * 64, r0 = 1LL * blockIdx.y * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 columns each, 4 row passes
   const bool vec = ((cols & 3) == 0) && ((rows & 3) == 0);
 #pragma unroll
@@ -195,12 +191,12 @@ cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __re
       if (vec && c + 3 < cols) {
         const float4 f = *reinterpret_cast<const float4*>(wsrc + r * cols + c);
         v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-        if (wb) st4a(wb + bz * rows * cols + prow(r) * cols + c, f);
+        if (wb_) st4a(wb_ + prow(r) * cols + c, f);
       } else {
         for (int e = 0; e < 4; ++e)
           if (c + e < cols) {
             v[e] = wsrc[r * cols + c + e];
-            if (wb) st1a(wb + bz * rows * cols + prow(r) * cols + c + e, v[e]);
+            if (wb_) st1a(wb_ + prow(r) * cols + c + e, v[e]);
           }
       }
     }
@@ -208,7 +204,7 @@ cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __re
     for (int e = 0; e < 4; ++e) tile[ty + 16 * pass][4 * tx + e] = v[e];
   }
   __syncthreads();
-  if (wbt == nullptr) return;
+  if (wbt_ == nullptr) return;
 #pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
     const long long c = c0 + ty + 16 * pass;  // output row = original column
@@ -217,7 +213,7 @@ cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __re
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[e] = tile[4 * tx + e][ty + 16 * pass];
-    AT* dst = wbt + bz * rows * cols + c * rows;
+    AT* dst = wbt_ + c * rows;
     if (vec && r + 3 < rows) {   // r % 4 == 0: the four rows stay adjacent under the 32-row interleave
       st4a(dst + prow(r), make_float4(v[0], v[1], v[2], v[3]));
     } else {
@@ -225,6 +221,38 @@ cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __re
         if (r + e < rows) st1a(dst + prow(r + e), v[e]);
     }
   }
+}
+
+template <typename AT>
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ w, AT* __restrict__ wb, AT* __restrict__ wbt, long long rows,
+                      long long cols, long long half) {
+  __shared__ float tile[64][65];
+  const long long o = 1LL * blockIdx.z * rows * cols;
+  cast_transpose_tile<AT>(w + o, wb ? wb + o : nullptr, wbt ? wbt + o : nullptr, rows, cols, half, 1LL * blockIdx.x * 64,
+                          1LL * blockIdx.y * 64, tile);
+}
+
+// All weight matrices of a range in ONE launch: a table of (offset, shape, first tile) rows, one per matrix, and a
+// binary search from the block index to its matrix.  Per optimizer step the bf16 copies were 222 launches of mostly
+// tiny matrices -- 3.7 ms of a 125 ms rank step at 8 GPUs.
+template <typename AT>
+__global__ void __launch_bounds__(256)
+cast_transpose_multi_kernel(const float* __restrict__ flat, AT* __restrict__ wb, AT* __restrict__ wbt,
+                            const md_cast_desc* __restrict__ desc, int n_desc) {
+  __shared__ float tile[64][65];
+  int lo = 0, hi = n_desc - 1;
+  const long long id = blockIdx.x;
+  while (lo < hi) {  // last descriptor whose tile_start <= id
+    const int mid = (lo + hi + 1) >> 1;
+    if (desc[mid].tile_start <= id) lo = mid;
+    else hi = mid - 1;
+  }
+  const md_cast_desc d = desc[lo];
+  const long long local = id - d.tile_start;
+  const long long bx = local % d.tiles_x, by = local / d.tiles_x;
+  cast_transpose_tile<AT>(flat + d.offset, wb + d.offset, d.need_t ? wbt + d.offset : nullptr, d.rows, d.cols, d.half,
+                          bx * 64, by * 64, tile);
 }
 
 // -------------------------------------------------------------------------------- timestep / cond
@@ -419,6 +447,14 @@ extern "C" int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t ba
   dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64), (unsigned)batch);
   MD_WITH_ACT(prec, cast_transpose_kernel<AT><<<grid, 256, 0, ST(stream)>>>(w, AP(AT, wb), AP(AT, wbt), rows, cols, interleave_half));
   return check_launch("md_cast_transpose");
+}
+extern "C" int md_cast_transpose_multi(const float* flat, void* wb, void* wbt, const md_cast_desc* desc, int64_t n_desc,
+                                       int64_t total_tiles, int prec, void* stream) {
+  if (n_desc == 0 || total_tiles == 0) return 0;
+  if (!flat || !wb || !wbt || !desc) return md_set_error(MD_ERR_INVALID, "md_cast_transpose_multi: null pointer");
+  MD_WITH_ACT(prec, cast_transpose_multi_kernel<AT><<<(unsigned)total_tiles, 256, 0, ST(stream)>>>(flat, AP(AT, wb), AP(AT, wbt), desc,
+                                                                                               (int)n_desc));
+  return check_launch("md_cast_transpose_multi");
 }
 extern "C" int md_timestep_embed(const float* t, void* out, int64_t B, int64_t dim, int prec, void* stream) {
   if (B == 0) return 0;

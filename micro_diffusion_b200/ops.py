@@ -72,11 +72,12 @@ _PROTOS = {
     "md_cast_f32_bf16": [_P, _P, _I64, _I, _P],
     "md_colsum": [_P, _I, _I64, _P, _I64, _I64, _P],
     "md_cast_transpose": [_P, _P, _P, _I64, _I64, _I64, _I64, _I, _P],
+    "md_cast_transpose_multi": [_P, _P, _P, _P, _I64, _I64, _I, _P],
     "md_sumsq": [_P, _P, _I64, _P],
     "md_adamw": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I64, _P, _I64, _P],
 }
 
-_TAKES_PREC = frozenset(['md_ln_fwd', 'md_ln_bwd', 'md_rownorm_fwd', 'md_rownorm_bwd', 'md_gate_bwd', 'md_swiglu_fwd', 'md_swiglu_bwd', 'md_act_fwd', 'md_act_bwd', 'md_gelu_tanh_f32_fwd', 'md_moe_gate_fwd', 'md_moe_gather', 'md_moe_combine_fwd', 'md_moe_combine_bwd', 'md_moe_dx_bwd', 'md_moe_gate_wgrad', 'md_cond_prepare', 'md_edm_prepare', 'md_patchify', 'md_timestep_embed', 'md_edm_loss_bwd', 'md_mean_tokens_fwd', 'md_cast_f32_bf16', 'md_cast_transpose'])
+_TAKES_PREC = frozenset(['md_ln_fwd', 'md_ln_bwd', 'md_rownorm_fwd', 'md_rownorm_bwd', 'md_gate_bwd', 'md_swiglu_fwd', 'md_swiglu_bwd', 'md_act_fwd', 'md_act_bwd', 'md_gelu_tanh_f32_fwd', 'md_moe_gate_fwd', 'md_moe_gather', 'md_moe_combine_fwd', 'md_moe_combine_bwd', 'md_moe_dx_bwd', 'md_moe_gate_wgrad', 'md_cond_prepare', 'md_edm_prepare', 'md_patchify', 'md_timestep_embed', 'md_edm_loss_bwd', 'md_mean_tokens_fwd', 'md_cast_f32_bf16', 'md_cast_transpose', 'md_cast_transpose_multi'])
 
 EXPORTED_SYMBOLS = ["md_last_error", "md_abi_version", "md_gemm_bf16", "md_attn_debug_dump", *_PROTOS.keys()]
 
@@ -451,6 +452,12 @@ class CudaOps:
         else:
             batch, rows, cols = w.shape
         self._call("md_cast_transpose", w.data_ptr(), _ptr(wb), _ptr(wbt), batch, rows, cols, interleave_half)
+
+    def cast_transpose_multi(self, flat, wb, wbt, desc, total_tiles):
+        """desc: int64 [n, 8] device tensor of md_cast_desc rows (offset, rows, cols, half, need_t, tile_start, tiles_x, 0)."""
+        assert desc.dtype == torch.int64 and desc.dim() == 2 and desc.shape[1] == 8 and desc.is_contiguous()
+        self._call("md_cast_transpose_multi", flat.data_ptr(), wb.data_ptr(), wbt.data_ptr(), desc.data_ptr(), desc.shape[0],
+                   total_tiles)
 
     def sumsq(self, x, out):
         self._call("md_sumsq", x.data_ptr(), out.data_ptr(), x.numel())

@@ -162,6 +162,7 @@ class ParamStore:
             for g in layout.groups.values():
                 if g.name.endswith(".w12") and g.batch == 1 and (g.rows // 2) % 32 == 0 and g.cols % 16 == 0:
                     self.interleave[g.name] = g.rows // 2
+        self._cast_tables: Dict[str, object] = {}
         self._copies_version: Dict[str, object] = {}
         self.param_ready: Dict[str, object] = {}  # part -> CUDA event of a pending parameter all-gather
         self.p: Dict[str, torch.Tensor] = {}  # fp32 views (reference shapes)
@@ -199,6 +200,25 @@ class ParamStore:
         lay = self.layout
         return offset >= lay.back_start or (lay.kv_back is not None and lay.kv_back[0] <= offset < lay.kv_back[1])
 
+    def _cast_table(self, part: str):
+        """md_cast_desc rows (one per matrix; expert banks contribute one row per expert) of the groups of `part`, on the
+        device, built once: the bf16 copies of a whole exchange range are one launch."""
+        hit = self._cast_tables.get(part)
+        if hit is not None:
+            return hit
+        rows, t = [], 0
+        for g in self.layout.groups.values():
+            if self.is_back(g.offset) != (part == "back"):
+                continue
+            tx, ty = (g.cols + 63) // 64, (g.rows + 63) // 64
+            for b in range(g.batch):
+                rows.append([g.offset + b * g.rows * g.cols, g.rows, g.cols, self.interleave.get(g.name, 0), int(g.need_t),
+                             t, tx, 0])
+                t += tx * ty
+        desc = torch.tensor(rows, dtype=torch.int64, device=self.device).reshape(-1, 8).contiguous()
+        self._cast_tables[part] = (desc, t)
+        return desc, t
+
     def refresh_copies(self, ops, token=None, force=False, part=None) -> bool:
         """Re-derive the bf16 operand copies if the master weights changed since the last call.
         `token` is any value that changes whenever a parameter is written (models/dit.py sums the
@@ -215,13 +235,8 @@ class ParamStore:
                 torch.cuda.current_stream(self.device).wait_event(ev)
             if not force and self._copies_version.get(pt) == v:
                 continue
-            for g in self.layout.groups.values():
-                if self.is_back(g.offset) != (pt == "back"):
-                    continue
-                src = self.flat[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
-                wb = self.wb[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
-                wbt = self.wbt[g.offset: g.offset + g.numel].view(g.batch, g.cols, g.rows) if g.need_t else None
-                ops.cast_transpose(src, wb, wbt, interleave_half=self.interleave.get(g.name, 0))
+            desc, tiles = self._cast_table(pt)
+            ops.cast_transpose_multi(self.flat, self.wb, self.wbt, desc, tiles)
             self._copies_version[pt] = v
             done = True
         return done

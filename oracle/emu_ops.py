@@ -539,6 +539,17 @@ class EmuOps:
         if wbt is not None:
             wbt.copy_(w.transpose(-1, -2))
 
+    def cast_transpose_multi(self, flat, wb, wbt, desc, total_tiles):
+        self.launches += 1
+        for off, rows, cols, half, need_t, _, _, _ in desc.tolist():
+            n = rows * cols
+            w = flat[off:off + n].view(rows, cols)
+            if half:
+                w = w.index_select(0, interleave_perm(half))
+            wb[off:off + n].view(rows, cols).copy_(w)
+            if need_t:
+                wbt[off:off + n].view(cols, rows).copy_(w.t())
+
     def sumsq(self, x, out):
         self.launches += 1
         out.add_((x.double() ** 2).sum().float())

@@ -331,6 +331,28 @@ def test_small_utilities():
     close(cu[0], cpu[0], "adamw p", 1e-5); close(cu[2], cpu[2], "adamw m", 1e-5); close(cu[3], cpu[3], "adamw v", 1e-5)
 
 
+def test_cast_transpose_multi():
+    """All bf16 operand copies of a parameter range in one launch (descriptor table) == the per-matrix kernel."""
+    shapes = [(130, 70, 0, 1), (64, 64, 0, 1), (256, 48, 128, 1), (33, 200, 0, 0), (8, 8, 0, 1), (192, 64, 96, 1)]
+    rows_, off, t = [], 0, 0
+    for (r, c, half, need_t) in shapes:
+        rows_.append([off, r, c, half, need_t, t, (c + 63) // 64, 0])
+        t += ((c + 63) // 64) * ((r + 63) // 64)
+        off += (r * c + 7) // 8 * 8
+    flat = rnd((off,), 1); wb = torch.full((off,), 3.0, dtype=BF16); wbt = torch.full((off,), 5.0, dtype=BF16)
+    desc = torch.tensor(rows_, dtype=torch.int64)
+    cpu, cu = both(lambda o, flat, wb, wbt, desc: o.cast_transpose_multi(flat, wb, wbt, desc, t), [flat, wb, wbt, desc])
+    assert torch.equal(cu[1].cpu(), cpu[1]) and torch.equal(cu[2].cpu(), cpu[2])
+    # and against the single-matrix entry point
+    for (o_, r, c, half, need_t, _, _, _) in rows_:
+        w = flat[o_:o_ + r * c].view(r, c)
+        a = torch.zeros(r, c, dtype=BF16); b = torch.zeros(c, r, dtype=BF16)
+        cpu1, _ = both(lambda o, w, a, b: o.cast_transpose(w, a, b, interleave_half=half), [w, a, b])
+        assert torch.equal(cpu[1][o_:o_ + r * c].view(r, c), cpu1[1])
+        if need_t:
+            assert torch.equal(cpu[2][o_:o_ + r * c].view(c, r), cpu1[2])
+
+
 def test_fused_clip_adamw_matches_torch_optim():
     """md_sumsq + md_adamw (row f-1) against the reference's optimizer stack: GradientClipping(norm, 0.25) +
     torch.optim.AdamW (train.py:39,86; configs/res_256_pretrain.yaml:6-8,50-57), three steps on the same gradients."""
