@@ -155,7 +155,8 @@ MD_API int md_attn_bwd_mma(const void* dout, int64_t lddo, const void* q, int64_
                            void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int64_t B, int64_t H,
                            int64_t Tq, int64_t Tk, int64_t hd, void* stream);
 /* The same forward and backward on the 5th-generation tensor cores (tcgen05.mma, accumulators and S / dP tiles in
- * TMEM, operands by TMA; csrc/attn_tc.cu) for head_dim 64 and Tk <= 256 -- every sequence of the res-256 configs.
+ * TMEM, operands by TMA; csrc/attn_tc.cu) for head_dim 64; forward: Tk <= 256 (all keys of a head in one S tile) -- every
+ * sequence of the res-256 configs; backward: any Tk <= 4096 (resident key blocks of 128).
  * Persistent, warp-specialised kernels; no delta scratch (derived from o and dout).  md_attn_fwd / md_attn_bwd
  * dispatch here whenever the shape is inside this envelope. */
 MD_API int md_attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,

@@ -854,7 +854,7 @@ static bool use_tc_fwd(int64_t Tq, int64_t Tk, int64_t hd, uintptr_t align, int6
   return MD_ATTN_TC_FWD_AUTO(Tq, Tk);
 }
 static bool use_tc_bwd(int64_t Tq, int64_t Tk, int64_t hd, uintptr_t align, int64_t lds) {
-  if (hd != 64 || Tk > 256 || (align & 15) != 0 || (lds % 8) != 0) return false;
+  if (hd != 64 || Tk > 4096 || (align & 15) != 0 || (lds % 8) != 0) return false;  // key blocks of 128: no 256-key limit
   const int m = attn_tc_policy();
   if (m >= 0) return m != 0;
   return MD_ATTN_TC_BWD_AUTO(Tq, Tk);

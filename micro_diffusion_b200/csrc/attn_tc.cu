@@ -517,6 +517,7 @@ constexpr int kBwdOffStats = kBwdOffBar + 256;          // 2 x 128 x (lse, delta
 constexpr int kBwdOffOld = kBwdOffStats + 2048;         // 256 threads x 64 B: dQ partial of the previous key block
 constexpr int kBwdSmemBytes = kBwdOffOld + 16384 + 1024;
 constexpr int kTile = 16 * 1024;
+constexpr int kBwdMaxKeys = 4096;
 // TMEM columns
 constexpr uint32_t kColS = 0, kColdP = 64, kColBuf = 128, kColdQ = 256, kColdK = 320, kColdV = 384;
 
@@ -1037,8 +1038,9 @@ extern "C" int md_attn_bwd_tc(const void* dout, int64_t lddo, const void* q, int
   using namespace md;
   using namespace md::attn_tc;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0) return B == 0 ? 0 : md_set_error(MD_ERR_INVALID, "md_attn_bwd_tc: bad sizes");
-  if (hd != kHd || Tk > kMaxCols)
-    return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_bwd_tc: needs head_dim 64 and Tk <= 256");
+  // the backward walks the keys in resident blocks of 128 (dQ partials summed across blocks), so it has no 256-key limit
+  if (hd != kHd || Tk > kBwdMaxKeys)
+    return md_set_error(MD_ERR_UNSUPPORTED, "md_attn_bwd_tc: needs head_dim 64 and Tk <= 4096");
   if (!dout || !q || !k || !v || !o || !lse || !dq || !dk || !dv)
     return md_set_error(MD_ERR_INVALID, "md_attn_bwd_tc: null pointer");
   const uintptr_t align = reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |

@@ -320,7 +320,7 @@ class CudaOps:
                        delta.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(),
                        dv.stride(0), B, H, Tq, Tk, hd, label=f"B={B} H={H} Tq={Tq} Tk={Tk}")
             return
-        if self.attn_tc and hd == 64 and Tk <= 256:  # tcgen05 backward
+        if self.attn_tc and hd == 64 and Tk <= 4096:  # tcgen05 backward (key blocks of 128: no 256-key limit)
             self._call("md_attn_bwd_tc", dout.data_ptr(), dout.stride(0), q.data_ptr(), q.stride(0), k.data_ptr(),
                        k.stride(0), v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(),
                        dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0),
