@@ -43,6 +43,14 @@ extern "C" {
 
 MD_API const char* md_last_error(void);
 MD_API int md_abi_version(void);
+/* Deterministic mode.  The fast path accumulates some gradients with floating-point atomics across thread blocks (split-K
+ * weight gradients, the per-column reductions of the LayerNorm / gate / router / bias gradients, the gradient norm), so
+ * two runs differ in the last bits.  With a workspace registered here those accumulations go through per-block partial
+ * sums in the workspace and a fixed-order reduction: the same inputs give bit-identical outputs (what the reference gets
+ * from cuBLAS + torch's deterministic reductions).  The workspace (device memory, >= 1 MiB, 256-byte aligned, owned by
+ * the caller; 1 GiB covers MicroDiT_XL_2 at microbatch 512) is reused by consecutive launches: issue all calls on one
+ * stream.  NULL turns the mode off.  Requests that do not fit fall back to an unsplit (slower, still deterministic) form. */
+MD_API int md_set_deterministic(void* workspace, int64_t bytes);
 
 /* ------------------------------------------------------------------------------------------ GEMM */
 #define MD_GEMM_NT 0 /* C[M,N] = A[M,K] . B[N,K]^T   (A, B row-major, K contiguous)                 */

@@ -9,6 +9,11 @@
 
 namespace md {
 int md_set_error(int code, const char* msg);  // records msg for md_last_error(); returns code
+// deterministic mode (capi_core.cu): scratch for per-block partials (nullptr: mode off / request too large) and the
+// fixed-order reduction out[i * out_stride] += sum_p ws[p * n + i]
+bool det_enabled();
+float* det_workspace(size_t need_bytes);
+int det_reduce(const float* ws, float* out, long long parts, long long n, long long out_stride, cudaStream_t stream);
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

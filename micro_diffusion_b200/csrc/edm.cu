@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256)
 edm_loss_kernel(const float* __restrict__ ftok, const int32_t* __restrict__ keep_tok, const void* __restrict__ lat,
                 int lat_f16, const float* __restrict__ xn, const float* __restrict__ coef,
                 float* __restrict__ per_sample, float* __restrict__ loss, const float* __restrict__ gscale,
-                AT* __restrict__ dftok, int B, int C, int H, int W, int p, int Tk) {
+                AT* __restrict__ dftok, int B, int C, int H, int W, int p, int Tk, float* __restrict__ det_ws) {
   const int b = blockIdx.x;
   const int gw = W / p;
   const int T = gw * (H / p);
@@ -116,7 +116,8 @@ edm_loss_kernel(const float* __restrict__ ftok, const int32_t* __restrict__ keep
     for (int w = 0; w < (blockDim.x >> 5); ++w) s += part[w];
     s = s * inv / Tk;
     per_sample[b] = s;
-    atomicAdd(loss, s / B);
+    if (det_ws != nullptr) det_ws[b] = s / B;   // deterministic mode: summed over samples in a fixed order afterwards
+    else atomicAdd(loss, s / B);
   }
 }
 
@@ -243,10 +244,12 @@ extern "C" int md_edm_loss_fwd(const float* ftok, const int32_t* keep_tok, const
   if (B == 0) return 0;
   if (!ftok || !lat || !xn || !coef || !per_sample || !loss)
     return md_set_error(MD_ERR_INVALID, "md_edm_loss_fwd: null pointer");
+  float* ws = det_enabled() ? det_workspace(static_cast<size_t>(B) * sizeof(float)) : nullptr;
   edm_loss_kernel<false, float><<<(unsigned)B, 256, 0, ST(stream)>>>(ftok, keep_tok, lat, lat_f16, xn, coef, per_sample,
                                                                      loss, nullptr, nullptr, (int)B, (int)C, (int)H,
-                                                                     (int)W, (int)p, (int)Tk);
-  return check_launch("md_edm_loss_fwd");
+                                                                     (int)W, (int)p, (int)Tk, ws);
+  if (int rc = check_launch("md_edm_loss_fwd")) return rc;
+  return ws ? det_reduce(ws, loss, B, 1, 1, ST(stream)) : 0;
 }
 
 extern "C" int md_edm_loss_bwd(const float* ftok, const int32_t* keep_tok, const void* lat, int lat_f16,
@@ -257,7 +260,7 @@ extern "C" int md_edm_loss_bwd(const float* ftok, const int32_t* keep_tok, const
     return md_set_error(MD_ERR_INVALID, "md_edm_loss_bwd: null pointer");
   MD_WITH_ACT(prec, edm_loss_kernel<true, AT><<<(unsigned)B, 256, 0, ST(stream)>>>(
                         ftok, keep_tok, lat, lat_f16, xn, coef, nullptr, nullptr, gscale, AP(AT, dftok), (int)B, (int)C,
-                        (int)H, (int)W, (int)p, (int)Tk));
+                        (int)H, (int)W, (int)p, (int)Tk, nullptr));
   return check_launch("md_edm_loss_bwd");
 }
 

@@ -152,7 +152,7 @@ __global__ void copy_f32_kernel(const float* __restrict__ x, float* __restrict__
 // ------------------------------------------------------------------------------------------ colsum
 // grid (ceil(N/256), ceil(rows/256)): each thread owns one column of a 256-row slab.
 __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, float* __restrict__ out,
-                              long long rows, long long N) {
+                              long long rows, long long N, float* __restrict__ ws) {
   const long long c = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
   const long long r0 = 1LL * blockIdx.y * 256, r1 = min(rows, r0 + 256);
@@ -164,7 +164,8 @@ __global__ void colsum_kernel(const void* __restrict__ x, int x_bf16, long long 
     const float* p = reinterpret_cast<const float*>(x);
     for (long long r = r0; r < r1; ++r) s += p[r * ld + c];
   }
-  atomicAdd(out + c, s);
+  if (ws != nullptr) ws[1LL * blockIdx.y * N + c] = s;   // deterministic mode: slab partials, fixed-order reduction afterwards
+  else atomicAdd(out + c, s);
 }
 
 // ---------------------------------------------------------------------------------- cast_transpose
@@ -297,7 +298,7 @@ __global__ void cond_prepare_kernel(const __half* cap, const double* __restrict_
 }
 
 // ----------------------------------------------------------------------------------- sumsq / AdamW
-__global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+__global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, float* __restrict__ ws) {
   float s = 0.f;
   const long long nv = n >> 2;
   for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += 1LL * gridDim.x * blockDim.x) {
@@ -315,7 +316,10 @@ __global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ ou
   if (threadIdx.x < 32) {
     float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+    if (threadIdx.x == 0) {
+      if (ws != nullptr) ws[blockIdx.x] = v;   // deterministic mode
+      else atomicAdd(out, v);
+    }
   }
 }
 
@@ -435,8 +439,14 @@ extern "C" int md_colsum(const void* x, int x_bf16, int64_t ld, float* out, int6
   if (rows == 0 || N == 0) return 0;
   if (!x || !out) return md_set_error(MD_ERR_INVALID, "md_colsum: null pointer");
   dim3 grid((unsigned)((N + 255) / 256), (unsigned)((rows + 255) / 256));
-  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(x, x_bf16, ld, out, rows, N);
-  return check_launch("md_colsum");
+  float* ws = nullptr;
+  if (det_enabled()) {
+    ws = det_workspace(static_cast<size_t>(grid.y) * N * sizeof(float));
+    if (ws == nullptr) return md_set_error(MD_ERR_INVALID, "md_colsum: deterministic workspace too small");
+  }
+  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(x, x_bf16, ld, out, rows, N, ws);
+  if (int rc = check_launch("md_colsum")) return rc;
+  return ws ? det_reduce(ws, out, grid.y, N, 1, ST(stream)) : 0;
 }
 extern "C" int md_cast_transpose(const float* w, void* wb, void* wbt, int64_t batch, int64_t rows, int64_t cols,
                                  int64_t interleave_half, int prec, void* stream) {
@@ -476,8 +486,11 @@ extern "C" int md_cond_prepare(const void* cap_f16, const double* keep, void* ou
 extern "C" int md_sumsq(const float* x, float* sumsq, int64_t n, void* stream) {
   if (n == 0) return 0;
   if (!x || !sumsq) return md_set_error(MD_ERR_INVALID, "md_sumsq: null pointer");
-  sumsq_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, ST(stream)>>>(x, sumsq, n);
-  return check_launch("md_sumsq");
+  const int grid = grid_for(n / 4 + 1, 256);
+  float* ws = det_enabled() ? det_workspace(static_cast<size_t>(grid) * sizeof(float)) : nullptr;
+  sumsq_kernel<<<grid, 256, 0, ST(stream)>>>(x, sumsq, n, ws);
+  if (int rc = check_launch("md_sumsq")) return rc;
+  return ws ? det_reduce(ws, sumsq, grid, 1, 1, ST(stream)) : 0;
 }
 extern "C" int md_adamw(float* p, const float* g, float* m, float* v, const float* sumsq, float clip, float lr,
                         float beta1, float beta2, float eps, float wd, int64_t step, int32_t* nonfinite, int64_t n,

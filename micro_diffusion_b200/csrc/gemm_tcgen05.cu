@@ -683,6 +683,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ++store_it;
             }
           }
+        } else if (!kMath && p.split_ws != nullptr) {
+          // deterministic split-K: this split's partial tile goes to the workspace [split][batch][M][N] with plain stores
+          // (zeros for an empty split); splitk_reduce_kernel adds the splits up in a fixed order
+          if (row_ok && col0 < p.N) {
+            float* dst = p.split_ws + ((1LL * sp * p.batch + bz) * p.M + row) * p.N + col0;
+            const int ncols = min(32, p.N - col0);
+            if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = has_k ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) dst[j] = has_k ? v[j] : 0.f;
+            }
+          }
         } else
         // No divergent `continue`: every lane must reach the next (warp-aligned) tcgen05 instruction together.
         if (row_ok && col0 < p.N && has_k) {
@@ -814,6 +830,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     if constexpr (kCtas == 2) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
     else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// C[b][rowmap(m)][n] += sum_sp ws[sp][b][m][n], sp = 0, 1, ... (deterministic split-K, second pass)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int splits, int batch, int M, int N,
+                     long long ldc, long long strideC, int row_interleave) {
+  const long long total = 1LL * batch * M * N;
+  for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int n = static_cast<int>(i % N);
+    const long long bm = i / N;
+    const int m = static_cast<int>(bm % M);
+    const int b = static_cast<int>(bm / M);
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += ws[1LL * sp * total + i];
+    int row = m;
+    if (row_interleave > 0) {
+      const int blk = m >> 6, in = m & 63;
+      row = (in < 32 ? 0 : row_interleave) + 32 * blk + (in & 31);
+    }
+    C[1LL * b * strideC + 1LL * row * ldc + n] += s;
   }
 }
 
@@ -997,6 +1034,7 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   dev.ldc2 = a->ldc2 > 0 ? a->ldc2 : a->N / 2;
   dev.strideC2 = a->strideC2;
   dev.row_interleave = static_cast<int>(a->row_interleave);
+  dev.split_ws = nullptr;
   dev.M = static_cast<int>(a->M); dev.N = static_cast<int>(a->N); dev.K = static_cast<int>(a->K);
   dev.batch = static_cast<int>(a->batch); dev.splits = splits;
   dev.ldc = a->ldc; dev.strideC = a->strideC; dev.strideBias = a->strideBias;
@@ -1042,14 +1080,31 @@ extern "C" int md_gemm_bf16(const md_gemm_args* a, void* stream_) {
   const bool swiglu = a->epilogue == EPI_SWIGLU || a->epilogue == EPI_SWIGLU_GRAD;  // only the 8-warp kernels carry them
   const bool math_tail = swiglu || a->epilogue == EPI_ACT_DUAL || a->epilogue == EPI_ACT_GRAD;
   if (math_tail && mn) return md_set_error(MD_ERR_UNSUPPORTED, "md_gemm_bf16: the activation / SwiGLU epilogues need the NT layout");
-  if (pair) {
-    if (mn) return use256 ? launch<256, true, 2>(a, dev, sm_count, stream) : launch<128, true, 2>(a, dev, sm_count, stream);
-    if (math_tail)
-      return use256 ? launch<256, false, 2, 8>(a, dev, sm_count, stream) : launch<128, false, 2, 8>(a, dev, sm_count, stream);
-    return use256 ? launch<256, false, 2>(a, dev, sm_count, stream) : launch<128, false, 2>(a, dev, sm_count, stream);
+  // deterministic mode: a split reduction goes through per-split partial tiles in the workspace and a fixed-order second
+  // pass; if the workspace cannot hold them the reduction is not split (one writer per element: deterministic, slower)
+  if (det_enabled() && a->epilogue == EPI_ATOMIC_F32 && dev.splits > 1) {
+    dev.split_ws = det_workspace(sizeof(float) * static_cast<size_t>(dev.splits) * a->batch * a->M * a->N);
+    if (dev.split_ws == nullptr) dev.splits = 1;
   }
-  if (mn) return use256 ? launch<256, true, 1>(a, dev, sm_count, stream) : launch<128, true, 1>(a, dev, sm_count, stream);
-  if (math_tail)
-    return use256 ? launch<256, false, 1, 8>(a, dev, sm_count, stream) : launch<128, false, 1, 8>(a, dev, sm_count, stream);
-  return use256 ? launch<256, false, 1>(a, dev, sm_count, stream) : launch<128, false, 1>(a, dev, sm_count, stream);
+  auto run = [&]() -> int {
+    if (pair) {
+      if (mn) return use256 ? launch<256, true, 2>(a, dev, sm_count, stream) : launch<128, true, 2>(a, dev, sm_count, stream);
+      if (math_tail)
+        return use256 ? launch<256, false, 2, 8>(a, dev, sm_count, stream) : launch<128, false, 2, 8>(a, dev, sm_count, stream);
+      return use256 ? launch<256, false, 2>(a, dev, sm_count, stream) : launch<128, false, 2>(a, dev, sm_count, stream);
+    }
+    if (mn) return use256 ? launch<256, true, 1>(a, dev, sm_count, stream) : launch<128, true, 1>(a, dev, sm_count, stream);
+    if (math_tail)
+      return use256 ? launch<256, false, 1, 8>(a, dev, sm_count, stream) : launch<128, false, 1, 8>(a, dev, sm_count, stream);
+    return use256 ? launch<256, false, 1>(a, dev, sm_count, stream) : launch<128, false, 1>(a, dev, sm_count, stream);
+  };
+  if (int rc = run()) return rc;
+  if (dev.split_ws != nullptr) {
+    const long long total = 1LL * a->batch * a->M * a->N;
+    const int blocks = static_cast<int>(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(dev.split_ws, reinterpret_cast<float*>(a->C), dev.splits, dev.batch, dev.M,
+                                                     dev.N, dev.ldc, dev.strideC, dev.row_interleave);
+    return check_launch("md_gemm_bf16 (deterministic split-K reduction)");
+  }
+  return 0;
 }

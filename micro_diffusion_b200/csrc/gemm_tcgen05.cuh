@@ -21,6 +21,7 @@ struct GemmDev {
   const float* res;
   const float* gate;
   const void* aux;
+  float* split_ws;  // deterministic split-K: partial tiles [split][batch][M][N] instead of atomics
   long long ldc, strideC, strideBias, ldgate, ldc2, strideC2;
   int M, N, K, batch, splits, rows_per_gate, epi, res_mod, act;
   int row_interleave;  // > 0: output row p of the atomic epilogue goes to the parameter row of the 32-row-interleaved stack

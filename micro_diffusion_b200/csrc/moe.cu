@@ -351,7 +351,7 @@ constexpr int kWgSlab = 64;
 template <int ME, int NJ, typename AT>
 __global__ void __launch_bounds__(256)
 moe_gate_wgrad_kernel(const float* __restrict__ dscores, const AT* __restrict__ x, float* __restrict__ dwg,
-                      long long rows, int D, int E) {
+                      long long rows, int D, int E, float* __restrict__ ws) {
   __shared__ __align__(16) float sds[kWgSlab * ME];
   const int c0 = 2 * threadIdx.x;
   float acc[NJ][2][ME];
@@ -406,8 +406,13 @@ moe_gate_wgrad_kernel(const float* __restrict__ dscores, const AT* __restrict__ 
 #pragma unroll
       for (int e = 0; e < ME; ++e)
         if (e < E) {
-          atomicAdd(dwg + e * D + c, acc[j][0][e]);
-          atomicAdd(dwg + e * D + c + 1, acc[j][1][e]);
+          if (ws != nullptr) {  // deterministic mode: this block's partial, reduced over blocks in a fixed order afterwards
+            ws[(1LL * blockIdx.x * E + e) * D + c] = acc[j][0][e];
+            ws[(1LL * blockIdx.x * E + e) * D + c + 1] = acc[j][1][e];
+          } else {
+            atomicAdd(dwg + e * D + c, acc[j][0][e]);
+            atomicAdd(dwg + e * D + c + 1, acc[j][1][e]);
+          }
         }
     }
   }
@@ -551,8 +556,13 @@ extern "C" int md_moe_gate_wgrad(const float* dscores, const void* x, float* dwg
   if (D > 2048) return md_set_error(MD_ERR_UNSUPPORTED, "md_moe_gate_wgrad: D > 2048");
   const long long slabs = (rows + kWgSlab - 1) / kWgSlab;
   const unsigned grid = (unsigned)(slabs < 148 * 2 ? slabs : 148 * 2);
+  float* ws = nullptr;
+  if (det_enabled()) {
+    ws = det_workspace(static_cast<size_t>(grid) * E * D * sizeof(float));
+    if (ws == nullptr) return md_set_error(MD_ERR_INVALID, "md_moe_gate_wgrad: deterministic workspace too small");
+  }
 #define WGRAD(ME, NJ) \
-  MD_WITH_ACT(prec, moe_gate_wgrad_kernel<ME, NJ, AT><<<grid, 256, 0, ST(stream)>>>(dscores, CAP(AT, x), dwg, rows, (int)D, (int)E))
+  MD_WITH_ACT(prec, moe_gate_wgrad_kernel<ME, NJ, AT><<<grid, 256, 0, ST(stream)>>>(dscores, CAP(AT, x), dwg, rows, (int)D, (int)E, ws))
   if (E <= 8) {
     if (D <= 512) WGRAD(8, 1);
     else if (D <= 1024) WGRAD(8, 2);
@@ -563,5 +573,6 @@ extern "C" int md_moe_gate_wgrad(const float* dscores, const void* x, float* dwg
     else WGRAD(16, 4);
   }
 #undef WGRAD
-  return check_launch("md_moe_gate_wgrad");
+  if (int rc = check_launch("md_moe_gate_wgrad")) return rc;
+  return ws ? det_reduce(ws, dwg, grid, E * D, 1, ST(stream)) : 0;
 }

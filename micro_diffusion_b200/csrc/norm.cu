@@ -143,7 +143,7 @@ ln_bwd_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const int32
               const float* __restrict__ gamma, const float* __restrict__ scale, long long ldmod, long long T,
               const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ dx, int dx_mode,
               float* __restrict__ dgamma, float* __restrict__ dshift, float* __restrict__ dscale, long long rows,
-              int D, int rpb) {
+              int D, int rpb, float* __restrict__ dgamma_ws) {
   extern __shared__ float red[];  // [4][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long smp = blockIdx.y;
@@ -241,7 +241,11 @@ ln_bwd_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const int32
         if (dshift) atomicAdd(dshift + smp * ldmod + c, v);
       } else {
         if (dscale) atomicAdd(dscale + smp * ldmod + c, v * (gamma ? gamma[c] : 1.f));
-        if (dgamma) atomicAdd(dgamma + c, v * (sc ? 1.f + sc[c] : 1.f));
+        if (dgamma) {
+          // deterministic mode (one block per sample): the per-sample term goes to the workspace, summed over samples later
+          if (dgamma_ws) dgamma_ws[smp * D + c] = v * (sc ? 1.f + sc[c] : 1.f);
+          else atomicAdd(dgamma + c, v * (sc ? 1.f + sc[c] : 1.f));
+        }
       }
     }
   }
@@ -263,7 +267,7 @@ ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const 
                    const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ dx, int dx_mode,
                    float* __restrict__ dgamma, float* __restrict__ dshift, float* __restrict__ dscale,
                    const AT* __restrict__ y_next, const float* __restrict__ gate_next, float* __restrict__ dgate_next,
-                   AT* __restrict__ dy_next, int rpb) {
+                   AT* __restrict__ dy_next, int rpb, float* __restrict__ dgamma_ws) {
   constexpr int D = 128 * TEAM * V;
   constexpr int kThreads = 32 * TEAM * NT;  // NT teams per block
   extern __shared__ float sm[];
@@ -406,7 +410,10 @@ ln_bwd_team_kernel(const AT* __restrict__ dy, const void* __restrict__ x, const 
         if (dshift) atomicAdd(dshift + smp * ldmod + c, v);
       } else if (pass == 1) {
         if (dscale) atomicAdd(dscale + smp * ldmod + c, v * (gamma ? gamma[c] : 1.f));
-        if (dgamma) atomicAdd(dgamma + c, v * (sc ? 1.f + sc[c] : 1.f));
+        if (dgamma) {
+          if (dgamma_ws) dgamma_ws[smp * D + c] = v * (sc ? 1.f + sc[c] : 1.f);   // deterministic mode, see ln_bwd_kernel
+          else atomicAdd(dgamma + c, v * (sc ? 1.f + sc[c] : 1.f));
+        }
       } else {
         atomicAdd(dgate_next + smp * ldmod + c, v);
       }
@@ -660,9 +667,21 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
     return md_set_error(MD_ERR_INVALID, "md_ln_bwd: the fused next-branch tail needs dx with dx_mode 0");
   if ((y_next != nullptr || gate_next != nullptr || dgate_next != nullptr) && dy_next == nullptr)
     return md_set_error(MD_ERR_INVALID, "md_ln_bwd: y_next / gate_next / dgate_next come with dy_next");
-  const int rpb = rows_per_block(T, rows / T);
+  // deterministic mode: one block per sample (a single contributor to every per-sample atomic) and the cross-sample sum
+  // of d gamma through the workspace in a fixed order
+  const bool det = det_enabled();
+  const int rpb = det ? static_cast<int>(T) : rows_per_block(T, rows / T);
   dim3 grid(static_cast<unsigned>((T + rpb - 1) / rpb), static_cast<unsigned>(rows / T));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* gws = nullptr;
+  if (det && dgamma != nullptr) {
+    gws = det_workspace(static_cast<size_t>(rows / T) * D * sizeof(float));
+    if (gws == nullptr) return md_set_error(MD_ERR_INVALID, "md_ln_bwd: deterministic workspace too small");
+  }
+  auto finish = [&]() -> int {
+    if (int rc = check_launch("md_ln_bwd")) return rc;
+    return gws ? det_reduce(gws, dgamma, rows / T, D, 1, st) : 0;
+  };
   if (D == 1024 || D == 768 || D == 512) {
     // width -> (float4 groups per lane, warps per row, rows in flight per block, blocks per SM, one-row-ahead loads)
 #define LN_BWD_TEAM(V, TEAM, NT, MINB, PF)                                                                              \
@@ -671,17 +690,17 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
     if (x_bf16)                                                                                                        \
       ln_bwd_team_kernel<V, TEAM, NT, MINB, PF, true, AT><<<grid, 32 * TEAM * NT, smem, st>>>(                          \
           CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T, mean, rstd, dx, dx_mode, dgamma, dshift, dscale,           \
-          CAP(AT, y_next), gate_next, dgate_next, AP(AT, dy_next), rpb);                                               \
+          CAP(AT, y_next), gate_next, dgate_next, AP(AT, dy_next), rpb, gws);                                          \
     else                                                                                                               \
       ln_bwd_team_kernel<V, TEAM, NT, MINB, PF, false, AT><<<grid, 32 * TEAM * NT, smem, st>>>(                         \
           CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T, mean, rstd, dx, dx_mode, dgamma, dshift, dscale,           \
-          CAP(AT, y_next), gate_next, dgate_next, AP(AT, dy_next), rpb);                                               \
+          CAP(AT, y_next), gate_next, dgate_next, AP(AT, dy_next), rpb, gws);                                          \
   } while (0))
     if (D == 1024) LN_BWD_TEAM(2, 4, 2, 2, true);
     else if (D == 768) LN_BWD_TEAM(2, 3, 2, 2, true);
     else LN_BWD_TEAM(2, 2, 4, 2, true);
 #undef LN_BWD_TEAM
-    return check_launch("md_ln_bwd");
+    return finish();
   }
   const size_t smem = 4 * D * sizeof(float);
 #define LN_BWD(VEC, EXACT)                                                                                             \
@@ -689,16 +708,16 @@ extern "C" int md_ln_bwd(const void* dy, const void* x, int x_bf16, const int32_
     if (x_bf16)                                                                                                        \
       ln_bwd_kernel<VEC, EXACT, true, AT><<<grid, 128, smem, st>>>(CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T,  \
                                                                    mean, rstd, dx, dx_mode, dgamma, dshift, dscale,   \
-                                                                   rows, static_cast<int>(D), rpb);                   \
+                                                                   rows, static_cast<int>(D), rpb, gws);              \
     else                                                                                                               \
       ln_bwd_kernel<VEC, EXACT, false, AT><<<grid, 128, smem, st>>>(CAP(AT, dy), x, src_rows, gamma, scale, ldmod, T, \
                                                                     mean, rstd, dx, dx_mode, dgamma, dshift, dscale,  \
-                                                                    rows, static_cast<int>(D), rpb);                  \
+                                                                    rows, static_cast<int>(D), rpb, gws);             \
   } while (0))
   if (D <= 1024) LN_BWD(8, false);
   else LN_BWD(16, false);
 #undef LN_BWD
-  if (int rc = check_launch("md_ln_bwd")) return rc;
+  if (int rc = finish()) return rc;
   // other widths: the next branch's gate backward runs as its own pass over the updated dx
   if (dy_next != nullptr)
     return md_gate_bwd(reinterpret_cast<const float*>(dx), y_next, gate_next, ldmod, T, dy_next, dgate_next, rows, D, prec,
@@ -742,7 +761,7 @@ extern "C" int md_gate_bwd(const float* dres, const void* y, const float* gate, 
   if (rows == 0) return 0;
   if (!dres || !dy) return md_set_error(MD_ERR_INVALID, "md_gate_bwd: null pointer");
   if (rows % T != 0) return md_set_error(MD_ERR_INVALID, "md_gate_bwd: rows must be a multiple of T");
-  const int rpb = rows_per_block(T, rows / T);
+  const int rpb = det_enabled() ? static_cast<int>(T) : rows_per_block(T, rows / T);  // deterministic: one block per sample
   dim3 grid(static_cast<unsigned>((T + rpb - 1) / rpb), static_cast<unsigned>(rows / T));
   const size_t smem = 4 * D * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -73,6 +73,7 @@ _PROTOS = {
     "md_colsum": [_P, _I, _I64, _P, _I64, _I64, _P],
     "md_cast_transpose": [_P, _P, _P, _I64, _I64, _I64, _I64, _I, _P],
     "md_cast_transpose_multi": [_P, _P, _P, _P, _I64, _I64, _I, _P],
+    "md_set_deterministic": [_P, _I64],
     "md_sumsq": [_P, _P, _I64, _P],
     "md_adamw": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _I64, _P, _I64, _P],
 }
@@ -118,6 +119,9 @@ class CudaOps:
             fn.restype = C.c_int
             fn.argtypes = argtypes
         self.launches = 0
+        self._det_ws = None
+        if os.environ.get("MD_DETERMINISTIC", "0") == "1":
+            self.set_deterministic(True)
         self.gemm_flops = 0      # algorithmic FLOPs of every md_gemm_bf16 launched (2*M*N*K*batch)
         # None: md_attn_fwd / md_attn_bwd choose between the tcgen05 and the mma.sync kernels per shape (MD_ATTN_TC in the
         # environment forces one); True / False: call that path directly where its envelope allows (tests, A/B tools)
@@ -143,6 +147,20 @@ class CudaOps:
         self.launches += 1
         if rc != 0:
             raise MicroditLibraryError(f"{name} failed ({rc}): {self.lib.md_last_error().decode()}")
+
+    def set_deterministic(self, on: bool = True, workspace_bytes: int = 1 << 30):
+        """Deterministic mode of the library (include/microdit_b200.h: md_set_deterministic): every cross-block floating-point
+        atomic accumulation goes through per-block partials in a workspace and a fixed-order reduction, so identical inputs
+        give bit-identical gradients and weights (MD_DETERMINISTIC=1 turns it on at construction).  Process-wide switch."""
+        if on:
+            if self._det_ws is None or self._det_ws.numel() < workspace_bytes:
+                self._det_ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
+            rc = self.lib.md_set_deterministic(self._det_ws.data_ptr(), self._det_ws.numel())
+        else:
+            rc = self.lib.md_set_deterministic(None, 0)
+            self._det_ws = None
+        if rc != 0:
+            raise MicroditLibraryError(f"md_set_deterministic failed ({rc}): {self.lib.md_last_error().decode()}")
 
     def profile_summary(self):
         """{op: (launches, total_ms, flops)} from the recorded events (call after torch.cuda.synchronize())."""

@@ -539,6 +539,9 @@ class EmuOps:
         if wbt is not None:
             wbt.copy_(w.transpose(-1, -2))
 
+    def set_deterministic(self, on=True, workspace_bytes=0):
+        pass  # the CPU contracts are deterministic by construction
+
     def cast_transpose_multi(self, flat, wb, wbt, desc, total_tiles):
         self.launches += 1
         for off, rows, cols, half, need_t, _, _, _ in desc.tolist():
