@@ -236,9 +236,13 @@ def test_deterministic_mode_reproduces_gradients_bit_for_bit(model):
     l2, g2, w2 = one_step(True)
     assert l1 == l2 and torch.equal(g1, g2) and torch.equal(w1, w2)
     l0, g0, w0 = one_step(False)
+    l0b, g0b, _ = one_step(False)
     assert abs(l0 - l1) / abs(l1) < 1e-6
     rel = float((g0 - g1).norm() / g1.norm())
-    same = torch.equal(g0, one_step(False)[1])
-    print(f"\n[deterministic mode, {model}] fast-path vs deterministic gradient rel-L2 {rel:.2e}; "
-          f"fast path run-to-run bit-identical: {same}")
-    assert rel < 1e-5
+    noise = float((g0 - g0b).norm() / g0.norm())   # the fast path's own run-to-run spread (atomic order + cancellation)
+    print(f"\n[deterministic mode, {model}] deterministic vs fast-path gradient rel-L2 {rel:.2e}; fast path run-to-run "
+          f"{noise:.2e} (bit-identical: {torch.equal(g0, g0b)})")
+    # the two modes compute the same sums in a different order: they may differ by what two fast-path runs differ by
+    # (on MicroDiT_XL_2 the caption-stem gradients, sums of 34 cross-attention contributions that largely cancel, move by
+    # ~3e-3 from run to run on the fast path)
+    assert rel < 3 * noise + 1e-6
