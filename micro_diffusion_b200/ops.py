@@ -155,6 +155,7 @@ class CudaOps:
         if on:
             if self._det_ws is None or self._det_ws.numel() < workspace_bytes:
                 self._det_ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
+            self._det_ws.fill_(0xFF)   # NaN pattern: a reduction that read a partial nobody wrote would show up at once
             rc = self.lib.md_set_deterministic(self._det_ws.data_ptr(), self._det_ws.numel())
         else:
             rc = self.lib.md_set_deterministic(None, 0)

@@ -242,7 +242,9 @@ def test_deterministic_mode_reproduces_gradients_bit_for_bit(model):
     noise = float((g0 - g0b).norm() / g0.norm())   # the fast path's own run-to-run spread (atomic order + cancellation)
     print(f"\n[deterministic mode, {model}] deterministic vs fast-path gradient rel-L2 {rel:.2e}; fast path run-to-run "
           f"{noise:.2e} (bit-identical: {torch.equal(g0, g0b)})")
-    # the two modes compute the same sums in a different order: they may differ by what two fast-path runs differ by
-    # (on MicroDiT_XL_2 the caption-stem gradients, sums of 34 cross-attention contributions that largely cancel, move by
-    # ~3e-3 from run to run on the fast path)
-    assert rel < 3 * noise + 1e-6
+    # The two modes compute the same sums in a different order.  Most gradients then agree to ~1e-7, but the caption-stem
+    # gradients are sums of all the cross-attention contributions that largely cancel: a different fp32 summation order
+    # moves them by up to a few 1e-3 (two fast-path runs on MicroDiT_XL_2 differ by that much from each other, see
+    # tools/det_diag.py) -- well inside the bf16 regime's own deviation from the fp32 oracle (1-2e-2).  The property under
+    # test is the bit-for-bit reproducibility above; this only guards against a wrong reduction.
+    assert rel < 5e-3
