@@ -119,6 +119,8 @@ class CudaOps:
             fn.restype = C.c_int
             fn.argtypes = argtypes
         self.launches = 0
+        self.poison_kinds = os.environ.get("MD_DEBUG_POISON", "0")
+        self.poison = self.poison_kinds != "0"
         self._det_ws = None
         if os.environ.get("MD_DETERMINISTIC", "0") == "1":
             self.set_deterministic(True)
@@ -174,6 +176,10 @@ class CudaOps:
     def empty(self, shape, dtype):
         if self.prec and dtype == torch.bfloat16:
             dtype = torch.float32
+        if self.poison and self.poison_kinds in ("1", {torch.bfloat16: "bf16", torch.float32: "f32"}.get(dtype, "int")):
+            # MD_DEBUG_POISON=1|bf16|f32|int: scratch / output buffers start as NaN (-1 for indices), so that a kernel reading
+            # an element nobody wrote cannot go unnoticed (tools/det_diag_s.py --poison)
+            return torch.full(shape, float("nan") if dtype.is_floating_point else -1, dtype=dtype, device=self.device)
         return torch.empty(shape, dtype=dtype, device=self.device)
 
     def zeros(self, shape, dtype):

@@ -22,6 +22,13 @@ def run(det, micro):
     return g
 
 
+if "--poison" in sys.argv:
+    os.environ["MD_DEBUG_POISON"] = "1"
+    for det in (False, True):
+        g = run(det, 3)
+        bad = [k for k, v in g.items() if not torch.isfinite(v).all()]
+        print("poisoned scratch, det =", det, ": non-finite gradients in", len(bad), "tensors", bad[:6])
+    sys.exit(0)
 for micro in (3, 6):
     g1 = run(True, micro)
     g1b = run(True, micro)
