@@ -5,7 +5,7 @@
 Runs `cuobjdump -sass` (no GPU needed) and counts, per kernel, the mnemonics that prove the Blackwell path
 (/opt/skills/guides/B200_PROFILING.md): UTCHMMA (tcgen05.mma), UTMALDG / UTMASTG (TMA load / store), LDTM / STTM (tcgen05.ld / st),
 UTCBAR (tcgen05.commit), SYNCS (mbarrier), plus HMMA (mma.sync), LDGSTS (cp.async), MUFU, RED/ATOM, and local-memory
-traffic (LDL / STL: spills or runtime-indexed arrays).
+traffic (LDL / STL: spills or runtime-indexed arrays) and the 256-bit global accesses (STG.256 / LDG.256).
 """
 import collections
 import os
@@ -15,7 +15,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "micro_diffusion_b200", "libmicrodit_b200.so")
-FAMILIES = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "MUFU", "RED", "ATOM", "LDL", "STL"]
+FAMILIES = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "MUFU", "RED", "ATOM", "LDL", "STL",
+            "STG.256", "LDG.256"]
 
 
 def demangle(names):
@@ -39,6 +40,8 @@ def main():
         if m:
             op = m.group(1)
             counts[cur]["_total"] += 1
+            if ".256" in line and ("STG." in line or "LDG." in line):   # 256-bit global accesses (sm_100)
+                counts[cur]["STG.256" if "STG." in line else "LDG.256"] += 1
             for f in FAMILIES:
                 if op.startswith(f):
                     counts[cur][f] += 1
