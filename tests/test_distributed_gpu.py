@@ -120,4 +120,4 @@ def test_two_gpu_step_matches_one_gpu_step_over_the_concatenated_batch(tmp_path,
     assert rel < 5e-3 and per[len(per) // 2] < 1e-5 and per[-1] < 2e-2
     assert torch.equal(got[0]["flat"], got[1]["flat"]) and torch.equal(got[0]["m"], got[1]["m"])
     assert torch.allclose(got[0]["flat"], flat, rtol=1e-4, atol=1e-6)
-    assert float((got[0]["m"] - m).norm() / m.norm()) < 1e-4
+    assert float((got[0]["m"] - m).norm() / m.norm()) < 5e-3   # the first moment is the (clipped) gradient: same bound
