@@ -157,3 +157,34 @@ def test_gemm_args_struct_layout_matches_the_header(tmp_path):
     for n in names:
         assert int(out[n]) == getattr(GemmArgs, n).offset, n
     assert int(out["sizeof"]) == ctypes.sizeof(GemmArgs)
+
+
+def test_cast_table_covers_every_operand_copy():
+    """ParamStore._cast_table (one md_cast_transpose_multi launch per exchange range) must produce exactly the copies the
+    per-matrix entry point produces, including the 32-row interleave of the fused-SwiGLU stacks and the expert banks."""
+    import torch
+    from oracle.emu_ops import EmuOps
+    from tests import parity_common as pc
+    ld = pc.build_product("S", device="cpu", ops_factory=lambda d: EmuOps(d, exact=False))
+    st = ld.dit.store
+    ops = ld.dit.engine.ops
+    st.flat.copy_(torch.randn(st.flat.shape, generator=torch.Generator().manual_seed(3)))
+    assert st.interleave, "the S configuration has SwiGLU stacks with f % 32 == 0"
+    st.refresh_copies(ops, None, force=True)
+    wb, wbt = st.wb.clone(), st.wbt.clone()
+    ref_b, ref_t = torch.zeros_like(wb), torch.zeros_like(wbt)
+    covered = 0
+    for g in st.layout.groups.values():
+        src = st.flat[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
+        b = ref_b[g.offset: g.offset + g.numel].view(g.batch, g.rows, g.cols)
+        t = ref_t[g.offset: g.offset + g.numel].view(g.batch, g.cols, g.rows) if g.need_t else None
+        ops.cast_transpose(src, b, t, interleave_half=st.interleave.get(g.name, 0))
+        covered += g.numel
+        assert torch.equal(wb[g.offset: g.offset + g.numel], ref_b[g.offset: g.offset + g.numel]), g.name
+        if g.need_t:
+            assert torch.equal(wbt[g.offset: g.offset + g.numel], ref_t[g.offset: g.offset + g.numel]), g.name
+    for part in ("front", "back"):
+        desc, tiles = st._cast_table(part)
+        d = desc.tolist()
+        assert all(d[i][5] < d[i + 1][5] for i in range(len(d) - 1)) and tiles == d[-1][5] + d[-1][6] * ((d[-1][1] + 63) // 64)
+    assert covered > 0
