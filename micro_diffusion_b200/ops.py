@@ -87,6 +87,9 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_DET_WORKSPACE = {}  # the deterministic-mode scratch registered with the library (md_set_deterministic), kept alive here
+
+
 def _mod(t):
     """(pointer, row pitch) of a per-sample modulation view [samples, D] (a column slice of the adaLN buffer)."""
     if t is None:
@@ -155,12 +158,18 @@ class CudaOps:
         atomic accumulation goes through per-block partials in a workspace and a fixed-order reduction, so identical inputs
         give bit-identical gradients and weights (MD_DETERMINISTIC=1 turns it on at construction).  Process-wide switch."""
         if on:
-            if self._det_ws is None or self._det_ws.numel() < workspace_bytes:
-                self._det_ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
-            self._det_ws.fill_(0xFF)   # NaN pattern: a reduction that read a partial nobody wrote would show up at once
-            rc = self.lib.md_set_deterministic(self._det_ws.data_ptr(), self._det_ws.numel())
+            ws = _DET_WORKSPACE.get("ws")
+            if ws is None or ws.numel() < workspace_bytes or ws.device != self.device:
+                ws = torch.empty(workspace_bytes, dtype=torch.uint8, device=self.device)
+            ws.fill_(0xFF)   # NaN pattern: a reduction that read a partial nobody wrote would show up at once
+            rc = self.lib.md_set_deterministic(ws.data_ptr(), ws.numel())
+            # the library keeps the pointer (process-wide switch): the buffer must outlive this CudaOps instance
+            _DET_WORKSPACE["ws"] = ws
+            self._det_ws = ws
         else:
             rc = self.lib.md_set_deterministic(None, 0)
+            torch.cuda.synchronize(self.device)   # no launch may still be writing partials when the buffer is released
+            _DET_WORKSPACE.pop("ws", None)
             self._det_ws = None
         if rc != 0:
             raise MicroditLibraryError(f"md_set_deterministic failed ({rc}): {self.lib.md_last_error().decode()}")
