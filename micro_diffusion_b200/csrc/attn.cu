@@ -2,11 +2,11 @@
 // head_dim 32 or 64: F.scaled_dot_product_attention at utils.py:188-193 (self) and utils.py:127-132
 // (cross, 77 caption tokens) and its autograd backward.
 //
-// Round-1 implementation: flash-style tiles of 64 queries x 64 keys per CTA (4 warps x 16 rows),
-// bf16 mma.sync m16n8k16 with fp32 accumulation and online softmax in the log2 domain; backward is
-// the deterministic two-kernel split (dK/dV per key tile, dQ per query tile; no atomics).
-// SDPA is 2.7 % of the step's FLOPs at the benchmark configuration, so the
-// tcgen05 rewrite of this kernel ranks after the GEMM work; DESIGN.md tracks it.
+// This file: the mma.sync kernels -- flash-style tiles of 64 queries x 64 keys per CTA (4 warps x 16 rows), bf16
+// mma.sync m16n8k16 with fp32 accumulation and online softmax in the log2 domain; backward is the deterministic
+// two-kernel split (dK/dV per key tile, dQ per query tile; no atomics) plus fused few-key variants -- and the
+// dispatch of md_attn_fwd / md_attn_bwd between them and the tcgen05 kernels of attn_tc.cu (head_dim 64: every forward
+// with Tk <= 256 and every backward with more than 128 keys go there; DESIGN.md section 5.2 has the measurements).
 #include <stdlib.h>
 
 #include "common.cuh"

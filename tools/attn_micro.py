@@ -1,6 +1,5 @@
-"""Attention micro-benchmark at the C2 / C3 shapes: production mma.sync kernels vs the experimental tcgen05 kernels
-(MD_ATTN_TC path), forward and backward, same operands.  First thing to run in round 2 after
-`MD_ATTN_TC=1 pytest tests/test_attn_tc_gpu.py` is green:
+"""Attention micro-benchmark at the C2 / C3 shapes: the mma.sync kernels vs the tcgen05 kernels (called directly, not
+through the per-shape dispatch of md_attn_fwd / md_attn_bwd), forward and backward, same operands:
 
     python tools/attn_micro.py            # both paths
     python tools/attn_micro.py --no-tc    # production kernels only
