@@ -899,11 +899,11 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
     rc = make_map(&tmB, a->B, a->N, a->K, a->batch, a->ldb, a->strideB, kBlockK);
     if (rc) return rc;
   }
-  // TMA store for the plain bf16 epilogue when the output view is TMA-addressable (16-byte aligned base and pitches)
+  // store mode of the bf16-output epilogues (MD_GEMM_TMA_STORE; the math tails additionally MD_GEMM_MATH_STORE)
   static int tma_store_env = -1;
   if (tma_store_env == -1) {
     const char* e = getenv("MD_GEMM_TMA_STORE");
-    tma_store_env = e ? atoi(e) : 3;  // 3 = 256-bit register-direct stores (default), 1 = TMA store, 2 = staged st.global, 0 = 16-byte direct
+    tma_store_env = e ? atoi(e) : 3;  // 3 = 256-bit register-direct stores (default), 1 = TMA store, 0 = 16-byte direct
   }
   static int debug_env = -1;
   if (debug_env == -1) {
@@ -918,7 +918,7 @@ static int launch(const md_gemm_args* a, GemmDev dev, int sm_count, cudaStream_t
                            (a->batch == 1 || (a->strideC % 8) == 0) &&
                            (!dual || (reinterpret_cast<uintptr_t>(a->C2) & 15) == 0) &&
                            (a->epilogue != EPI_ACT_GRAD || (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0);
-  // staged + coalesced st.global (tma_store = 2): always for the math tails, MD_GEMM_TMA_STORE=2 forces it for the plain store
+  // staged + coalesced st.global (tma_store = 2): the math tails' fallback when the view is only 16-byte addressable
   const bool math = a->epilogue == EPI_ACT_DUAL || a->epilogue == EPI_ACT_GRAD;
   // 32-byte pieces for the register-direct 256-bit path
   const bool aligned32 = aligned_out && (reinterpret_cast<uintptr_t>(a->C) & 31) == 0 && (a->ldc % 16) == 0 &&
