@@ -123,3 +123,23 @@ def test_prompt_cache_goes_stale_with_the_weights():
         next(ld.dit.parameters()).add_(0.1)
     with pytest.raises(RuntimeError):
         ld.dit.engine.denoise(x, sg, cap, edm=ld._edm_scalars(), prompt=pcache)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_fused_and_unfused_sequencing_agree(monkeypatch, exact):
+    """The A/B switches (MD_FUSE_ACT / MD_FUSE_LN / MD_FUSE_SWIGLU) only re-sequence the same arithmetic.  exact=True (fp32
+    contracts: GELU / GELU' epilogues and the gate backward inside the LayerNorm backward) must agree to fp32 rounding;
+    exact=False adds the bf16 rounding points and the interleaved w1|w2 stacks of the fused SwiGLU, where the fused form
+    keeps d h in fp32 instead of bf16: agreement within the bf16 regime."""
+    def run():
+        loss, grads, den, ld = pc.product_run("S", ops_factory=lambda d: EmuOps(d, exact=exact))
+        return loss, grads, ld
+    loss1, g1, ld1 = run()
+    assert ld1.dit.engine.fuse_act and ld1.dit.engine.fuse_ln and bool(ld1.dit.store.interleave) == (not exact)
+    for k in ("MD_FUSE_ACT", "MD_FUSE_LN", "MD_FUSE_SWIGLU"):
+        monkeypatch.setenv(k, "0")
+    loss0, g0, ld0 = run()
+    assert not ld0.dit.engine.fuse_act and not ld0.dit.engine.fuse_ln and not ld0.dit.store.interleave
+    assert abs(loss1 - loss0) / abs(loss0) < (1e-6 if exact else 1e-3)
+    errs = sorted(pc.rel_l2(g1[k], g0[k]) for k in g0)
+    assert errs[-1] < (1e-5 if exact else 5e-2) and errs[len(errs) // 2] < (1e-5 if exact else 1e-2), errs[-3:]
